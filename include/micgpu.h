@@ -1,0 +1,120 @@
+/*
+ * micgpu.h -- C ABI of libmicgpu.so, the B200 (sm_100a) codec path for MIC
+ * (pappuks/medical-image-codec).  Plain pointers and sizes only; this is what a
+ * cgo / ctypes binding links against.
+ *
+ * Conventions (same as the reference's C twin, ojph/mic_decompress_c.h:24-49,
+ * ojph/mic_parallel.h:49-55): 0 = success, negative = error class; the caller
+ * owns every buffer; all host<->device copies complete inside the call, so Go
+ * may pass pointers into Go-managed memory; calls are thread-safe (one
+ * internal lock per device context).
+ *
+ * There is NO CPU fallback: every entry point fails with MICGPU_E_CUDA when no
+ * CUDA device is usable.
+ */
+#ifndef MICGPU_H
+#define MICGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error classes -------------------------------------------------------- */
+#define MICGPU_OK 0
+#define MICGPU_E_HEADER (-1)      /* bad magic / args / truncated container (C twin -1) */
+#define MICGPU_E_NCOUNT (-2)      /* corrupt ncount header (C twin -2) */
+#define MICGPU_E_ALLOC (-3)
+#define MICGPU_E_DTABLE (-4)      /* corrupt decode table (C twin -4) */
+#define MICGPU_E_BITSTREAM (-6)   /* bit reader over-read (C twin -6) */
+#define MICGPU_E_RLE (-8)         /* RLE stream malformed / too short */
+#define MICGPU_E_SIZE (-9)        /* output capacity / geometry mismatch */
+#define MICGPU_E_UNSUPPORTED (-10)
+#define MICGPU_E_CUDA (-20)       /* CUDA runtime failure or no device */
+
+/* unit kinds for micgpu_decoder_add_unit */
+#define MICGPU_KIND_SPATIAL 0     /* DecompressSingleFrame (multiframecompress.go:97) */
+#define MICGPU_KIND_RLE 1         /* decompressResidualFrame (multiframecompress.go:165) */
+
+/* ---- library ---------------------------------------------------------------- */
+int micgpu_device_count(void);
+/* Text of the last error raised on the calling thread. */
+const char *micgpu_last_error(void);
+/* Pinned host memory helpers (optional; pageable buffers work, slower). */
+void *micgpu_host_alloc(size_t bytes);
+void micgpu_host_free(void *p);
+/* Release the per-device default contexts used by the one-shot calls. */
+void micgpu_shutdown(void);
+
+/* ---- batch decoder: plan once from HOST copies of the streams, run many ---- */
+typedef struct micgpu_decoder micgpu_decoder;
+
+micgpu_decoder *micgpu_decoder_create(int device);
+void micgpu_decoder_destroy(micgpu_decoder *d);
+/* Forget the current plan. */
+int micgpu_decoder_begin(micgpu_decoder *d);
+/* Add one FSE frame.  `frame` is a host pointer (only its first bytes are read
+ * for planning); comp_off is where the frame will sit inside the compressed
+ * device buffer passed to micgpu_decoder_run_device, out_off the first output
+ * element (uint16) it decodes to.  SPATIAL: width x height pixels.
+ * RLE: width*height is the output capacity in elements.  Returns the unit index. */
+int micgpu_decoder_add_unit(micgpu_decoder *d, const uint8_t *frame, size_t frame_len, uint64_t comp_off, int kind,
+                            uint32_t width, uint32_t height, uint64_t out_off);
+/* Add every strip of a PICS container (parallelstrips.go:270-330).  The whole
+ * blob is assumed to be copied at comp_off; pixels land at out_off. */
+int micgpu_decoder_add_pics(micgpu_decoder *d, const uint8_t *pics, size_t len, uint64_t comp_off, uint64_t out_off,
+                            int *width, int *height);
+/* Add every frame of an independent-mode MIC2 container (multiframecompress.go:227-262). */
+int micgpu_decoder_add_mic2(micgpu_decoder *d, const uint8_t *mic2, size_t len, uint64_t comp_off, uint64_t out_off,
+                            int *width, int *height, int *frames, int *temporal);
+/* Size scratch for the plan.  Must be called after the last add_*. */
+int micgpu_decoder_commit(micgpu_decoder *d);
+int micgpu_decoder_unit_count(const micgpu_decoder *d);
+/* Decode the planned batch.  d_comp: device buffer holding the streams
+ * (64-byte aligned, readable for comp_bytes + 128 bytes); d_out: device buffer
+ * of out_elems uint16.  cuda_stream: a cudaStream_t (NULL = default stream).
+ * Asynchronous with respect to the host. */
+int micgpu_decoder_run_device(micgpu_decoder *d, const void *d_comp, size_t comp_bytes, void *d_out, size_t out_elems,
+                              void *cuda_stream);
+/* Wait for the last run and fetch per-unit status (0 = ok, else MICGPU_E_*).
+ * Returns the first non-zero status, or 0. */
+int micgpu_decoder_unit_status(micgpu_decoder *d, int *status, int n, void *cuda_stream);
+/* Kernels launched by the last run_device call. */
+int micgpu_decoder_last_launches(const micgpu_decoder *d);
+/* Convenience: copy `comp` (host) to the device, run, copy `out_elems` uint16 back. */
+int micgpu_decoder_run_host(micgpu_decoder *d, const uint8_t *comp, size_t comp_bytes, uint16_t *out, size_t out_elems);
+
+/* ---- container-level one-shot calls (host buffers in, host buffers out) ----- */
+/* DecompressParallelStrips (parallelstrips.go:270).  pixels_out holds cap_px
+ * uint16; *width/*height are set from the header. */
+int micgpu_pics_decompress(const uint8_t *pics, size_t len, uint16_t *pixels_out, size_t cap_px, int *width, int *height);
+/* n independent PICS images in one launch sequence; outs[i] holds caps[i] uint16.
+ * status[i] (optional) receives the per-image result. */
+int micgpu_pics_decompress_batch(int n, const uint8_t *const *blobs, const size_t *lens, uint16_t *const *outs,
+                                 const size_t *caps, int *status);
+/* DecompressSingleFrame (multiframecompress.go:97): any of the 1/2/4/8-state or rANS-8 streams. */
+int micgpu_decompress_single_frame(const uint8_t *frame, size_t len, uint16_t *pixels_out, int width, int height);
+/* DecompressMultiFrame / DecompressFrame (multiframecompress.go:227,266). */
+int micgpu_mic2_decompress(const uint8_t *mic2, size_t len, uint16_t *frames_out, size_t cap_px, int *width, int *height,
+                           int *frames, int *temporal);
+int micgpu_mic2_decompress_frame(const uint8_t *mic2, size_t len, int frame_idx, uint16_t *pixels_out, size_t cap_px,
+                                 int *width, int *height);
+
+/* ---- drop-in symbols of the reference C twin (same signatures) -------------- */
+/* ojph/mic_decompress_c.h:24-49 */
+int mic_decompress_two_state(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);
+int mic_decompress_two_state_simd(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);
+int mic_decompress_four_state(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);
+int mic_decompress_four_state_simd(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);
+int mic_decompress_eight_state(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);
+int mic_decompress_eight_state_simd(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);
+/* ojph/mic_parallel.h:49-55 (max_threads is accepted and ignored: one batched launch) */
+int mic_decompress_parallel(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height, int max_threads);
+int mic_decompress_parallel_scalar(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height, int max_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICGPU_H */

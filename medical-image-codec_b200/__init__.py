@@ -1,0 +1,19 @@
+"""micgpu -- B200-native (sm_100a) codec path for MIC (pappuks/medical-image-codec).
+
+The product is libmicgpu.so (hand-written CUDA kernels behind a C ABI, see
+include/micgpu.h).  This package is the thin host-side mirror of the
+reference's Go API for that path, used by the tests and bench.py; it never
+touches oracle/ and has no CPU fallback: importing `api` fails loudly when the
+native library is missing.
+"""
+from . import api  # noqa: F401
+from .api import (  # noqa: F401
+    Decoder,
+    DecompressFrame,
+    DecompressMultiFrame,
+    DecompressParallelStrips,
+    DecompressParallelStripsBatch,
+    DecompressSingleFrame,
+    MicGpuError,
+    lib,
+)

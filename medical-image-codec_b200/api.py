@@ -1,0 +1,231 @@
+"""ctypes binding of libmicgpu.so, named after the reference's Go API.
+
+Go API mirrored here (reference file:line):
+  DecompressParallelStrips   parallelstrips.go:270
+  DecompressSingleFrame      multiframecompress.go:97
+  DecompressMultiFrame       multiframecompress.go:227
+  DecompressFrame            multiframecompress.go:266
+Errors surface as MicGpuError carrying the C ABI's negative error class, the
+way ojph/mic_c.go:36-38 turns rc != 0 into a Go error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmicgpu.so")
+
+E_HEADER, E_NCOUNT, E_ALLOC, E_DTABLE, E_BITSTREAM, E_RLE, E_SIZE, E_UNSUPPORTED, E_CUDA = -1, -2, -3, -4, -6, -8, -9, -10, -20
+KIND_SPATIAL, KIND_RLE = 0, 1
+
+
+class MicGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"micgpu rc={code}: {msg}")
+        self.code = code
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(micgpu has no CPU fallback)"
+        )
+    return C.CDLL(_LIB_PATH)
+
+
+lib = _load()
+
+_u8p = C.POINTER(C.c_uint8)
+_u16p = C.POINTER(C.c_uint16)
+_ip = C.POINTER(C.c_int)
+
+lib.micgpu_last_error.restype = C.c_char_p
+lib.micgpu_device_count.restype = C.c_int
+lib.micgpu_host_alloc.restype = C.c_void_p
+lib.micgpu_host_alloc.argtypes = [C.c_size_t]
+lib.micgpu_host_free.argtypes = [C.c_void_p]
+lib.micgpu_decoder_create.restype = C.c_void_p
+lib.micgpu_decoder_create.argtypes = [C.c_int]
+lib.micgpu_decoder_destroy.argtypes = [C.c_void_p]
+lib.micgpu_decoder_begin.argtypes = [C.c_void_p]
+lib.micgpu_decoder_add_unit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64]
+lib.micgpu_decoder_add_pics.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, _ip, _ip]
+lib.micgpu_decoder_add_mic2.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, _ip, _ip, _ip, _ip]
+lib.micgpu_decoder_commit.argtypes = [C.c_void_p]
+lib.micgpu_decoder_unit_count.argtypes = [C.c_void_p]
+lib.micgpu_decoder_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.micgpu_decoder_unit_status.argtypes = [C.c_void_p, _ip, C.c_int, C.c_void_p]
+lib.micgpu_decoder_last_launches.argtypes = [C.c_void_p]
+lib.micgpu_decoder_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+lib.micgpu_pics_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_pics_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip]
+lib.micgpu_decompress_single_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+lib.micgpu_mic2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip, _ip, _ip]
+lib.micgpu_mic2_decompress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
+for _n in ("two", "four", "eight"):
+    for _s in ("", "_simd"):
+        getattr(lib, f"mic_decompress_{_n}_state{_s}").argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+lib.mic_decompress_parallel.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int]
+lib.mic_decompress_parallel_scalar.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int]
+
+
+def last_error() -> str:
+    return (lib.micgpu_last_error() or b"").decode("utf-8", "replace")
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MicGpuError(rc, last_error())
+
+
+def _bytes_view(b) -> np.ndarray:
+    if isinstance(b, np.ndarray):
+        return np.ascontiguousarray(b, dtype=np.uint8)
+    return np.frombuffer(b, dtype=np.uint8)
+
+
+def _rd32(a: np.ndarray, off: int) -> int:
+    return int(a[off]) | int(a[off + 1]) << 8 | int(a[off + 2]) << 16 | int(a[off + 3]) << 24
+
+
+# ---- Go-named one-shot calls (host buffers) --------------------------------------
+def DecompressParallelStrips(compressed):
+    """parallelstrips.go:270 -> (pixels[h*w] uint16, width, height)."""
+    a = _bytes_view(compressed)
+    if a.size < 20 or bytes(a[:4]) != b"PICS":
+        raise MicGpuError(E_HEADER, "parallelstrips: invalid magic")
+    w, h = _rd32(a, 4), _rd32(a, 8)
+    if w <= 0 or h <= 0 or w * h > (1 << 34):
+        raise MicGpuError(E_HEADER, "parallelstrips: invalid dimensions")
+    out = np.empty(w * h, np.uint16)
+    ow, oh = C.c_int(), C.c_int()
+    _check(lib.micgpu_pics_decompress(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(ow), C.byref(oh)))
+    return out, ow.value, oh.value
+
+
+def DecompressParallelStripsBatch(blobs):
+    """Batch of independent PICS images in one launch sequence -> list of (pixels, w, h)."""
+    views = [_bytes_view(b) for b in blobs]
+    n = len(views)
+    outs, dims = [], []
+    for a in views:
+        if a.size < 20 or bytes(a[:4]) != b"PICS":
+            raise MicGpuError(E_HEADER, "parallelstrips: invalid magic")
+        w, h = _rd32(a, 4), _rd32(a, 8)
+        dims.append((w, h))
+        outs.append(np.empty(w * h, np.uint16))
+    bp = (C.c_void_p * n)(*[a.ctypes.data for a in views])
+    ln = (C.c_size_t * n)(*[a.size for a in views])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    cp = (C.c_size_t * n)(*[o.size for o in outs])
+    st = (C.c_int * n)()
+    _check(lib.micgpu_pics_decompress_batch(n, bp, ln, op, cp, st))
+    return [(o, w, h) for o, (w, h) in zip(outs, dims)]
+
+
+def DecompressSingleFrame(compressed, width: int, height: int) -> np.ndarray:
+    """multiframecompress.go:97."""
+    a = _bytes_view(compressed)
+    out = np.empty(width * height, np.uint16)
+    _check(lib.micgpu_decompress_single_frame(a.ctypes.data, a.size, out.ctypes.data, width, height))
+    return out
+
+
+def DecompressMultiFrame(data):
+    """multiframecompress.go:227 -> (frames[n,h,w] uint16, header dict)."""
+    a = _bytes_view(data)
+    if a.size < 20 or bytes(a[:4]) != b"MIC2":
+        raise MicGpuError(E_HEADER, "MIC2: invalid magic")
+    w, h, n = _rd32(a, 4), _rd32(a, 8), _rd32(a, 12)
+    out = np.empty(max(n * w * h, 1), np.uint16)
+    ow, oh, on, ot = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib.micgpu_mic2_decompress(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(ow), C.byref(oh), C.byref(on), C.byref(ot)))
+    hdr = {"Width": ow.value, "Height": oh.value, "FrameCount": on.value, "Temporal": bool(ot.value)}
+    return out[: n * w * h].reshape(n, h, w), hdr
+
+
+def DecompressFrame(data, frame_idx: int):
+    """multiframecompress.go:266 -> pixels[h,w]."""
+    a = _bytes_view(data)
+    if a.size < 20 or bytes(a[:4]) != b"MIC2":
+        raise MicGpuError(E_HEADER, "MIC2: invalid magic")
+    w, h = _rd32(a, 4), _rd32(a, 8)
+    out = np.empty(max(w * h, 1), np.uint16)
+    ow, oh = C.c_int(), C.c_int()
+    _check(lib.micgpu_mic2_decompress_frame(a.ctypes.data, a.size, frame_idx, out.ctypes.data, out.size, C.byref(ow), C.byref(oh)))
+    return out[: w * h].reshape(h, w)
+
+
+# ---- batch decoder over device-resident buffers -------------------------------------
+class Decoder:
+    """Plan a batch from host copies of the streams, then run it on device buffers."""
+
+    def __init__(self, device: int = 0):
+        self._h = lib.micgpu_decoder_create(device)
+        if not self._h:
+            raise MicGpuError(E_CUDA, last_error())
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            lib.micgpu_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin(self):
+        self._keep = []
+        _check(lib.micgpu_decoder_begin(self._h))
+
+    def add_unit(self, frame, comp_off: int, kind: int, width: int, height: int, out_off: int) -> int:
+        a = _bytes_view(frame)
+        self._keep.append(a)
+        rc = lib.micgpu_decoder_add_unit(self._h, a.ctypes.data, a.size, comp_off, kind, width, height, out_off)
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def add_pics(self, blob, comp_off: int, out_off: int):
+        a = _bytes_view(blob)
+        w, h = C.c_int(), C.c_int()
+        _check(lib.micgpu_decoder_add_pics(self._h, a.ctypes.data, a.size, comp_off, out_off, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def add_mic2(self, blob, comp_off: int, out_off: int):
+        a = _bytes_view(blob)
+        w, h, n, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib.micgpu_decoder_add_mic2(self._h, a.ctypes.data, a.size, comp_off, out_off, C.byref(w), C.byref(h), C.byref(n), C.byref(t)))
+        return w.value, h.value, n.value, bool(t.value)
+
+    def commit(self):
+        _check(lib.micgpu_decoder_commit(self._h))
+
+    @property
+    def unit_count(self) -> int:
+        return lib.micgpu_decoder_unit_count(self._h)
+
+    @property
+    def last_launches(self) -> int:
+        return lib.micgpu_decoder_last_launches(self._h)
+
+    def run_device(self, d_comp_ptr: int, comp_bytes: int, d_out_ptr: int, out_elems: int, stream_ptr: int = 0):
+        _check(lib.micgpu_decoder_run_device(self._h, d_comp_ptr, comp_bytes, d_out_ptr, out_elems, stream_ptr))
+
+    def unit_status(self, stream_ptr: int = 0, raise_on_error: bool = True):
+        n = self.unit_count
+        st = (C.c_int * max(n, 1))()
+        rc = lib.micgpu_decoder_unit_status(self._h, st, n, stream_ptr)
+        if rc and raise_on_error:
+            _check(rc)
+        return list(st)[:n]
+
+    def run_host(self, comp: np.ndarray, out: np.ndarray):
+        _check(lib.micgpu_decoder_run_host(self._h, comp.ctypes.data, comp.size, out.ctypes.data, out.size))

@@ -1,0 +1,254 @@
+// k_ans.cu -- K2: interleaved N-state tANS / rANS decode (N in {1,2,4,8}).
+//
+// Replaces decompress (fsedecompressu16.go:267-377), decompress2State
+// (fse2state.go:203-308), decompress4State (fse4state.go:195-353),
+// decompress8State (fse8state.go:230-380), ransDecompress8State
+// (rans8state.go:223-412) and the amd64/arm64 assembly kernels.
+//
+// Mapping: one "slot" = N adjacent lanes of a warp decodes one unit; lane k owns
+// state k.  All N states share ONE bitstream that is consumed round-robin
+// (A,B,..), so within a round lane k reads its nbBits field right below the
+// fields of lanes < k: the offset is an exclusive prefix sum of nbBits over the
+// slot, obtained with one or two redux.sync.or over byte-packed lanes.
+// The decode table lives in shared memory (4 B or 2 B per cell) and the
+// bitstream is staged through a 128 B per-slot shared-memory ring that is
+// refilled from registers loaded one 64 B half ahead (plus an L2 prefetch
+// further ahead), so no global-memory latency sits on the state->state chain.
+//
+// Output is the *state* stream (the table index each symbol was emitted from);
+// K3 maps states to symbols through tabS, which keeps the 16-bit symbol out of
+// this kernel's shared-memory footprint.
+//
+// Bit coordinates: the reference reader starts at the last byte, skips the
+// padding and the 1-bit sentinel and reads fields MSB-first walking to byte 0
+// (bitreader.go:26-62).  With the stream viewed as one little-endian integer,
+// a field of n bits read when P bits remain unread is bits [P-n, P).
+#include "mic_device.cuh"
+
+namespace micgpu {
+
+constexpr int K2_THREADS = 128;
+constexpr int RING_WORDS = 32;
+constexpr int HALF_WORDS = 16;
+
+template <int N>
+__device__ __forceinline__ uint32_t slot_prefix(uint32_t nb, int k, unsigned slotmask, uint32_t* tot) {
+  if (N == 1) {
+    *tot = nb;
+    return 0;
+  } else if (N <= 4) {
+    uint32_t r = __reduce_or_sync(slotmask, nb << (8 * k));
+    *tot = (r * 0x01010101u) >> 24;
+    uint32_t below = r & ((1u << (8 * k)) - 1u);
+    return (below * 0x01010101u) >> 24;
+  } else {
+    uint32_t r0 = __reduce_or_sync(slotmask, k < 4 ? nb << (8 * k) : 0u);
+    uint32_t r1 = __reduce_or_sync(slotmask, k >= 4 ? nb << (8 * (k - 4)) : 0u);
+    uint32_t s0 = (r0 * 0x01010101u) >> 24;
+    *tot = s0 + ((r1 * 0x01010101u) >> 24);
+    uint32_t m0 = k < 4 ? ((1u << (8 * k)) - 1u) : 0xffffffffu;
+    uint32_t m1 = k <= 4 ? 0u : ((1u << (8 * (k - 4))) - 1u);
+    return (((r0 & m0) * 0x01010101u) >> 24) + (((r1 & m1) * 0x01010101u) >> 24);
+  }
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(K2_THREADS)
+k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
+             const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots_per_cta) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int PW = HALF_WORDS / N;  // ring words each lane carries for the in-flight half
+  const int tid = threadIdx.x;
+  const int slot = tid / N;
+  const int k = tid % N;
+  const int lane = tid & 31;
+  if (slot >= slots_per_cta) return;
+  const unsigned slotmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane - k));
+
+  const size_t tbytes = MODE == 2 ? 0 : ((size_t)(1u << max_log) * (MODE == 0 ? 4 : 2));
+  uint8_t* mytab = smem + (size_t)slot * tbytes;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)slots_per_cta * tbytes) + slot * RING_WORDS;
+
+  for (int li = blockIdx.x * slots_per_cta + slot; li < nlist; li += gridDim.x * slots_per_cta) {
+    MicUnit* U = &units[list[li]];
+    if (U->status != MIC_OK) continue;
+    const int L = (int)U->table_log;
+    const uint32_t S = 1u << L;
+    const uint32_t* A = tabA + U->tab_off;
+    __syncwarp(slotmask);
+    // ---- stage the decode table ------------------------------------------
+    if (MODE == 0) {
+      uint4* T4 = reinterpret_cast<uint4*>(mytab);
+      const uint4* A4 = reinterpret_cast<const uint4*>(A);
+      for (uint32_t i = k; i < S / 4; i += N) T4[i] = A4[i];
+    } else if (MODE == 1) {
+      uint2* T2 = reinterpret_cast<uint2*>(mytab);
+      const uint4* A4 = reinterpret_cast<const uint4*>(A);
+      for (uint32_t i = k; i < S / 4; i += N) {
+        uint4 e = A4[i];
+        // nextState = (newState + S) >> nbBits  (inverse of fsedecompressu16.go:250-251)
+        uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
+        uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
+        T2[i] = make_uint2(n0 | (n1 << 16), n2 | (n3 << 16));
+      }
+    }
+    const uint32_t* T32 = reinterpret_cast<const uint32_t*>(mytab);
+    const uint16_t* T16 = reinterpret_cast<const uint16_t*>(mytab);
+
+    // ---- bitstream geometry ----------------------------------------------
+    const uint8_t* bs = comp + U->comp_off + U->bits_off;
+    const uint32_t blen = U->bits_len;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(bs);
+    const uint32_t* wbase = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)63);
+    const uint32_t shift = (uint32_t)(addr & 63) * 8;      // first data bit in ring coordinates
+    const uint32_t lastb = bs[blen - 1];                   // non-zero (checked by K1)
+    uint32_t P = shift + 8u * (blen - 1) + (31u - __clz(lastb));  // unread bits are [shift, P)
+
+    uint32_t pre[PW];
+    auto load_half = [&](int hh) {
+      if (hh >= 0) {
+        const uint32_t* src = wbase + hh * HALF_WORDS + k * PW;
+        if (PW == 2) {
+          uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
+          pre[0] = v.x; pre[1] = v.y;
+        } else {
+#pragma unroll
+          for (int i = 0; i < PW / 4; i++) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            pre[4 * i] = v.x; pre[4 * i + 1] = v.y; pre[4 * i + 2] = v.z; pre[4 * i + 3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PW; i++) pre[i] = 0;
+      }
+    };
+    auto store_half = [&](int hh) {
+#pragma unroll
+      for (int i = 0; i < PW; i++) ring[(hh * HALF_WORDS + k * PW + i) & (RING_WORDS - 1)] = pre[i];
+    };
+    int cur_half = (int)((P - 1) >> 5) / HALF_WORDS;
+    load_half(cur_half); store_half(cur_half);
+    load_half(cur_half - 1); store_half(cur_half - 1);
+    load_half(cur_half - 2);
+    __syncwarp(slotmask);
+
+    auto extract = [&](uint32_t lo, uint32_t nb) -> uint32_t {
+      uint32_t wi = lo >> 5;
+      uint32_t w0 = ring[wi & (RING_WORDS - 1)], w1 = ring[(wi + 1) & (RING_WORDS - 1)];
+      return __funnelshift_r(w0, w1, lo & 31) & ((1u << nb) - 1u);
+    };
+    auto advance = [&](uint32_t tot) {
+      P -= tot;
+      int h = (int)((P - 1) >> 5) / HALF_WORDS;
+      if (P > shift && h < cur_half) {
+        // half cur_half is dead: overwrite it with half cur_half-2 (already in registers)
+        store_half(cur_half - 2);
+        cur_half -= 1;
+        load_half(cur_half - 2);
+        if (k == 0 && cur_half >= 6)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + (cur_half - 6) * HALF_WORDS));
+        __syncwarp(slotmask);
+      }
+    };
+
+    int err = 0;
+    uint32_t state = 0;
+    // ---- initial states: A first, tableLog bits each (fse8state.go:239-250) ----
+    {
+      uint32_t tot = (uint32_t)(N * L);
+      if (P - shift < tot) {
+        err = 1;
+      } else {
+        state = extract(P - (uint32_t)(k + 1) * L, (uint32_t)L);
+        advance(tot);
+      }
+    }
+    uint16_t* out = states_out + U->sym_off;
+    uint32_t nsym = 0;
+
+    if (N == 1) {
+      // 1-state: no symbol count; stop on bit exhaustion (fsedecompressu16.go:361-376)
+      const uint32_t cap = U->sym_cap;
+      while (!err) {
+        uint32_t nb, ns;
+        if (MODE == 0) { uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
+        else if (MODE == 1) { uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }
+        else { uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
+        if (P == shift && nb > 0) {      // decoderU16.finished()
+          if (state != 0) {
+            if (nsym >= cap) { err = 2; break; }
+            out[nsym++] = (uint16_t)state;  // final()
+          }
+          break;
+        }
+        if (nsym >= cap) { err = 2; break; }
+        out[nsym++] = (uint16_t)state;
+        if (P - shift < nb) { err = 1; break; }   // partial over-read -> io.ErrUnexpectedEOF
+        uint32_t bits = nb ? extract(P - nb, nb) : 0u;
+        state = ns + bits;
+        advance(nb);
+      }
+    } else {
+      const uint32_t count = U->count;
+      if (count > U->sym_cap) err = 2;
+      for (uint32_t base = 0; base < count && !err; base += N) {
+        const bool active = base + (uint32_t)k < count;
+        uint32_t nb, ns;
+        if (MODE == 0) { uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
+        else if (MODE == 1) { uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }
+        else { uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
+        if (!active) nb = 0;
+        uint32_t tot;
+        const uint32_t before = slot_prefix<N>(nb, k, slotmask, &tot);
+        if (P - shift < tot) { err = 1; break; }
+        const uint32_t bits = nb ? extract(P - before - nb, nb) : 0u;
+        if (active) {
+          out[base + k] = (uint16_t)state;
+          state = ns + bits;
+        }
+        advance(tot);
+      }
+      nsym = count;
+    }
+    if (k == 0) {
+      U->nsym = nsym;
+      if (err) U->status = err == 1 ? MIC_E_BITSTREAM : MIC_E_SIZE;
+    }
+  }
+}
+
+size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta) {
+  size_t t = smem_mode == 2 ? 0 : ((size_t)(1u << max_log) * (smem_mode == 0 ? 4 : 2));
+  return (size_t)slots_per_cta * (t + RING_WORDS * 4);
+}
+
+template <int N, int MODE>
+static void launch_one(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, const uint32_t* d_tabA,
+                       uint16_t* d_states, int max_log, int slots, int grid, cudaStream_t st) {
+  size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
+  cudaFuncSetAttribute(k_ans_decode<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_ans_decode<N, MODE><<<grid, K2_THREADS, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
+}
+
+template <int N>
+static void launch_n(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, const uint32_t* d_tabA,
+                     uint16_t* d_states, int max_log, int mode, int slots, int grid, cudaStream_t st) {
+  if (mode == 0) launch_one<N, 0>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);
+  else if (mode == 1) launch_one<N, 1>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);
+  else launch_one<N, 2>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);
+}
+
+void launch_ans_decode(MicUnit* d_units, const int* d_list, int nlist, int nstates, const uint8_t* d_comp,
+                       const uint32_t* d_tabA, uint16_t* d_states, int max_log, int smem_mode, int slots_per_cta,
+                       int grid, cudaStream_t st) {
+  if (nlist <= 0) return;
+  switch (nstates) {
+    case 1: launch_n<1>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, smem_mode, slots_per_cta, grid, st); break;
+    case 2: launch_n<2>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, smem_mode, slots_per_cta, grid, st); break;
+    case 4: launch_n<4>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, smem_mode, slots_per_cta, grid, st); break;
+    default: launch_n<8>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, smem_mode, slots_per_cta, grid, st); break;
+  }
+}
+
+}  // namespace micgpu

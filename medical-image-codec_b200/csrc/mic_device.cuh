@@ -1,0 +1,43 @@
+// mic_device.cuh -- shared device-side declarations for the micgpu kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mic_unit.h"
+
+namespace micgpu {
+
+// ---- launchers (defined in the k_*.cu files) -------------------------------
+void launch_build_tables(MicUnit* d_units, int nunits, const uint8_t* d_comp, uint32_t* d_tabA, uint16_t* d_tabS,
+                         uint8_t* d_scratch, unsigned long long scratch_stride, int max_log, int grid, cudaStream_t st);
+
+// ANS decode of the units listed in d_list (all with the same state count).
+// Output: the *state* stream (table indices, u16) at units[i].sym_off; symbols
+// are recovered later through tabS.  smem_mode: 0 = u32 entries in shared
+// memory, 1 = u16 nextState entries in shared memory, 2 = table stays in L2.
+void launch_ans_decode(MicUnit* d_units, const int* d_list, int nlist, int nstates, const uint8_t* d_comp,
+                       const uint32_t* d_tabA, uint16_t* d_states, int max_log, int smem_mode, int slots_per_cta,
+                       int grid, cudaStream_t st);
+size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta);
+
+// RLE expand (+ escape split for spatial units).  Spatial units produce the
+// residual plane D (pitch wp) and the literal bit mask M; RLE units write
+// their expanded stream straight to d_out.
+void launch_rle_expand(MicUnit* d_units, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
+                       uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int grid, cudaStream_t st);
+
+// Inverse avg(top,left) predictor as an anti-diagonal wavefront; one CTA per spatial unit.
+void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,
+                            uint16_t* d_out, int max_width, int max_height, cudaStream_t st);
+int delta_wavefront_threads(int max_width, int max_height);
+
+// In-place frame-axis running sum for temporal MIC2 (frames contiguous, fpx pixels each).
+void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int sm_count, cudaStream_t st);
+
+// ---- small device helpers ---------------------------------------------------
+__device__ __forceinline__ uint32_t ld_u32_unaligned_safe(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ int bit_len16(uint32_t v) { return 32 - __clz(v); }  // bits.Len16 for v < 65536
+
+}  // namespace micgpu

@@ -1,0 +1,51 @@
+// mic_unit.h -- unit descriptor shared by host planning code and device kernels.
+//
+// A "unit" is one independent FSE frame of the MIC hot path: a PICS strip, a
+// MIC2 frame (spatial or temporal residual), one plane of a MIC3 tile or a
+// WaveletV2 coefficient stream (reference: multiframecompress.go:97,165;
+// parallelstrips.go:292-321; wsicompress.go:487-524; waveletfsecompressu16.go:374-421).
+#pragma once
+#include <stdint.h>
+
+enum MicUnitKind {
+  MIC_KIND_SPATIAL = 0,  // Delta(avg(top,left),escape)+RLE symbol stream -> w*h pixels
+  MIC_KIND_RLE = 1,      // RLE stream with 2-word length prefix (temporal residual / wavelet)
+};
+
+enum MicStatus {
+  MIC_OK = 0,
+  MIC_E_HEADER = -1,     // bad magic / truncated frame          (C twin: -1)
+  MIC_E_NCOUNT = -2,     // readNCount corruption                (C twin: -2)
+  MIC_E_ALLOC = -3,
+  MIC_E_DTABLE = -4,     // buildDtable corruption               (C twin: -4)
+  MIC_E_BITSTREAM = -6,  // bit reader over-read / zero last byte (C twin: -6)
+  MIC_E_RLE = -8,        // RLE stream over-run or malformed header
+  MIC_E_SIZE = -9,       // decoded size does not match the unit's geometry
+  MIC_E_UNSUPPORTED = -10,
+};
+
+struct MicUnit {
+  // ---- host-filled ------------------------------------------------------
+  unsigned long long comp_off;  // byte offset of the FSE frame in the device compressed buffer
+  unsigned long long sym_off;   // element offset (u16) in the state-stream scratch
+  unsigned long long tab_off;   // entry offset in the decode-table scratch
+  unsigned long long d_off;     // element offset (u16) in the residual plane scratch (pitch wp)
+  unsigned long long m_off;     // word offset in the literal-mask scratch (pitch wp/32)
+  unsigned long long out_off;   // element offset (u16) in the output buffer
+  unsigned int comp_len;
+  unsigned int kind;
+  unsigned int width, height;   // spatial: image geometry; RLE: width = expected outlen, height = 1
+  unsigned int wp;              // padded pitch (multiple of 32 elements)
+  unsigned int nstates;         // 1,2,4,8 (from the magic prefix, fse2state.go:102-116)
+  unsigned int rans;            // 1 when magic is [0xFF,0x08]
+  unsigned int table_log;       // peeked from the ncount header (fsedecompressu16.go:61)
+  unsigned int count;           // symbol count from the 6-byte prefix (0: 1-state, unknown)
+  unsigned int sym_cap;         // capacity (elements) reserved at sym_off
+  // ---- device-filled ----------------------------------------------------
+  unsigned int bits_off;        // byte offset of the bitstream inside the frame
+  unsigned int bits_len;        // bitstream length in bytes
+  unsigned int nsym;            // symbols actually decoded
+  unsigned int thr;             // deltaThreshold (deltarlecompressu16.go:72-74)
+  unsigned int delim;           // delimiterForOverflow
+  int status;                   // MicStatus
+};

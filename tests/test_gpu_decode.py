@@ -1,0 +1,142 @@
+"""GPU parity: CUDA decode path (through the C ABI) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(oracle, img, w, h, coder):
+    """One FSE frame of a spatial unit with the requested entropy coder."""
+    mx = int(img.max())
+    if coder in (1, 2, 4, 8):
+        return oracle.compress_single_frame(img, w, h, mx, coder)
+    sym = oracle.delta_rle_compress(img, w, h, mx)
+    return oracle.fse_compress(sym, coder)
+
+
+@pytest.mark.parametrize("coder", [1, 2, 4, 8, 108])
+def test_single_frame_mr(mic, oracle, coder):
+    # 256x256 12-bit MR: tableLog 13 (the reference's own round-trip image, fseu16_test.go:28-53)
+    rng = np.random.default_rng(5)
+    w, h = 256, 256
+    y, x = np.mgrid[0:h, 0:w]
+    img = ((np.sin(x / 17.0) + np.cos(y / 23.0) + 2) * 700 + rng.integers(0, 40, (h, w))).astype(np.uint16).ravel()
+    blob = _frame(oracle, img, w, h, coder)
+    got = mic.DecompressSingleFrame(blob, w, h)
+    assert np.array_equal(got, oracle.decompress_single_frame(blob, w, h))
+    assert np.array_equal(got, img)
+
+
+@pytest.mark.parametrize("coder", [1, 2, 8])
+def test_single_frame_16bit_tablelog16(mic, oracle, coder):
+    # full 16-bit range forces tableLog 16: the decode table stays in L2 (mode 2)
+    rng = np.random.default_rng(7)
+    w, h = 300, 200
+    img = (np.cumsum(rng.integers(-300, 301, w * h)) % 65536).astype(np.uint16)
+    img[::97] = 65535
+    blob = _frame(oracle, img, w, h, coder)
+    got = mic.DecompressSingleFrame(blob, w, h)
+    assert np.array_equal(got, img)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 40), (40, 1), (3, 3), (7, 5), (31, 33), (33, 31), (64, 64), (257, 129), (1000, 37)])
+@pytest.mark.parametrize("coder", [2, 8])
+def test_ragged_sizes(mic, oracle, w, h, coder):
+    rng = np.random.default_rng(w * 1000 + h)
+    img = (rng.integers(0, 50, w * h) + 1000).astype(np.uint16)
+    try:
+        blob = _frame(oracle, img, w, h, coder)
+    except Exception:
+        pytest.skip("input rejected by the encoder (incompressible / too short)")
+    got = mic.DecompressSingleFrame(blob, w, h)
+    assert np.array_equal(got, img)
+
+
+def test_escapes_and_runs(mic, oracle):
+    # sharp edges (escape + literal), literals equal to the delimiter, long constant runs
+    w, h = 500, 120
+    img = np.zeros((h, w), np.uint16)
+    img[:, 100:200] = 4095          # literal == delimiter (depth 12)
+    img[10:50, 250:400] = 2000
+    img[60:, ::2] = 4095
+    img[60:, 1::2] = 0
+    img[100:, :] = 777
+    img = img.ravel()
+    for coder in (2, 4, 8):
+        blob = _frame(oracle, img, w, h, coder)
+        got = mic.DecompressSingleFrame(blob, w, h)
+        assert np.array_equal(got, img), coder
+
+
+@pytest.mark.parametrize("nstates", [2, 4, 8])
+@pytest.mark.parametrize("strips", [1, 3, 8])
+def test_pics(mic, oracle, synth, nstates, strips):
+    w, h = 611, 403
+    img = synth.xr_image(11, w, h).ravel()
+    blob = oracle.pics_compress(img, w, h, int(img.max()), strips, nstates)
+    got, ow, oh = mic.DecompressParallelStrips(blob)
+    assert (ow, oh) == (w, h)
+    assert np.array_equal(got, img)
+
+
+def test_pics_full_size_strip_table(mic, oracle, synth, reftwin):
+    # BASELINE config 2 geometry for one image: 2577x2048, 8 strips of 256 rows, 8-state and 2-state
+    w, h = 2577, 2048
+    img = synth.xr_image(1, w, h).ravel()
+    for nstates in (8, 2):
+        blob = oracle.pics_compress(img, w, h, int(img.max()), 8, nstates)
+        got, _, _ = mic.DecompressParallelStrips(blob)
+        assert np.array_equal(got, img)
+    # the reference's own pthread decoder agrees on the 2-state container
+    assert np.array_equal(reftwin.decompress_parallel(blob, w, h, 8), got)
+
+
+def test_pics_batch(mic, oracle, synth):
+    w, h = 300, 200
+    imgs = [synth.xr_image(20 + i, w, h).ravel() for i in range(5)]
+    blobs = [oracle.pics_compress(im, w, h, int(im.max()), 4, 8 if i % 2 else 2) for i, im in enumerate(imgs)]
+    res = mic.DecompressParallelStripsBatch(blobs)
+    for (px, ow, oh), im in zip(res, imgs):
+        assert (ow, oh) == (w, h)
+        assert np.array_equal(px, im)
+
+
+@pytest.mark.parametrize("temporal", [False, True])
+def test_mic2(mic, oracle, synth, temporal):
+    # 128x128x5 like TestMultiFrame{Independent,Temporal}Roundtrip (multiframe_test.go:149,192)
+    st = synth.tomo_stack(7, 5, 128, 128)
+    blob = oracle.mic2_compress(st.ravel(), 128, 128, 1023, temporal)
+    frames, hdr = mic.DecompressMultiFrame(blob)
+    assert hdr["Temporal"] == temporal and hdr["FrameCount"] == 5
+    assert np.array_equal(frames, st)
+    for idx in (0, 2, 4):
+        assert np.array_equal(mic.DecompressFrame(blob, idx), st[idx])
+
+
+def test_twin_symbols(mic, oracle, synth):
+    import ctypes as C
+
+    w, h = 320, 240
+    img = synth.xr_image(4, w, h).ravel()
+    for nstates, name in ((2, "two"), (4, "four"), (8, "eight")):
+        blob = np.frombuffer(oracle.compress_single_frame(img, w, h, int(img.max()), nstates), np.uint8)
+        for suffix in ("", "_simd"):
+            out = np.zeros(w * h, np.uint16)
+            rc = getattr(mic.lib, f"mic_decompress_{name}_state{suffix}")(blob.ctypes.data, blob.size, out.ctypes.data, w, h)
+            assert rc == 0 and np.array_equal(out, img)
+    pics = np.frombuffer(oracle.pics_compress(img, w, h, int(img.max()), 8, 4), np.uint8)
+    out = np.zeros(w * h, np.uint16)
+    assert mic.lib.mic_decompress_parallel(pics.ctypes.data, pics.size, out.ctypes.data, w, h, 8) == 0
+    assert np.array_equal(out, img)
+    assert mic.lib.mic_decompress_parallel(pics.ctypes.data, pics.size, out.ctypes.data, w + 1, h, 8) == -1
+
+
+def test_corrupt_streams_report_errors(mic, oracle, synth):
+    w, h = 200, 100
+    img = synth.xr_image(9, w, h).ravel()
+    blob = bytearray(oracle.compress_single_frame(img, w, h, int(img.max()), 8))
+    trunc = bytes(blob[: len(blob) // 2])
+    with pytest.raises(mic.MicGpuError):
+        mic.DecompressSingleFrame(trunc + b"\x00", w, h)       # zero last byte: bitreader.go:33-36
+    with pytest.raises(mic.MicGpuError):
+        mic.DecompressParallelStrips(b"PICX" + bytes(40))

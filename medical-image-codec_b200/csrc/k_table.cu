@@ -76,12 +76,16 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
   __shared__ int s_status, s_symlen, s_consumed, s_tlog;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Only symbols with a non-zero normalised count matter and there are at most 2^L of them, so
+  // all scratch is indexed by "present index" and sized by the table, not by the 65536-symbol alphabet.
   const unsigned cap = 1u << max_log;                       // entries reserved per array
   uint8_t* my = scratch + (unsigned long long)blockIdx.x * scratch_stride;
-  int32_t* norm = reinterpret_cast<int32_t*>(my);           // [cap]
+  int32_t* norm = reinterpret_cast<int32_t*>(my);           // [cap] normalised count of present symbol i
   uint32_t* cumul = reinterpret_cast<uint32_t*>(norm + cap);   // [cap]
   uint32_t* symnext = cumul + cap;                          // [cap]
-  uint16_t* sym_of_rank = reinterpret_cast<uint16_t*>(symnext + cap);  // [cap]
+  uint16_t* pres_sym = reinterpret_cast<uint16_t*>(symnext + cap);  // [cap] symbol value of present symbol i
+  uint16_t* sym_of_rank = pres_sym + cap;                   // [cap] present index owning spread rank k
+  uint16_t* cell_idx = sym_of_rank + cap;                   // [cap] present index of table cell u
 
   for (int ui = blockIdx.x; ui < nunits; ui += gridDim.x) {
     MicUnit* U = &units[ui];
@@ -95,7 +99,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
     if (warp == 0) {
       int status = MIC_OK;
       int consumed = 0;
-      uint32_t charnum = 0;
+      uint32_t charnum = 0, npres = 0;
       int tlog = 0;
       NCountReader rd{frame + hdr, flen - hdr, s_win, -1};
       const int iend = rd.blen;
@@ -134,9 +138,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
             }
             n0 += bit_stream & 3;
             bit_count += 2;
-            if (n0 > 65535u || n0 > cap) { status = MIC_E_NCOUNT; break; }
-            if (lane == 0)
-              for (uint32_t c = charnum; c < n0; c++) norm[c] = 0;
+            if (n0 > 65535u) { status = MIC_E_NCOUNT; break; }
             charnum = n0;
             if (off <= iend - 7 || off + (int)(bit_count >> 3) <= iend - 4) {
               off += (int)(bit_count >> 3);
@@ -159,8 +161,12 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
           count--;
           if (count < 0) { remaining += count; got_total -= count; }
           else { remaining -= count; got_total += count; }
-          if (charnum >= cap) { status = MIC_E_NCOUNT; break; }  // more symbols than table cells: cannot normalise
-          if (lane == 0) norm[charnum] = count;
+          if (charnum > 65535u) { status = MIC_E_NCOUNT; break; }
+          if (count != 0) {
+            if (npres >= cap) { status = MIC_E_NCOUNT; break; }  // more present symbols than table cells
+            if (lane == 0) { norm[npres] = count; pres_sym[npres] = (uint16_t)charnum; }
+            npres++;
+          }
           charnum++;
           previous0 = (count == 0);
           while (remaining < threshold) { nb_bits--; threshold >>= 1; }
@@ -180,7 +186,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
           if (hdr + consumed >= flen) status = MIC_E_BITSTREAM;  // bitReader.init: "too short"
         }
       }
-      if (lane == 0) { s_status = status; s_symlen = (int)charnum; s_consumed = consumed; s_tlog = tlog; }
+      if (lane == 0) { s_status = status; s_symlen = (int)npres; s_consumed = consumed; s_tlog = tlog; }
     }
     __syncthreads();
     if (s_status != MIC_OK) {
@@ -189,7 +195,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
     }
     const int L = s_tlog;
     const uint32_t S = 1u << L;
-    const uint32_t symlen = (uint32_t)s_symlen;
+    const uint32_t symlen = (uint32_t)s_symlen;   // number of present symbols
     uint32_t* A = tabA + U->tab_off;
     uint16_t* Sy = tabS + U->tab_off;
     const bool rans = U->rans != 0;
@@ -223,8 +229,8 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
           // tANS: lowprob symbols laid down from the top in symbol order (fsedecompressu16.go:207-211)
           // rANS: after all normal symbols, ascending (ransu16.go:116-129)
           uint32_t cell = rans ? (S - nlow + lr) : (S - 1 - lr);
-          Sy[cell] = (uint16_t)s;
-          if (rans) A[cell] = ((uint32_t)L << 16);  // newState 0, nbBits = tableLog
+          cell_idx[cell] = (uint16_t)s;
+          if (rans) { A[cell] = ((uint32_t)L << 16); Sy[cell] = pres_sym[s]; }  // newState 0, nbBits = tableLog
           lr++;
         } else {
           symnext[s] = 0;
@@ -240,7 +246,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
         uint32_t x_next = (uint32_t)norm[s] + (k - cumul[s]);
         uint32_t nb = (uint32_t)L - (31u - __clz(x_next));
         uint32_t ns = (x_next << nb) - S;
-        Sy[k] = (uint16_t)s;
+        Sy[k] = pres_sym[s];
         A[k] = ns | (nb << 16);
       }
     } else {
@@ -258,7 +264,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
       unsigned rank = BlockScan::run(live, s_scan, &tot_live);
       for (uint32_t j = j0; j < j1; j++) {
         uint32_t pos = (j * step) & mask;
-        if (pos <= high_threshold) Sy[pos] = sym_of_rank[rank++];
+        if (pos <= high_threshold) cell_idx[pos] = sym_of_rank[rank++];
       }
       __syncthreads();
       // ---------------- phase 4: nextState ranking (warp 0) -----------------
@@ -266,7 +272,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
         int bad = 0;
         for (uint32_t u0 = 0; u0 < S; u0 += 32) {
           uint32_t u = u0 + lane;
-          uint32_t sym = Sy[u];
+          uint32_t sym = cell_idx[u];
           unsigned peers = __match_any_sync(0xffffffffu, sym);
           unsigned r = __popc(peers & ((1u << lane) - 1u));
           uint32_t basev = symnext[sym];
@@ -279,6 +285,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
           uint32_t ns = (next_state << nb) - S;
           if (next_state >= 2 * S || ns >= S || (ns == u && nb == 0)) bad = 1;  // fsedecompressu16.go:252-258
           A[u] = (ns & 0xFFFF) | (nb << 16);
+          Sy[u] = pres_sym[sym];
         }
         bad = __any_sync(0xffffffffu, bad);
         if (bad && lane == 0) s_status = MIC_E_DTABLE;

@@ -199,7 +199,7 @@ int plan_commit(micgpu_decoder* d) {
     a.grid = std::min((n + slots - 1) / slots, d->sm_count * ctas_per_sm);
   }
   // ---- K1 scratch ------------------------------------------------------------
-  const unsigned long long per_cta = 14ull << d->max_log_all;
+  const unsigned long long per_cta = 18ull << d->max_log_all;
   int g1 = std::min<int>((int)d->units.size(), d->sm_count * 8);
   const unsigned long long k1_budget = 256ull << 20;
   if ((unsigned long long)g1 * per_cta > k1_budget) g1 = (int)std::max<unsigned long long>(d->sm_count / 2, k1_budget / per_cta);

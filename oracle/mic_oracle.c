@@ -246,6 +246,9 @@ static int normalize_count2(scratch *s) {
     if (cnt <= low_one) { s->norm[i] = 1; distributed++; total -= cnt; continue; }
     s->norm[i] = NYA;
   }
+  /* More present symbols than table cells: the Go code underflows toDistribute and spins for
+   * ~2^32 iterations (inputs far too small for the coder); the oracle reports it instead. */
+  if (distributed >= (1u << tl)) return ORC_ERR_INTERNAL;
   u32 to_distribute = (1u << tl) - distributed;
   if ((total / to_distribute) > low_one) {
     low_one = (total * 3) / (to_distribute * 2);
@@ -253,6 +256,7 @@ static int normalize_count2(scratch *s) {
       u32 cnt = s->count[i];
       if (s->norm[i] == NYA && cnt <= low_one) { s->norm[i] = 1; distributed++; total -= cnt; }
     }
+    if (distributed >= (1u << tl)) return ORC_ERR_INTERNAL;
     to_distribute = (1u << tl) - distributed;
   }
   if (distributed == s->symbol_len + 1) {

@@ -31,10 +31,13 @@ def test_single_frame_mr(mic, oracle, coder):
 def test_single_frame_16bit_tablelog16(mic, oracle, coder):
     # full 16-bit range forces tableLog 16: the decode table stays in L2 (mode 2)
     rng = np.random.default_rng(7)
-    w, h = 300, 200
+    # (needs >= 2^18 symbols: optimalTableLog caps tableLog at highBits(n-1)-2, fsecompressu16.go:483-486)
+    w, h = 530, 520
     img = (np.cumsum(rng.integers(-300, 301, w * h)) % 65536).astype(np.uint16)
     img[::97] = 65535
     blob = _frame(oracle, img, w, h, coder)
+    sym = oracle.delta_rle_compress(img, w, h, 65535)
+    assert oracle.fse_table_info(sym)[0] == 16
     got = mic.DecompressSingleFrame(blob, w, h)
     assert np.array_equal(got, img)
 

@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric for the MIC hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's C implementation on host cores
+
+Workload (config.workload): BASELINE configs[1] -- PICS-8 parallel strips Delta+RLE+FSE on synthetic
+2577x2048 12-bit radiographs, a batch of 256 images per GPU (2048 independent strips), 8-state FSE strips
+(CompressParallelStrips8State, parallelstrips.go:199).  One step = one decode pass over the whole batch.
+
+`value`  : decode GB/s of raw pixel bytes, streams resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : the same metric through the C-ABI host call micgpu_pics_decompress_batch (host buffers in
+           and out, H2D/D2H inside the timed region).
+`roofline`: dominant kernel's (compressed bytes read + raw bytes written) / its CUDA-event time vs the
+           measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline`: the reference's own C decoder (oracle/_ref, built from /root/reference/ojph/*.c) on the
+           host cores of the same box, bounded sample.
+
+Input generation (not timed): synthetic images are encoded once on the host with the CPU oracle, because
+the CUDA encoder of this round does not exist yet; the oracle is not on the measured path.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "medical-image-codec_b200"
+
+W, H, STRIPS = 2577, 2048, 8
+METRIC = "pics8_decode_GBps"
+UNIT = "GB/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def make_inputs(batch: int, distinct: int, nstates: int, seed0: int):
+    """-> (list of PICS blobs (bytes), raw image bytes per image).  `distinct` images are generated and
+    encoded; the batch cycles through them (each copy is a separate buffer on the device)."""
+    from oracle.oracle import Oracle
+
+    synth = importlib.import_module(PKG + ".synth")
+    o = Oracle()
+
+    def one(i):
+        img = synth.xr_image(seed0 + i, W, H)
+        return o.pics_compress(img.ravel(), W, H, int(img.max()), STRIPS, nstates)
+
+    with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+        uniq = list(ex.map(one, range(distinct)))
+    return [uniq[i % distinct] for i in range(batch)], W * H * 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload_key: str):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload_key)
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own C decoder on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle.oracle import RefTwin
+
+    ref = RefTwin()
+    nthreads = host_threads()
+    sample = min(args.batch, max(nthreads, 32))
+    nst = args.nstates
+    blobs, raw_per = make_inputs(sample, min(sample, args.distinct), nst, 1)
+    views = [np.frombuffer(b, np.uint8) for b in blobs]
+    outs = [np.empty(W * H, np.uint16) for _ in range(sample)]
+    name = {2: "two", 4: "four", 8: "eight"}[nst]
+    fn = getattr(ref.lib, f"mic_decompress_{name}_state_simd")
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+
+    # one task per strip: the reference's per-strip C decoder under a host thread pool sized to the cores
+    # (mic_decompress_parallel itself only dispatches 2-/4-state strips, ojph/mic_parallel.c:203-215)
+    tasks = []
+    for a, o in zip(views, outs):
+        ns, sh = int.from_bytes(a[12:16].tobytes(), "little"), int.from_bytes(a[16:20].tobytes(), "little")
+        hdr = 20 + 8 * ns
+        for s in range(ns):
+            off = int.from_bytes(a[20 + 8 * s:24 + 8 * s].tobytes(), "little")
+            ln = int.from_bytes(a[24 + 8 * s:28 + 8 * s].tobytes(), "little")
+            y0 = s * sh
+            rows = min(sh, H - y0)
+            tasks.append((a.ctypes.data + hdr + off, ln, o.ctypes.data + y0 * W * 2, rows))
+
+    def work(t):
+        rc = fn(t[0], t[1], t[2], W, t[3])
+        if rc != 0:
+            raise RuntimeError(f"reference decoder rc={rc}")
+
+    def step():
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            list(ex.map(work, tasks))
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    gbs = sample * raw_per / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"PICS-8 {nst}-state Delta+RLE+FSE decode, synthetic 2577x2048 12-bit XR, sample of {sample} images "
+                               f"({sample * STRIPS} strips) of the batch of {args.batch}", "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": round(gbs, 4), "unit": UNIT, "cores": nthreads, "kind": "reference",
+                         "sample": f"{sample} images x {STRIPS} strips, mic_decompress_{name}_state_simd per strip, {nthreads} host threads"},
+        "e2e": {"value": round(gbs, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+
+    import __graft_entry__ as g
+
+    g.build()
+    mic = importlib.import_module(PKG)
+    api = mic.api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (micgpu has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nst = args.nstates
+    t_setup = time.time()
+    blobs, raw_per = make_inputs(args.batch, args.distinct, nst, 1 + 1000 * rank)
+    n = len(blobs)
+    raw_bytes = n * raw_per
+    # pinned host staging: streams back to back at 64-byte aligned offsets
+    offs, tot = [], 0
+    for b in blobs:
+        offs.append(tot)
+        tot += (len(b) + 63) & ~63
+    comp_bytes_alg = sum(len(b) for b in blobs)
+    h_comp_ptr = api.lib.micgpu_host_alloc(tot + 256)
+    h_out_ptr = api.lib.micgpu_host_alloc(raw_bytes)
+    if not h_comp_ptr or not h_out_ptr:
+        raise SystemExit("pinned allocation failed: " + api.last_error())
+    h_comp = np.ctypeslib.as_array(C.cast(h_comp_ptr, C.POINTER(C.c_uint8)), shape=(tot + 256,))
+    h_out = np.ctypeslib.as_array(C.cast(h_out_ptr, C.POINTER(C.c_uint16)), shape=(raw_bytes // 2,))
+    for b, o in zip(blobs, offs):
+        h_comp[o:o + len(b)] = np.frombuffer(b, np.uint8)
+    log(f"[rank {rank}] setup: {n} images, {tot / 1e6:.1f} MB compressed, ratio {raw_bytes / comp_bytes_alg:.3f}, {time.time() - t_setup:.1f}s")
+
+    # ---- device-resident arm -----------------------------------------------------------------
+    d_comp = torch.empty(tot + 256, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(raw_bytes // 2, dtype=torch.int16, device="cuda")
+    d_comp.copy_(torch.from_numpy(h_comp))
+    dec = api.Decoder(local_rank)
+    dec.begin()
+    for b, o, i in zip(blobs, offs, range(n)):
+        dec.add_pics(h_comp[o:o + len(b)], o, i * W * H)
+    dec.commit()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        dec.run_device(d_comp.data_ptr(), tot, d_out.data_ptr(), raw_bytes // 2, stream)
+
+    for _ in range(args.warmup):
+        step_dev()
+    st = dec.unit_status(stream)
+    assert not any(st), "unit decode failed"
+    # correctness guard inside the bench: image 0 decodes to the generator's pixels
+    synth = importlib.import_module(PKG + ".synth")
+    ref0 = synth.xr_image(1 + 1000 * rank, W, H).ravel()
+    got0 = d_out[: W * H].cpu().numpy().view(np.uint16)
+    assert np.array_equal(got0, ref0), "decoded pixels differ from the source image"
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+
+    # per-kernel breakdown (separate pass, CUDA events between launches on the same stream)
+    dec.set_profiling(True)
+    acc = {}
+    prof_iters = max(1, min(args.steps, 3))
+    for _ in range(prof_iters):
+        step_dev()
+        for name, ms in dec.kernel_times():
+            acc[name] = acc.get(name, 0.0) + ms / prof_iters
+    dec.set_profiling(False)
+    launches = dec.last_launches
+
+    # ---- end-to-end arm: C-ABI host call, pinned host buffers, copies inside the timed region ----
+    bp = (C.c_void_p * n)(*[h_comp_ptr + o for o in offs])
+    ln = (C.c_size_t * n)(*[len(b) for b in blobs])
+    op = (C.c_void_p * n)(*[h_out_ptr + i * raw_per for i in range(n)])
+    cp = (C.c_size_t * n)(*[W * H] * n)
+    stat = (C.c_int * n)()
+
+    def step_e2e():
+        rc = api.lib.micgpu_pics_decompress_batch(n, bp, ln, op, cp, stat)
+        if rc != 0:
+            raise RuntimeError("micgpu_pics_decompress_batch rc=%d: %s" % (rc, api.last_error()))
+
+    e2e_warm = max(1, min(args.warmup, 2))
+    for _ in range(e2e_warm):
+        step_e2e()
+    assert np.array_equal(h_out[: W * H], ref0), "e2e decoded pixels differ from the source image"
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------
+    if dist:
+        t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    total_raw = raw_bytes * world
+    value = total_raw / (ms_dev * 1e-3) / 1e9
+    e2e_val = total_raw / (ms_e2e * 1e-3) / 1e9
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        dom = max(acc.items(), key=lambda kv: kv[1]) if acc else ("none", ms_dev)
+        alg_bytes = comp_bytes_alg + raw_bytes          # per launch of the dominant kernel: this rank's whole batch
+        achieved = alg_bytes / (dom[1] * 1e-3) / 1e9
+        wkey = f"pics8_{nst}state_b{args.batch}"
+        roof = {
+            "bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": ncu_traffic(wkey),
+            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(dom[1], 4),
+            "pipeline_achieved": round(alg_bytes / (ms_dev * 1e-3) / 1e9, 2),
+            "pipeline_frac": round(alg_bytes / (ms_dev * 1e-3) / 1e9 / peak, 4),
+            "stages_ms": {k: round(v, 4) for k, v in acc.items()},
+        }
+        cpu = cpu_baseline_sample(args, nst)
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_dev, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "data": "synthetic",
+            "config": {"workload": f"PICS-8 {nst}-state Delta+RLE+FSE decode, synthetic 2577x2048 12-bit XR, batch of {args.batch} images per GPU "
+                                   f"({args.batch * STRIPS} strips; {args.distinct} distinct images cycled, separate buffers)",
+                       "ratio": round(raw_bytes / comp_bytes_alg, 3), "l2": "inputs larger than L2 (no flush needed)",
+                       "inputs": "encoded on the host with the CPU oracle before timing (CUDA encoder not built yet)"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": comp_bytes_alg, "d2h_bytes_per_step": raw_bytes,
+                    "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps, "api": "micgpu_pics_decompress_batch (pinned host buffers)"},
+            "gpu_launches": launches * args.steps,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(args, nst):
+    """Reference C decoder on this box's host cores, bounded sample (rank 0, any N)."""
+    try:
+        from oracle.oracle import RefTwin
+
+        ref = RefTwin()
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    nthreads = host_threads()
+    sample = max(nthreads, 16)
+    blobs, raw_per = make_inputs(sample, min(sample, 16), nst, 1)
+    name = {2: "two", 4: "four", 8: "eight"}[nst]
+    fn = getattr(ref.lib, f"mic_decompress_{name}_state_simd")
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+    views = [np.frombuffer(b, np.uint8) for b in blobs]
+    outs = [np.empty(W * H, np.uint16) for _ in range(sample)]
+    tasks = []
+    for a, o in zip(views, outs):
+        ns, sh = int.from_bytes(a[12:16].tobytes(), "little"), int.from_bytes(a[16:20].tobytes(), "little")
+        hdr = 20 + 8 * ns
+        for s in range(ns):
+            off = int.from_bytes(a[20 + 8 * s:24 + 8 * s].tobytes(), "little")
+            ln = int.from_bytes(a[24 + 8 * s:28 + 8 * s].tobytes(), "little")
+            tasks.append((a.ctypes.data + hdr + off, ln, o.ctypes.data + s * sh * W * 2, min(sh, H - s * sh)))
+
+    def work(t):
+        if fn(t[0], t[1], t[2], W, t[3]) != 0:
+            raise RuntimeError("reference decoder failed")
+
+    def step():
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            list(ex.map(work, tasks))
+
+    step()
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 5.0 and reps < 50):
+        step()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    # single-thread figure on one image for context
+    t1 = time.perf_counter()
+    for t in tasks[:STRIPS]:
+        work(t)
+    st = time.perf_counter() - t1
+    return {"value": round(sample * raw_per / dt / 1e9, 4), "unit": UNIT, "cores": nthreads, "kind": "reference",
+            "sample": f"{sample} images x {STRIPS} strips x {reps} reps, mic_decompress_{name}_state_simd per strip under {nthreads} host threads",
+            "single_thread_GBps": round(raw_per / st / 1e9, 4)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic images generated per rank")
+    ap.add_argument("--nstates", type=int, default=8, choices=[2, 4, 8], help="FSE state count of the strips")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.distinct = min(args.distinct, args.batch)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,11 @@ int micgpu_decoder_run_device(micgpu_decoder *d, const void *d_comp, size_t comp
 int micgpu_decoder_unit_status(micgpu_decoder *d, int *status, int n, void *cuda_stream);
 /* Kernels launched by the last run_device call. */
 int micgpu_decoder_last_launches(const micgpu_decoder *d);
+/* Per-kernel timing with CUDA events on the launch stream (off by default).  After a run,
+ * micgpu_decoder_kernel_times waits for it and returns the number of kernels, their names
+ * (';'-separated) and durations in milliseconds. */
+int micgpu_decoder_set_profiling(micgpu_decoder *d, int on);
+int micgpu_decoder_kernel_times(micgpu_decoder *d, char *names, size_t names_cap, float *ms, int cap);
 /* Convenience: copy `comp` (host) to the device, run, copy `out_elems` uint16 back. */
 int micgpu_decoder_run_host(micgpu_decoder *d, const uint8_t *comp, size_t comp_bytes, uint16_t *out, size_t out_elems);
 

@@ -60,6 +60,8 @@ lib.micgpu_decoder_unit_count.argtypes = [C.c_void_p]
 lib.micgpu_decoder_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.micgpu_decoder_unit_status.argtypes = [C.c_void_p, _ip, C.c_int, C.c_void_p]
 lib.micgpu_decoder_last_launches.argtypes = [C.c_void_p]
+lib.micgpu_decoder_set_profiling.argtypes = [C.c_void_p, C.c_int]
+lib.micgpu_decoder_kernel_times.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
 lib.micgpu_decoder_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
 lib.micgpu_pics_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_pics_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip]
@@ -226,6 +228,19 @@ class Decoder:
         if rc and raise_on_error:
             _check(rc)
         return list(st)[:n]
+
+    def set_profiling(self, on: bool):
+        _check(lib.micgpu_decoder_set_profiling(self._h, int(on)))
+
+    def kernel_times(self):
+        """[(kernel name, ms)] of the last run (requires set_profiling(True)); waits for the run."""
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n = lib.micgpu_decoder_kernel_times(self._h, names, 4096, ms, 64)
+        if n < 0:
+            _check(n)
+        nm = names.value.decode().split(";") if n else []
+        return [(nm[i], float(ms[i])) for i in range(n)]
 
     def run_host(self, comp: np.ndarray, out: np.ndarray):
         _check(lib.micgpu_decoder_run_host(self._h, comp.ctypes.data, comp.size, out.ctypes.data, out.size))

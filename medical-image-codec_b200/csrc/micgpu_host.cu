@@ -99,6 +99,11 @@ struct micgpu_decoder {
   MicUnit* h_units = nullptr;   // pinned staging copy
   size_t h_units_cap = 0;
   cudaStream_t stream = nullptr;  // used by the host-buffer convenience calls
+  // optional per-kernel timing (CUDA events on the launch stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> ev_names;
+  int ev_used = 0;
 
   ~micgpu_decoder() {
     cudaSetDevice(device);
@@ -106,6 +111,7 @@ struct micgpu_decoder {
     d_D.release(); d_M.release(); d_k1.release(); d_comp.release(); d_out.release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
+    for (auto e : ev) cudaEventDestroy(e);
   }
 };
 
@@ -233,6 +239,18 @@ int plan_commit(micgpu_decoder* d) {
   return 0;
 }
 
+void prof_mark(micgpu_decoder* d, const char* name, cudaStream_t st) {
+  if (!d->profiling) return;
+  if (d->ev_used >= (int)d->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    d->ev.push_back(e);
+    d->ev_names.push_back("");
+  }
+  d->ev_names[d->ev_used] = name;
+  cudaEventRecord(d->ev[d->ev_used++], st);
+}
+
 int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, void* d_out, size_t out_elems, cudaStream_t st) {
   if (!d->committed) return fail(MICGPU_E_HEADER, "decoder plan not committed");
   if (out_elems < d->out_need) return fail(MICGPU_E_SIZE, "output buffer holds %zu elements, plan needs %llu", out_elems, d->out_need);
@@ -247,6 +265,8 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   if (d->m_total) CUDA_TRY(cudaMemsetAsync(d->d_M.p, 0, d->m_total * sizeof(uint32_t), st));
   MicUnit* du = (MicUnit*)d->d_units.p;
   const uint8_t* comp = (const uint8_t*)d_comp;
+  d->ev_used = 0;
+  prof_mark(d, "k_build_tables", st);
   launch_build_tables(du, nu, comp, (uint32_t*)d->d_tabA.p, (uint16_t*)d->d_tabS.p, (uint8_t*)d->d_k1.p, d->k1_stride,
                       d->max_log_all, d->k1_grid, st);
   d->launches++;
@@ -256,24 +276,30 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
     const int n = (int)d->lists[g].size();
     if (n) {
       const AnsPlan& a = d->ans[g];
+      static const char* NAMES[4] = {"k_ans_decode<1>", "k_ans_decode<2>", "k_ans_decode<4>", "k_ans_decode<8>"};
+      prof_mark(d, NAMES[g], st);
       launch_ans_decode(du, dl + loff, n, a.nstates, comp, (const uint32_t*)d->d_tabA.p, (uint16_t*)d->d_states.p, a.max_log,
                         a.mode, a.slots, a.grid, st);
       d->launches++;
     }
     loff += n;
   }
+  prof_mark(d, "k_rle_expand", st);
   launch_rle_expand(du, nu, (const uint16_t*)d->d_states.p, (const uint16_t*)d->d_tabS.p, (uint16_t*)d->d_D.p,
                     (uint32_t*)d->d_M.p, (uint16_t*)d_out, std::min(nu, d->sm_count * 8), st);
   d->launches++;
   if (!d->spatial.empty()) {
+    prof_mark(d, "k_delta_wavefront", st);
     launch_delta_wavefront(du, dl + loff, (int)d->spatial.size(), (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p,
                            (uint16_t*)d_out, d->max_w, d->max_h, st);
     d->launches++;
   }
   for (const TemporalGroup& t : d->temporal) {
+    prof_mark(d, "k_temporal_accumulate", st);
     launch_temporal_accumulate((uint16_t*)d_out + t.out_off, t.fpx, t.nframes, d->sm_count, st);
     d->launches++;
   }
+  prof_mark(d, "end", st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -533,6 +559,34 @@ int micgpu_decoder_unit_status(micgpu_decoder* d, int* status, int n, void* cuda
 }
 
 int micgpu_decoder_last_launches(const micgpu_decoder* d) { return d ? d->launches : 0; }
+
+int micgpu_decoder_set_profiling(micgpu_decoder* d, int on) {
+  if (!d) return fail(MICGPU_E_HEADER, "null decoder");
+  std::lock_guard<std::mutex> lk(d->mu);
+  d->profiling = on != 0;
+  return 0;
+}
+
+int micgpu_decoder_kernel_times(micgpu_decoder* d, char* names, size_t names_cap, float* ms, int cap) {
+  if (!d) return fail(MICGPU_E_HEADER, "null decoder");
+  std::lock_guard<std::mutex> lk(d->mu);
+  const int n = d->ev_used > 0 ? d->ev_used - 1 : 0;
+  if (n == 0) return 0;
+  CUDA_TRY(cudaEventSynchronize(d->ev[d->ev_used - 1]));
+  std::string joined;
+  for (int i = 0; i < n && i < cap; i++) {
+    float t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&t, d->ev[i], d->ev[i + 1]));
+    ms[i] = t;
+    if (i) joined += ";";
+    joined += d->ev_names[i];
+  }
+  if (names && names_cap) {
+    strncpy(names, joined.c_str(), names_cap - 1);
+    names[names_cap - 1] = 0;
+  }
+  return std::min(n, cap);
+}
 
 int micgpu_decoder_run_host(micgpu_decoder* d, const uint8_t* comp, size_t comp_bytes, uint16_t* out, size_t out_elems) {
   if (!d) return fail(MICGPU_E_HEADER, "null decoder");

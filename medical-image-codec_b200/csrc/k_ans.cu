@@ -10,6 +10,10 @@
 // (A,B,..), so within a round lane k reads its nbBits field right below the
 // fields of lanes < k: the offset is an exclusive prefix sum of nbBits over the
 // slot, obtained with one or two redux.sync.or over byte-packed lanes.
+// One warp hosts exactly one slot (lanes >= N exit): with several slots per warp the
+// partial-mask collectives are serialised by the compiler (WARPSYNC.COLLECTIVE) and a
+// lock-step multi-slot warp has too little thread-level parallelism for this
+// latency-bound chain -- measured 54 ms and 27 ms versus this layout (profiles/).
 // The decode table lives in shared memory (4 B or 2 B per cell) and the
 // bitstream is staged through a 128 B per-slot shared-memory ring that is
 // refilled from registers loaded one 64 B half ahead (plus an L2 prefetch
@@ -27,47 +31,53 @@
 
 namespace micgpu {
 
-constexpr int K2_THREADS = 128;
 constexpr int RING_WORDS = 32;
 constexpr int HALF_WORDS = 16;
 
+// Exclusive prefix sum and total of nb (<= 16) over the N active lanes of the warp.  Lane k drops
+// its nb into byte (k mod 4) of one of two words; one redux.sync.or per word hands every lane the
+// packed counts of the whole slot, and the prefix is a masked horizontal byte sum.  The mask is
+// the warp's full active mask (lanes >= N have exited), so the redux is a single instruction.
 template <int N>
-__device__ __forceinline__ uint32_t slot_prefix(uint32_t nb, int k, unsigned slotmask, uint32_t* tot) {
+__device__ __forceinline__ uint32_t slot_prefix(uint32_t nb, int k, uint32_t* tot) {
+  constexpr unsigned MASK = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
   if (N == 1) {
     *tot = nb;
     return 0;
   } else if (N <= 4) {
-    uint32_t r = __reduce_or_sync(slotmask, nb << (8 * k));
+    const uint32_t r = __reduce_or_sync(MASK, nb << (8 * k));
     *tot = (r * 0x01010101u) >> 24;
-    uint32_t below = r & ((1u << (8 * k)) - 1u);
-    return (below * 0x01010101u) >> 24;
+    return ((r & ((1u << (8 * k)) - 1u)) * 0x01010101u) >> 24;
   } else {
-    uint32_t r0 = __reduce_or_sync(slotmask, k < 4 ? nb << (8 * k) : 0u);
-    uint32_t r1 = __reduce_or_sync(slotmask, k >= 4 ? nb << (8 * (k - 4)) : 0u);
-    uint32_t s0 = (r0 * 0x01010101u) >> 24;
+    const uint32_t r0 = __reduce_or_sync(MASK, k < 4 ? nb << (8 * k) : 0u);
+    const uint32_t r1 = __reduce_or_sync(MASK, k >= 4 ? nb << (8 * (k - 4)) : 0u);
+    const uint32_t s0 = (r0 * 0x01010101u) >> 24;
     *tot = s0 + ((r1 * 0x01010101u) >> 24);
-    uint32_t m0 = k < 4 ? ((1u << (8 * k)) - 1u) : 0xffffffffu;
-    uint32_t m1 = k <= 4 ? 0u : ((1u << (8 * (k - 4))) - 1u);
+    const uint32_t m0 = k < 4 ? ((1u << (8 * k)) - 1u) : 0xffffffffu;
+    const uint32_t m1 = k <= 4 ? 0u : ((1u << (8 * (k - 4))) - 1u);
     return (((r0 & m0) * 0x01010101u) >> 24) + (((r1 & m1) * 0x01010101u) >> 24);
   }
 }
 
+// One warp = one slot = one unit at a time; only the first N lanes stay alive (lane k owns
+// state k).  The state->state chain is latency bound and a warp issues in order, so throughput
+// comes from having many warps (units) resident per SM, not from filling lanes.
 template <int N, int MODE>
-__global__ void __launch_bounds__(K2_THREADS)
+__global__ void __launch_bounds__(1024)
 k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
              const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots_per_cta) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int PW = HALF_WORDS / N;  // ring words each lane carries for the in-flight half
-  const int tid = threadIdx.x;
-  const int slot = tid / N;
-  const int k = tid % N;
-  const int lane = tid & 31;
-  if (slot >= slots_per_cta) return;
-  const unsigned slotmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane - k));
+  constexpr unsigned MASK = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
+  const int slot = threadIdx.x >> 5;
+  const int k = threadIdx.x & 31;
+  if (k >= N) return;
 
   const size_t tbytes = MODE == 2 ? 0 : ((size_t)(1u << max_log) * (MODE == 0 ? 4 : 2));
   uint8_t* mytab = smem + (size_t)slot * tbytes;
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)slots_per_cta * tbytes) + slot * RING_WORDS;
+  const uint32_t* T32 = reinterpret_cast<const uint32_t*>(mytab);
+  const uint16_t* T16 = reinterpret_cast<const uint16_t*>(mytab);
 
   for (int li = blockIdx.x * slots_per_cta + slot; li < nlist; li += gridDim.x * slots_per_cta) {
     MicUnit* U = &units[list[li]];
@@ -75,7 +85,7 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
     const int L = (int)U->table_log;
     const uint32_t S = 1u << L;
     const uint32_t* A = tabA + U->tab_off;
-    __syncwarp(slotmask);
+    __syncwarp(MASK);
     // ---- stage the decode table ------------------------------------------
     if (MODE == 0) {
       uint4* T4 = reinterpret_cast<uint4*>(mytab);
@@ -84,16 +94,15 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
     } else if (MODE == 1) {
       uint2* T2 = reinterpret_cast<uint2*>(mytab);
       const uint4* A4 = reinterpret_cast<const uint4*>(A);
+#pragma unroll 4
       for (uint32_t i = k; i < S / 4; i += N) {
-        uint4 e = A4[i];
+        const uint4 e = A4[i];
         // nextState = (newState + S) >> nbBits  (inverse of fsedecompressu16.go:250-251)
-        uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
-        uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
+        const uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
+        const uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
         T2[i] = make_uint2(n0 | (n1 << 16), n2 | (n3 << 16));
       }
     }
-    const uint32_t* T32 = reinterpret_cast<const uint32_t*>(mytab);
-    const uint16_t* T16 = reinterpret_cast<const uint16_t*>(mytab);
 
     // ---- bitstream geometry ----------------------------------------------
     const uint8_t* bs = comp + U->comp_off + U->bits_off;
@@ -102,19 +111,19 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
     const uint32_t* wbase = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)63);
     const uint32_t shift = (uint32_t)(addr & 63) * 8;      // first data bit in ring coordinates
     const uint32_t lastb = bs[blen - 1];                   // non-zero (checked by K1)
-    uint32_t P = shift + 8u * (blen - 1) + (31u - __clz(lastb));  // unread bits are [shift, P)
+    uint32_t P = shift + 8u * (blen - 1) + (31u - __clz(lastb | 1u));  // unread bits are [shift, P)
 
     uint32_t pre[PW];
     auto load_half = [&](int hh) {
       if (hh >= 0) {
         const uint32_t* src = wbase + hh * HALF_WORDS + k * PW;
         if (PW == 2) {
-          uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
           pre[0] = v.x; pre[1] = v.y;
         } else {
 #pragma unroll
           for (int i = 0; i < PW / 4; i++) {
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
             pre[4 * i] = v.x; pre[4 * i + 1] = v.y; pre[4 * i + 2] = v.z; pre[4 * i + 3] = v.w;
           }
         }
@@ -131,16 +140,17 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
     load_half(cur_half); store_half(cur_half);
     load_half(cur_half - 1); store_half(cur_half - 1);
     load_half(cur_half - 2);
-    __syncwarp(slotmask);
+    __syncwarp(MASK);
 
     auto extract = [&](uint32_t lo, uint32_t nb) -> uint32_t {
-      uint32_t wi = lo >> 5;
-      uint32_t w0 = ring[wi & (RING_WORDS - 1)], w1 = ring[(wi + 1) & (RING_WORDS - 1)];
+      const uint32_t wi = lo >> 5;
+      const uint32_t w0 = ring[wi & (RING_WORDS - 1)], w1 = ring[(wi + 1) & (RING_WORDS - 1)];
       return __funnelshift_r(w0, w1, lo & 31) & ((1u << nb) - 1u);
     };
+    // consume `tot` bits (warp-uniform)
     auto advance = [&](uint32_t tot) {
       P -= tot;
-      int h = (int)((P - 1) >> 5) / HALF_WORDS;
+      const int h = (int)((P - 1) >> 5) / HALF_WORDS;
       if (P > shift && h < cur_half) {
         // half cur_half is dead: overwrite it with half cur_half-2 (already in registers)
         store_half(cur_half - 2);
@@ -148,15 +158,15 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
         load_half(cur_half - 2);
         if (k == 0 && cur_half >= 6)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + (cur_half - 6) * HALF_WORDS));
-        __syncwarp(slotmask);
       }
+      __syncwarp(MASK);
     };
 
     int err = 0;
     uint32_t state = 0;
     // ---- initial states: A first, tableLog bits each (fse8state.go:239-250) ----
     {
-      uint32_t tot = (uint32_t)(N * L);
+      const uint32_t tot = (uint32_t)(N * L);
       if (P - shift < tot) {
         err = 1;
       } else {
@@ -172,9 +182,9 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
       const uint32_t cap = U->sym_cap;
       while (!err) {
         uint32_t nb, ns;
-        if (MODE == 0) { uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
-        else if (MODE == 1) { uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }
-        else { uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
+        if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
+        else if (MODE == 1) { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); ns = (nx << nb) - S; }
+        else { const uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
         if (P == shift && nb > 0) {      // decoderU16.finished()
           if (state != 0) {
             if (nsym >= cap) { err = 2; break; }
@@ -185,26 +195,27 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
         if (nsym >= cap) { err = 2; break; }
         out[nsym++] = (uint16_t)state;
         if (P - shift < nb) { err = 1; break; }   // partial over-read -> io.ErrUnexpectedEOF
-        uint32_t bits = nb ? extract(P - nb, nb) : 0u;
+        const uint32_t bits = nb ? extract(P - nb, nb) : 0u;
         state = ns + bits;
         advance(nb);
       }
     } else {
       const uint32_t count = U->count;
       if (count > U->sym_cap) err = 2;
-      for (uint32_t base = 0; base < count && !err; base += N) {
+      uint16_t* op = out + k;
+      for (uint32_t base = 0; base < count && !err; base += N, op += N) {
         const bool active = base + (uint32_t)k < count;
         uint32_t nb, ns;
-        if (MODE == 0) { uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
-        else if (MODE == 1) { uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }
-        else { uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
+        if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
+        else if (MODE == 1) { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); ns = (nx << nb) - S; }
+        else { const uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
         if (!active) nb = 0;
         uint32_t tot;
-        const uint32_t before = slot_prefix<N>(nb, k, slotmask, &tot);
+        const uint32_t before = slot_prefix<N>(nb, k, &tot);
         if (P - shift < tot) { err = 1; break; }
         const uint32_t bits = nb ? extract(P - before - nb, nb) : 0u;
         if (active) {
-          out[base + k] = (uint16_t)state;
+          *op = (uint16_t)state;
           state = ns + bits;
         }
         advance(tot);
@@ -228,7 +239,7 @@ static void launch_one(MicUnit* d_units, const int* d_list, int nlist, const uin
                        uint16_t* d_states, int max_log, int slots, int grid, cudaStream_t st) {
   size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
   cudaFuncSetAttribute(k_ans_decode<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_ans_decode<N, MODE><<<grid, K2_THREADS, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
+  k_ans_decode<N, MODE><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
 }
 
 template <int N>

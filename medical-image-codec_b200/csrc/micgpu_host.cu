@@ -176,6 +176,13 @@ int plan_commit(micgpu_decoder* d) {
     d->lists[nstates_index(u.nstates)].push_back((int)i);
     d->out_need = std::max(d->out_need, u.out_off + px);
   }
+  // slots of one warp run in lockstep to the longest unit: keep similar lengths together
+  for (auto& l : d->lists)
+    std::stable_sort(l.begin(), l.end(), [&](int a, int b) {
+      const MicUnit &ua = d->units[a], &ub = d->units[b];
+      const unsigned long long ca = ua.nstates > 1 ? ua.count : ua.comp_len, cb = ub.nstates > 1 ? ub.count : ub.comp_len;
+      return ca > cb;
+    });
   // ---- K2 launch shapes ----------------------------------------------------
   static const int NS[4] = {1, 2, 4, 8};
   const size_t budget = d->smem_optin;
@@ -187,7 +194,7 @@ int plan_commit(micgpu_decoder* d) {
     int ml = 5;
     for (int i : d->lists[g]) ml = std::max(ml, (int)d->units[i].table_log);
     a.max_log = ml;
-    const int slots_max = 128 / a.nstates;
+    const int slots_max = 32;   // one slot per warp, at most 32 warps per CTA
     const int need_per_sm = (n + d->sm_count - 1) / d->sm_count;
     auto fit = [&](int mode) {
       size_t per = ans_decode_smem_bytes(ml, mode, 1);
@@ -201,7 +208,7 @@ int plan_commit(micgpu_decoder* d) {
     a.slots = slots;
     // CTAs per SM by shared memory (1 KB reserved per CTA) and by 2048 threads
     const size_t per_cta = ans_decode_smem_bytes(ml, mode, slots) + 1024;
-    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>((228 * 1024) / per_cta, 16));
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>((228 * 1024) / per_cta, (size_t)std::max(1, 64 / slots)));
     a.grid = std::min((n + slots - 1) / slots, d->sm_count * ctas_per_sm);
   }
   // ---- K1 scratch ------------------------------------------------------------

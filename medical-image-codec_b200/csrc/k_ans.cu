@@ -31,28 +31,34 @@
 
 namespace micgpu {
 
-constexpr int RING_WORDS = 32;
+constexpr int RING_WORDS = 32;    // ring[32] mirrors ring[0] so word pairs never wrap
+constexpr int RING_STRIDE = 36;   // words reserved per slot (16 B aligned)
 constexpr int HALF_WORDS = 16;
 
-// Exclusive prefix sum and total of nb (<= 16) over the N active lanes of the warp.  Lane k drops
-// its nb into byte (k mod 4) of one of two words; one redux.sync.or per word hands every lane the
-// packed counts of the whole slot, and the prefix is a masked horizontal byte sum.  The mask is
-// the warp's full active mask (lanes >= N have exited), so the redux is a single instruction.
-template <int N>
+// Exclusive prefix sum and total of nb over the N active lanes of the warp (lanes >= N have
+// exited, so MASK is the warp's whole active mask and each redux is one instruction).
+// NB4: nb <= 15 (tableLog <= 15) -> lane k drops nb into nibble k of ONE word; redux.or hands every
+// lane all counts, the prefix is a masked horizontal nibble sum; the total is a redux.add.
+template <int N, bool NB4>
 __device__ __forceinline__ uint32_t slot_prefix(uint32_t nb, int k, uint32_t* tot) {
   constexpr unsigned MASK = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
   if (N == 1) {
     *tot = nb;
     return 0;
+  } else if (NB4) {
+    const uint32_t r = __reduce_or_sync(MASK, nb << (4 * k));
+    *tot = __reduce_add_sync(MASK, nb);
+    const uint32_t x = r & ((1u << (4 * k)) - 1u);
+    const uint32_t t = (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu);
+    return (t * 0x01010101u) >> 24;
   } else if (N <= 4) {
     const uint32_t r = __reduce_or_sync(MASK, nb << (8 * k));
-    *tot = (r * 0x01010101u) >> 24;
+    *tot = __reduce_add_sync(MASK, nb);
     return ((r & ((1u << (8 * k)) - 1u)) * 0x01010101u) >> 24;
   } else {
     const uint32_t r0 = __reduce_or_sync(MASK, k < 4 ? nb << (8 * k) : 0u);
     const uint32_t r1 = __reduce_or_sync(MASK, k >= 4 ? nb << (8 * (k - 4)) : 0u);
-    const uint32_t s0 = (r0 * 0x01010101u) >> 24;
-    *tot = s0 + ((r1 * 0x01010101u) >> 24);
+    *tot = __reduce_add_sync(MASK, nb);
     const uint32_t m0 = k < 4 ? ((1u << (8 * k)) - 1u) : 0xffffffffu;
     const uint32_t m1 = k <= 4 ? 0u : ((1u << (8 * (k - 4))) - 1u);
     return (((r0 & m0) * 0x01010101u) >> 24) + (((r1 & m1) * 0x01010101u) >> 24);
@@ -62,7 +68,7 @@ __device__ __forceinline__ uint32_t slot_prefix(uint32_t nb, int k, uint32_t* to
 // One warp = one slot = one unit at a time; only the first N lanes stay alive (lane k owns
 // state k).  The state->state chain is latency bound and a warp issues in order, so throughput
 // comes from having many warps (units) resident per SM, not from filling lanes.
-template <int N, int MODE>
+template <int N, int MODE, bool NB4>
 __global__ void __launch_bounds__(1024)
 k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
              const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots_per_cta) {
@@ -75,7 +81,7 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
 
   const size_t tbytes = MODE == 2 ? 0 : ((size_t)(1u << max_log) * (MODE == 0 ? 4 : 2));
   uint8_t* mytab = smem + (size_t)slot * tbytes;
-  uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)slots_per_cta * tbytes) + slot * RING_WORDS;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)slots_per_cta * tbytes) + slot * RING_STRIDE;
   const uint32_t* T32 = reinterpret_cast<const uint32_t*>(mytab);
   const uint16_t* T16 = reinterpret_cast<const uint16_t*>(mytab);
 
@@ -111,7 +117,7 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
     const uint32_t* wbase = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)63);
     const uint32_t shift = (uint32_t)(addr & 63) * 8;      // first data bit in ring coordinates
     const uint32_t lastb = bs[blen - 1];                   // non-zero (checked by K1)
-    uint32_t P = shift + 8u * (blen - 1) + (31u - __clz(lastb | 1u));  // unread bits are [shift, P)
+    int P = (int)(shift + 8u * (blen - 1) + (31u - __clz(lastb | 1u)));  // unread bits are [shift, P); < 2^31 (frames < 256 MB)
 
     uint32_t pre[PW];
     auto load_half = [&](int hh) {
@@ -135,31 +141,34 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
     auto store_half = [&](int hh) {
 #pragma unroll
       for (int i = 0; i < PW; i++) ring[(hh * HALF_WORDS + k * PW + i) & (RING_WORDS - 1)] = pre[i];
+      if (k == 0 && (hh & 1) == 0) ring[RING_WORDS] = pre[0];   // mirror of ring[0]
     };
-    int cur_half = (int)((P - 1) >> 5) / HALF_WORDS;
+    int cur_half = ((P - 1) >> 5) / HALF_WORDS;
+    int cross = cur_half * (HALF_WORDS * 32);   // P <= cross  <=>  the top unread bit left half cur_half
     load_half(cur_half); store_half(cur_half);
     load_half(cur_half - 1); store_half(cur_half - 1);
     load_half(cur_half - 2);
     __syncwarp(MASK);
 
-    auto extract = [&](uint32_t lo, uint32_t nb) -> uint32_t {
-      const uint32_t wi = lo >> 5;
-      const uint32_t w0 = ring[wi & (RING_WORDS - 1)], w1 = ring[(wi + 1) & (RING_WORDS - 1)];
-      return __funnelshift_r(w0, w1, lo & 31) & ((1u << nb) - 1u);
+    const uint8_t* ringb = reinterpret_cast<const uint8_t*>(ring);
+    // bits [lo, lo+nb) of the stream; nb == 0 yields 0
+    auto extract = [&](int lo, uint32_t nb) -> uint32_t {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + (((uint32_t)lo >> 3) & 0x7Cu));
+      return __funnelshift_r(w[0], w[1], (uint32_t)lo & 31u) & ((1u << nb) - 1u);
     };
     // consume `tot` bits (warp-uniform)
     auto advance = [&](uint32_t tot) {
-      P -= tot;
-      const int h = (int)((P - 1) >> 5) / HALF_WORDS;
-      if (P > shift && h < cur_half) {
+      P -= (int)tot;
+      if (P <= cross) {
         // half cur_half is dead: overwrite it with half cur_half-2 (already in registers)
         store_half(cur_half - 2);
         cur_half -= 1;
+        cross -= HALF_WORDS * 32;
         load_half(cur_half - 2);
         if (k == 0 && cur_half >= 6)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + (cur_half - 6) * HALF_WORDS));
+        __syncwarp(MASK);
       }
-      __syncwarp(MASK);
     };
 
     int err = 0;
@@ -167,10 +176,10 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
     // ---- initial states: A first, tableLog bits each (fse8state.go:239-250) ----
     {
       const uint32_t tot = (uint32_t)(N * L);
-      if (P - shift < tot) {
+      if ((uint32_t)P - shift < tot) {
         err = 1;
       } else {
-        state = extract(P - (uint32_t)(k + 1) * L, (uint32_t)L);
+        state = extract(P - (k + 1) * L, (uint32_t)L);
         advance(tot);
       }
     }
@@ -185,7 +194,7 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
         if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
         else if (MODE == 1) { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); ns = (nx << nb) - S; }
         else { const uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
-        if (P == shift && nb > 0) {      // decoderU16.finished()
+        if (P == (int)shift && nb > 0) {      // decoderU16.finished()
           if (state != 0) {
             if (nsym >= cap) { err = 2; break; }
             out[nsym++] = (uint16_t)state;  // final()
@@ -194,8 +203,8 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
         }
         if (nsym >= cap) { err = 2; break; }
         out[nsym++] = (uint16_t)state;
-        if (P - shift < nb) { err = 1; break; }   // partial over-read -> io.ErrUnexpectedEOF
-        const uint32_t bits = nb ? extract(P - nb, nb) : 0u;
+        if ((uint32_t)P - shift < nb) { err = 1; break; }   // partial over-read -> io.ErrUnexpectedEOF
+        const uint32_t bits = extract(P - (int)nb, nb);
         state = ns + bits;
         advance(nb);
       }
@@ -203,23 +212,39 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
       const uint32_t count = U->count;
       if (count > U->sym_cap) err = 2;
       uint16_t* op = out + k;
-      for (uint32_t base = 0; base < count && !err; base += N, op += N) {
-        const bool active = base + (uint32_t)k < count;
+      // One round = N symbols.  The loop body carries no error branch: an over-read only makes P run
+      // below `shift`, which is remembered in `under` and reported after the loop (reads stay inside the ring).
+      int under = 0;
+      const uint32_t full = err ? 0u : count / N;
+      for (uint32_t r = 0; r < full; r++, op += N) {
         uint32_t nb, ns;
         if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
         else if (MODE == 1) { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); ns = (nx << nb) - S; }
         else { const uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
+        uint32_t tot;
+        const uint32_t before = slot_prefix<N, NB4>(nb, k, &tot);
+        const uint32_t bits = extract(P - (int)before - (int)nb, nb);
+        *op = (uint16_t)state;
+        state = ns + bits;
+        advance(tot);
+        under |= P - (int)shift;          // sign bit set once P < shift
+      }
+      const uint32_t tail = err ? 0u : count - full * N;
+      if (tail) {
+        const bool active = (uint32_t)k < tail;
+        uint32_t nb, ns;
+        if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
+        else if (MODE == 1) { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); ns = (nx << nb) - S; }
+        else { const uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
+        (void)ns;
         if (!active) nb = 0;
         uint32_t tot;
-        const uint32_t before = slot_prefix<N>(nb, k, &tot);
-        if (P - shift < tot) { err = 1; break; }
-        const uint32_t bits = nb ? extract(P - before - nb, nb) : 0u;
-        if (active) {
-          *op = (uint16_t)state;
-          state = ns + bits;
-        }
-        advance(tot);
+        slot_prefix<N, NB4>(nb, k, &tot);
+        if (active) *op = (uint16_t)state;
+        P -= (int)tot;
+        under |= P - (int)shift;
       }
+      if (under < 0 && !err) err = 1;
       nsym = count;
     }
     if (k == 0) {
@@ -231,15 +256,20 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
 
 size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta) {
   size_t t = smem_mode == 2 ? 0 : ((size_t)(1u << max_log) * (smem_mode == 0 ? 4 : 2));
-  return (size_t)slots_per_cta * (t + RING_WORDS * 4);
+  return (size_t)slots_per_cta * (t + RING_STRIDE * 4);
 }
 
 template <int N, int MODE>
 static void launch_one(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, const uint32_t* d_tabA,
                        uint16_t* d_states, int max_log, int slots, int grid, cudaStream_t st) {
   size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
-  cudaFuncSetAttribute(k_ans_decode<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_ans_decode<N, MODE><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
+  if (max_log <= 15) {
+    cudaFuncSetAttribute(k_ans_decode<N, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_ans_decode<N, MODE, true><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
+  } else {
+    cudaFuncSetAttribute(k_ans_decode<N, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_ans_decode<N, MODE, false><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
+  }
 }
 
 template <int N>

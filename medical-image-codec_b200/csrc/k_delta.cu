@@ -1,35 +1,61 @@
-// k_delta.cu -- K4: inverse avg(top,left) predictor as an anti-diagonal wavefront.
+// k_delta.cu -- K4: inverse avg(top,left) predictor as a blocked anti-diagonal wavefront.
 //
 // Replaces DeltaRleDecompressU16.DecodeNextSymbol[NC] (deltarlecompressu16.go:102-128)
-// and the C twin's delta_decode_simd.  out = ((left+top)>>1) + diff is not
-// linear in `left`, so there is no closed-form row scan; instead thread y owns
-// row y and at step t reconstructs pixel (y, t-y): `left` is the thread's own
-// previous result, `top` arrives from lane-1 by shuffle (it was produced one
-// step earlier).  Warps chain through one shared-memory boundary row each,
-// gated by a progress counter every K4_GATE columns, so a 256-row strip takes
-// ~W+H steps.  Units taller than the CTA are processed in passes of blockDim
-// rows; the last row of a pass seeds the next one.
-//
-// Inputs: residual plane D (row pitch wp, 16 B aligned rows; a literal pixel
-// holds its raw value) and literal bit mask M (wp/32 words per row), both
-// produced by K3.  Output rows are packed (pitch W): pixels are gathered eight
-// at a time and written with 16 B stores once the row address is aligned.
+// and the C twin's delta_decode_simd.  out = ((left+top)>>1) + diff is not linear in
+// `left`, so there is no closed-form row scan.  Row 0 IS linear (out = left + diff, with
+// literal pixels as resets) and is reconstructed by a segmented warp scan; after that
+// thread y owns row y and walks it in blocks of 8 pixels, one block per step, trailing the
+// row above by one block (two when the 16-byte phase of the rows wraps):
+//   * `left` is the thread's own previous pixel, the 8 `top` pixels arrive as four packed
+//     registers shuffled from lane-1 (the block it finished in the previous step) and are
+//     re-phased with the previously received block by the row-to-row alignment step
+//     delta = W mod 8 (a warp-uniform funnel shift);
+//   * rows are addressed in "padded" coordinates p = a_y + x with a_y the 8-pixel phase of
+//     the OUTPUT row address, so every block is one aligned 16 B load of the residual plane D
+//     (K3 writes D with the same phase) and one aligned 16 B store of pixels;
+//   * warps chain through one shared-memory boundary row each, gated by a block counter.
+// The 8 pixels of a block are unrolled with compile-time register selection: ~11
+// instructions per pixel per warp step versus ~130 for a one-pixel-per-step wavefront
+// (measured, profiles/), at the price of a longer pipeline fill (8 columns of skew per row).
 #include "mic_device.cuh"
 
 namespace micgpu {
 
-constexpr int K4_GATE = 8;
+struct Grp {
+  uint32_t w[4];  // 8 packed u16, element j in bits 16*(j&1) of w[j>>1]
+};
 
-__device__ __forceinline__ int ld_volatile_s32(const int* p) {
-  return *reinterpret_cast<const volatile int*>(p);
+__device__ __forceinline__ uint32_t fs16(uint32_t a, uint32_t b) { return __funnelshift_r(a, b, 16); }
+
+// out = concat(p, c)[8-delta .. 16-delta) in u16 units (delta warp-uniform)
+__device__ __forceinline__ Grp rephase(const Grp& p, const Grp& c, int delta) {
+  Grp o;
+  switch (delta) {
+    case 0: o = c; break;
+    case 1: o.w[0] = fs16(p.w[3], c.w[0]); o.w[1] = fs16(c.w[0], c.w[1]); o.w[2] = fs16(c.w[1], c.w[2]); o.w[3] = fs16(c.w[2], c.w[3]); break;
+    case 2: o.w[0] = p.w[3]; o.w[1] = c.w[0]; o.w[2] = c.w[1]; o.w[3] = c.w[2]; break;
+    case 3: o.w[0] = fs16(p.w[2], p.w[3]); o.w[1] = fs16(p.w[3], c.w[0]); o.w[2] = fs16(c.w[0], c.w[1]); o.w[3] = fs16(c.w[1], c.w[2]); break;
+    case 4: o.w[0] = p.w[2]; o.w[1] = p.w[3]; o.w[2] = c.w[0]; o.w[3] = c.w[1]; break;
+    case 5: o.w[0] = fs16(p.w[1], p.w[2]); o.w[1] = fs16(p.w[2], p.w[3]); o.w[2] = fs16(p.w[3], c.w[0]); o.w[3] = fs16(c.w[0], c.w[1]); break;
+    case 6: o.w[0] = p.w[1]; o.w[1] = p.w[2]; o.w[2] = p.w[3]; o.w[3] = c.w[0]; break;
+    default: o.w[0] = fs16(p.w[0], p.w[1]); o.w[1] = fs16(p.w[1], p.w[2]); o.w[2] = fs16(p.w[2], p.w[3]); o.w[3] = fs16(p.w[3], c.w[0]); break;
+  }
+  return o;
 }
+
+template <int J>
+__device__ __forceinline__ uint32_t grp_get(const Grp& g) {
+  return (J & 1) ? (g.w[J >> 1] >> 16) : (g.w[J >> 1] & 0xFFFFu);
+}
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 __global__ void __launch_bounds__(1024)
 k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist,
                   const uint16_t* __restrict__ D, const uint32_t* __restrict__ M, uint16_t* __restrict__ out,
                   int brow_pitch) {
-  extern __shared__ __align__(16) uint16_t s_brow[];  // (nwarps+1) boundary rows of brow_pitch elements
-  __shared__ int s_prog[33];                          // s_prog[w+1]: columns finished by warp w's last lane
+  extern __shared__ __align__(16) uint16_t s_brow[];  // (nwarps+1) boundary rows, padded coordinates
+  __shared__ int s_prog[33];                          // s_prog[w+1]: blocks finished by warp w's last lane
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -38,114 +64,161 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
   const int W = (int)U->width, H = (int)U->height;
   const unsigned wp = U->wp;
   const int thr = (int)U->thr;
+  const int align0 = (int)U->align0;
+  const int delta = W & 7;
   const uint16_t* Du = D + U->d_off;
   const uint32_t* Mu = M + U->m_off;
   uint16_t* Ou = out + U->out_off;
 
-  const int passes = (H + (int)blockDim.x - 1) / (int)blockDim.x;
-  for (int p = 0; p < passes; p++) {
-    const int y = p * (int)blockDim.x + tid;
-    const int wy0 = p * (int)blockDim.x + warp * 32;   // first row of this warp
-    __syncthreads();
-    if (p > 0) {
-      for (int i = tid; i < W; i += blockDim.x) s_brow[i] = s_brow[(size_t)nwarps * brow_pitch + i];
+  // ---------------- row 0: segmented prefix sum (warp 0) -----------------------------------
+  if (warp == 0) {
+    const int a0 = align0 & 7;
+    unsigned carry = 0;
+    for (int base = 0; base < W; base += 32) {
+      const int x = base + lane;
+      const bool valid = x < W;
+      unsigned d = 0, flag = 0;
+      if (valid) {
+        d = Du[a0 + x];
+        flag = (Mu[(a0 + x) >> 5] >> ((a0 + x) & 31)) & 1u;
+      }
+      unsigned val = flag ? d : (d - (unsigned)thr);   // row 0: pred = left (0 at x = 0)
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned v2 = __shfl_up_sync(0xffffffffu, val, off);
+        const unsigned f2 = __shfl_up_sync(0xffffffffu, flag, off);
+        if (lane >= off) {
+          if (!flag) val += v2;
+          flag |= f2;
+        }
+      }
+      if (!flag) val += carry;
+      val &= 0xFFFFu;
+      if (valid) {
+        Ou[x] = (uint16_t)val;
+        s_brow[a0 + x] = (uint16_t)val;
+      }
+      carry = __shfl_sync(0xffffffffu, val, 31);
     }
-    if (tid <= nwarps) s_prog[tid] = tid == 0 ? W : 0;
+  }
+
+  const int rows_per_pass = (int)blockDim.x;
+  const int passes = (H - 1 + rows_per_pass - 1) / rows_per_pass;
+  for (int p = 0; p < passes; p++) {
+    const int y = 1 + p * rows_per_pass + tid;
+    const int wy0 = 1 + p * rows_per_pass + warp * 32;   // first row of this warp
+    __syncthreads();
+    if (p > 0)
+      for (int i = tid; i < brow_pitch; i += blockDim.x) s_brow[i] = s_brow[(size_t)nwarps * brow_pitch + i];
+    if (tid <= nwarps) s_prog[tid] = tid == 0 ? 0x7fffffff : 0;
     __syncthreads();
     if (wy0 >= H) continue;   // whole warp idle this pass (still reaches the barriers above)
 
     const bool row_active = y < H;
-    const bool has_top = wy0 > 0;                       // lane 0 has a row above it
+    const int a = (align0 + (y & 7) * delta) & 7;             // phase of this row: (align0 + y*W) mod 8
+    const int nblk = row_active ? (a + W + 7) >> 3 : 0;
+    const int wrap = (delta != 0 && a < delta) ? 1 : 0;       // phase wrapped relative to row y-1
+    const int nblk_prev = (((a - delta) & 7) + W + 7) >> 3;   // blocks of row y-1
+    // start step: lane l trails lane l-1 by one block, two when the phase wrapped
+    int s = lane == 0 ? 0 : 1 + wrap;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t2 = __shfl_up_sync(0xffffffffu, s, off);
+      if (lane >= off) s += t2;
+    }
+    const int T = __reduce_max_sync(0xffffffffu, s + nblk);
+
     const uint16_t* brow_in = s_brow + (size_t)warp * brow_pitch;
     uint16_t* brow_out = s_brow + (size_t)(warp + 1) * brow_pitch;
     const int* prog_in = &s_prog[warp];
     int* prog_out = &s_prog[warp + 1];
 
-    const uint16_t* Drow = Du + (size_t)(row_active ? y : 0) * wp;
-    const uint32_t* Mrow = Mu + (size_t)(row_active ? y : 0) * (wp >> 5);
-    uint16_t* Orow = Ou + (size_t)(row_active ? y : 0) * W;
-    const int ea = (int)((reinterpret_cast<uintptr_t>(Orow) >> 1) & 7);
-    const int hx = (8 - ea) & 7;                                   // first 16 B aligned column
-    const int tail = hx <= W ? hx + ((W - hx) >> 3) * 8 : 0;       // columns >= tail are written scalar
-    const int headx = hx <= W ? hx : W;
+    const size_t yr = (size_t)(row_active ? y : 1);
+    const uint16_t* Drow = Du + yr * wp;
+    const uint32_t* Mrow = Mu + yr * (wp >> 5);
+    uint16_t* Orow = Ou + yr * W;
+    uint16_t* Oal = Orow - a;     // 16-byte aligned: block b is Oal[8b .. 8b+8)
 
-    unsigned long long dlo = 0, dhi = 0, n1lo = 0, n1hi = 0, n2lo = 0, n2hi = 0;
-    unsigned mb = 0, m1 = 0, m2 = 0;
-    unsigned long long olo = 0, ohi = 0;
-    auto load_group = [&](int gx, unsigned long long& lo, unsigned long long& hi, unsigned& mbits) {
-      if (row_active && gx < (int)wp) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(Drow + gx));
-        lo = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
-        hi = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
-        mbits = (__ldg(Mrow + (gx >> 5)) >> (gx & 24)) & 0xFFu;
-      } else {
-        lo = hi = 0; mbits = 0;
-      }
-    };
-    load_group(0, n1lo, n1hi, m1);
-    load_group(8, n2lo, n2hi, m2);
-
-    unsigned left = 0, prev_out = 0;
-    int x = -lane;
-    const int steps = W + 31;
-    for (int t = 0; t < steps; t++, x++) {
-      if (has_top && (t & (K4_GATE - 1)) == 0 && t < W) {
-        const int need = min(t + K4_GATE, W);
-        while (ld_volatile_s32(prog_in) < need) { }
-        __threadfence_block();   // order the boundary-row reads after the progress read
-      }
-      unsigned top = __shfl_up_sync(0xffffffffu, prev_out, 1);
-      if (lane == 0) top = (has_top && t < W) ? brow_in[t] : 0u;
-      const bool active = row_active && x >= 0 && x < W;
-      if (x >= 0 && (x & 7) == 0) {
-        dlo = n1lo; dhi = n1hi; mb = m1;
-        n1lo = n2lo; n1hi = n2hi; m1 = m2;
-        load_group(x + 16, n2lo, n2hi, m2);
-      }
-      const unsigned d = (unsigned)(dlo & 0xFFFFu);
-      const unsigned lit = mb & 1u;
-      if (x >= 0) {
-        dlo = (dlo >> 16) | (dhi << 48);
-        dhi >>= 16;
-        mb >>= 1;
-      }
-      // predictor (deltarlecompressu16.go:112-126): (0,0)->0, row 0->left, col 0->top, else (left+top)>>1
-      unsigned pred;
-      const bool up = y > 0;
-      if (x > 0 && up) pred = (left + top) >> 1;
-      else if (x > 0) pred = left;
-      else pred = up ? top : 0u;
-      unsigned val = lit ? d : ((pred + d - (unsigned)thr) & 0xFFFFu);
-      if (!active) val = 0;
-      left = val;
-      prev_out = val;
-      if (active) {
-        if (lane == 31) brow_out[x] = (uint16_t)val;
-        if (x < headx || x >= tail) {
-          Orow[x] = (uint16_t)val;
-        } else {
-          olo = (olo >> 16) | (ohi << 48);
-          ohi = (ohi >> 16) | ((unsigned long long)val << 48);
-          if (((x - hx) & 7) == 7) {
-            uint4 v;
-            v.x = (unsigned)olo; v.y = (unsigned)(olo >> 32); v.z = (unsigned)ohi; v.w = (unsigned)(ohi >> 32);
-            *reinterpret_cast<uint4*>(Orow + x - 7) = v;
-          }
-        }
-        if (lane == 31 && ((((x + 1) & (K4_GATE - 1)) == 0) || x == W - 1)) {
+    Grp tp = {{0, 0, 0, 0}}, g = {{0, 0, 0, 0}};
+    uint4 dn1 = make_uint4(0, 0, 0, 0), dn2 = dn1;
+    if (nblk > 0) dn1 = __ldg(reinterpret_cast<const uint4*>(Drow));
+    if (nblk > 1) dn2 = __ldg(reinterpret_cast<const uint4*>(Drow) + 1);
+    unsigned left = 0;
+    int b = -s;
+    for (int t = 0; t < T; t++, b++) {
+      Grp rc;
+#pragma unroll
+      for (int i = 0; i < 4; i++) rc.w[i] = __shfl_up_sync(0xffffffffu, g.w[i], 1);
+      if (lane == 0) {
+        const int c = t + wrap;
+        if (c < nblk_prev) {
+          while (ld_volatile_s32(prog_in) <= c) __nanosleep(20);
           __threadfence_block();
-          *reinterpret_cast<volatile int*>(prog_out) = x + 1;
+          const uint4 v = *reinterpret_cast<const uint4*>(brow_in + 8 * c);
+          rc.w[0] = v.x; rc.w[1] = v.y; rc.w[2] = v.z; rc.w[3] = v.w;
         }
       }
+      if (b >= 0 && b < nblk) {
+        const Grp tw = rephase(tp, rc, delta);
+        const uint4 dv = dn1;
+        dn1 = dn2;
+        if (b + 2 < nblk) dn2 = __ldg(reinterpret_cast<const uint4*>(Drow) + (b + 2));
+        const unsigned mbyte = (__ldg(Mrow + (b >> 2)) >> ((b & 3) * 8)) & 0xFFu;
+        Grp dg;
+        dg.w[0] = dv.x; dg.w[1] = dv.y; dg.w[2] = dv.z; dg.w[3] = dv.w;
+        const int x0 = 8 * b - a;
+        if (mbyte == 0 && x0 >= 1 && x0 + 8 <= W) {
+          // ---- interior block: 8 unrolled pixels, aligned 16 B store ----
+          unsigned v[8];
+#define PIX(J)                                                                        \
+  {                                                                                   \
+    const unsigned top = grp_get<J>(tw);                                              \
+    const unsigned e = grp_get<J>(dg) - (unsigned)thr;                                \
+    left = (((left + top) >> 1) + e) & 0xFFFFu;                                       \
+    v[J] = left;                                                                      \
+  }
+          PIX(0) PIX(1) PIX(2) PIX(3) PIX(4) PIX(5) PIX(6) PIX(7)
+#undef PIX
+          g.w[0] = v[0] | (v[1] << 16); g.w[1] = v[2] | (v[3] << 16);
+          g.w[2] = v[4] | (v[5] << 16); g.w[3] = v[6] | (v[7] << 16);
+          *reinterpret_cast<uint4*>(Oal + 8 * b) = make_uint4(g.w[0], g.w[1], g.w[2], g.w[3]);
+        } else {
+          // ---- head / tail / literal block: per-pixel predicates, 2-byte stores ----
+          unsigned v[8];
+#define PIXS(J)                                                                       \
+  {                                                                                   \
+    const int x = x0 + J;                                                             \
+    v[J] = 0;                                                                         \
+    if (x >= 0 && x < W) {                                                            \
+      const unsigned top = grp_get<J>(tw);                                            \
+      const unsigned d = grp_get<J>(dg);                                              \
+      const unsigned l = x == 0 ? top : left;          /* column 0: pred = top */     \
+      left = ((mbyte >> J) & 1u) ? d : ((((l + top) >> 1) + d - (unsigned)thr) & 0xFFFFu); \
+      v[J] = left;                                                                    \
+      Orow[x] = (uint16_t)left;                                                       \
+    }                                                                                 \
+  }
+          PIXS(0) PIXS(1) PIXS(2) PIXS(3) PIXS(4) PIXS(5) PIXS(6) PIXS(7)
+#undef PIXS
+          g.w[0] = v[0] | (v[1] << 16); g.w[1] = v[2] | (v[3] << 16);
+          g.w[2] = v[4] | (v[5] << 16); g.w[3] = v[6] | (v[7] << 16);
+        }
+        if (lane == 31) {
+          *reinterpret_cast<uint4*>(brow_out + 8 * b) = make_uint4(g.w[0], g.w[1], g.w[2], g.w[3]);
+          __threadfence_block();
+          *reinterpret_cast<volatile int*>(prog_out) = b + 1;
+        }
+      }
+      tp = rc;
     }
   }
 }
 
 int delta_wavefront_threads(int max_width, int max_height) {
-  int threads = (max_height + 31) / 32 * 32;
+  int threads = (max_height - 1 + 31) / 32 * 32;   // row 0 is handled by the prologue scan
   if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
-  const int pitch = (max_width + 7) / 8 * 8;
+  const int pitch = (max_width + 16 + 7) / 8 * 8;
   // keep (nwarps+1) boundary rows within ~200 KB of shared memory
   while (threads > 32 && (size_t)(threads / 32 + 1) * pitch * sizeof(uint16_t) > 200u * 1024u) threads -= 32;
   return threads;
@@ -156,7 +229,7 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
   if (nlist <= 0) return;
   const int threads = delta_wavefront_threads(max_width, max_height);
   const int nwarps = threads / 32;
-  const int pitch = (max_width + 7) / 8 * 8;
+  const int pitch = (max_width + 16 + 7) / 8 * 8;
   const size_t smem = (size_t)(nwarps + 1) * pitch * sizeof(uint16_t);
   cudaFuncSetAttribute(k_delta_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_delta_wavefront<<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);

@@ -56,7 +56,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     const uint16_t* st = states + U->sym_off;
     const uint16_t* Sy = tabS + U->tab_off;
     const bool spatial = U->kind == MIC_KIND_SPATIAL;
-    const unsigned W = U->width, H = U->height, wp = U->wp;
+    const unsigned W = U->width, H = U->height, wp = U->wp, align0 = U->align0;
     const unsigned long long npx = (unsigned long long)W * H;
 
     if (nsym < (spatial ? 2 : 3)) {
@@ -97,7 +97,20 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       __syncthreads();
       if (restage) {
         const int nb = min(nsym - ipos, IN_N);
-        for (int i = tid; i < nb; i += K3_THREADS) s_in[i] = Sy[st[ipos + i]];
+        // two dependent global loads per symbol (state, then tabS[state], L1-resident): batch 8 of each
+        for (int i0 = tid; i0 < nb; i0 += 8 * K3_THREADS) {
+          unsigned stv[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const int i = i0 + q * K3_THREADS;
+            stv[q] = i < nb ? __ldg(st + ipos + i) : 0u;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const int i = i0 + q * K3_THREADS;
+            if (i < nb) s_in[i] = __ldg(Sy + stv[q]);
+          }
+        }
         if (tid == 0) { ws.wbase = ipos; ws.wend = ipos + nb; }
       }
       __syncthreads();
@@ -178,6 +191,34 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         if (tid == 0) { U->thr = thr; U->delim = delim; }
       }
       first = false;
+      // Fast path: no element of the chunk equals the delimiter (and no pending literal), so every
+      // element is a plain pixel and the chunk goes to D without the marker/compaction passes.
+      {
+        bool has = false;
+        for (int i = tid; i < nout; i += K3_THREADS) has |= (s_e[i] == delim) && !(i == 0 && skip0);
+        const int anyd = __syncthreads_or(has ? 1 : 0) | (int)carry_m;
+        if (!anyd) {
+          const int skip = skip0 ? 1 : 0;
+          int n = nout - skip;
+          if (n < 0) n = 0;
+          const int npix_chunk = n;
+          if (pix + (unsigned)n > npx) n = (int)(npx - pix);
+          if (tid < n) {
+            unsigned long long gp = pix + (unsigned)tid;
+            unsigned y = (unsigned)(gp / W), x = (unsigned)(gp - (unsigned long long)y * W);
+            uint16_t* Du = D + U->d_off;
+            for (int i = tid; i < n; i += K3_THREADS) {
+              const unsigned ay = (align0 + (y & 7u) * (W & 7u)) & 7u;
+              Du[(unsigned long long)y * wp + ay + x] = s_e[i + skip];
+              x += K3_THREADS;
+              while (x >= W) { x -= W; y++; }
+            }
+          }
+          pix += (unsigned)npix_chunk;
+          if (done || pix >= npx) break;
+          continue;
+        }
+      }
       const int nwin = (nout + 31) >> 5;
       // C1: per-window masks of non-delimiter elements
       for (int w = warp; w < nwin; w += K3_WARPS) {
@@ -280,7 +321,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
             s_p[pl] = s_e[e];
             if (prevm) {   // literal pixel (deltarlecompressu16.go:105-106)
               const unsigned y = (unsigned)(gp / W), x = (unsigned)(gp - (unsigned long long)y * W);
-              atomicOr(&M[U->m_off + (unsigned long long)y * (wp >> 5) + (x >> 5)], 1u << (x & 31));
+              const unsigned pc = ((align0 + (y & 7u) * (W & 7u)) & 7u) + x;   // padded column
+              atomicOr(&M[U->m_off + (unsigned long long)y * (wp >> 5) + (pc >> 5)], 1u << (pc & 31));
             }
           }
         }
@@ -295,7 +337,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           unsigned y = (unsigned)(gp / W), x = (unsigned)(gp - (unsigned long long)y * W);
           uint16_t* Du = D + U->d_off;
           for (int i = tid; i < n; i += K3_THREADS) {
-            Du[(unsigned long long)y * wp + x] = s_p[i];
+            const unsigned ay = (align0 + (y & 7u) * (W & 7u)) & 7u;
+            Du[(unsigned long long)y * wp + ay + x] = s_p[i];
             x += K3_THREADS;
             while (x >= W) { x -= W; y++; }
           }

@@ -35,12 +35,14 @@ struct MicUnit {
   unsigned int comp_len;
   unsigned int kind;
   unsigned int width, height;   // spatial: image geometry; RLE: width = expected outlen, height = 1
-  unsigned int wp;              // padded pitch (multiple of 32 elements)
+  unsigned int wp;              // padded pitch (multiple of 32 elements, >= width + 8)
   unsigned int nstates;         // 1,2,4,8 (from the magic prefix, fse2state.go:102-116)
   unsigned int rans;            // 1 when magic is [0xFF,0x08]
   unsigned int table_log;       // peeked from the ncount header (fsedecompressu16.go:61)
   unsigned int count;           // symbol count from the 6-byte prefix (0: 1-state, unknown)
   unsigned int sym_cap;         // capacity (elements) reserved at sym_off
+  unsigned int align0;          // (output element address of pixel (0,0)) mod 8, set per run; row y of D and M
+                                // is stored at padded column a_y + x with a_y = (align0 + y*width) mod 8
   // ---- device-filled ----------------------------------------------------
   unsigned int bits_off;        // byte offset of the bitstream inside the frame
   unsigned int bits_len;        // bitstream length in bytes

@@ -162,7 +162,7 @@ int plan_commit(micgpu_decoder* d) {
     d->tab_total += 1ull << u.table_log;
     d->max_log_all = std::max(d->max_log_all, (int)u.table_log);
     if (u.kind == MIC_KIND_SPATIAL) {
-      u.wp = (u.width + 31) & ~31u;
+      u.wp = (u.width + 8 + 31) & ~31u;   // room for the 0..7 pixel row phase (mic_unit.h align0)
       u.d_off = d->d_total;
       d->d_total += (unsigned long long)u.wp * u.height;
       u.m_off = d->m_total;
@@ -267,6 +267,8 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   d->launches = 0;
   const int nu = (int)d->units.size();
   if (!nu) return 0;
+  for (MicUnit& u : d->units)
+    u.align0 = (unsigned)(((reinterpret_cast<uintptr_t>(d_out) >> 1) + u.out_off) & 7u);
   memcpy(d->h_units, d->units.data(), nu * sizeof(MicUnit));
   CUDA_TRY(cudaMemcpyAsync(d->d_units.p, d->h_units, nu * sizeof(MicUnit), cudaMemcpyHostToDevice, st));
   if (d->m_total) CUDA_TRY(cudaMemsetAsync(d->d_M.p, 0, d->m_total * sizeof(uint32_t), st));

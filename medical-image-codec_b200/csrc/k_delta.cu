@@ -48,13 +48,15 @@ __device__ __forceinline__ uint32_t grp_get(const Grp& g) {
   return (J & 1) ? (g.w[J >> 1] >> 16) : (g.w[J >> 1] & 0xFFFFu);
 }
 
+constexpr int K4_LAG = 2;
+
 __device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 __global__ void __launch_bounds__(1024)
 k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist,
                   const uint16_t* __restrict__ D, const uint32_t* __restrict__ M, uint16_t* __restrict__ out,
                   int brow_pitch) {
-  extern __shared__ __align__(16) uint16_t s_brow[];  // (nwarps+1) boundary rows, padded coordinates
+  extern __shared__ __align__(16) uint16_t s_brow[];  // (nwarps+1) boundary rows, padded coordinates, then the exchange slots
   __shared__ int s_prog[33];                          // s_prog[w+1]: blocks finished by warp w's last lane
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,21 +141,37 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
     uint16_t* Orow = Ou + yr * W;
     uint16_t* Oal = Orow - a;     // 16-byte aligned: block b is Oal[8b .. 8b+8)
 
+    // lane -> lane+1 hand-over of the finished block through shared memory (double buffered):
+    // one 16 B store, one warp barrier and one 16 B load per step instead of four shuffles
+    uint4* xch = reinterpret_cast<uint4*>(s_brow + (size_t)(nwarps + 1) * brow_pitch) + warp * 64;
+    xch[lane] = make_uint4(0, 0, 0, 0);
+    xch[32 + lane] = make_uint4(0, 0, 0, 0);
+
     Grp tp = {{0, 0, 0, 0}}, g = {{0, 0, 0, 0}};
     uint4 dn1 = make_uint4(0, 0, 0, 0), dn2 = dn1;
     if (nblk > 0) dn1 = __ldg(reinterpret_cast<const uint4*>(Drow));
     if (nblk > 1) dn2 = __ldg(reinterpret_cast<const uint4*>(Drow) + 1);
+    unsigned mw = nblk > 0 ? __ldg(Mrow) : 0u;          // literal bits of blocks 4q..4q+3
+    unsigned mwn = nblk > 4 ? __ldg(Mrow + 1) : 0u;
     unsigned left = 0;
     int b = -s;
+    int seen = 0;                                       // lane 0: producer progress seen so far
     for (int t = 0; t < T; t++, b++) {
+      __syncwarp();
       Grp rc;
-#pragma unroll
-      for (int i = 0; i < 4; i++) rc.w[i] = __shfl_up_sync(0xffffffffu, g.w[i], 1);
+      {
+        const uint4 v = xch[((t + 1) & 1) * 32 + ((lane + 31) & 31)];   // lane-1's block of step t-1
+        rc.w[0] = v.x; rc.w[1] = v.y; rc.w[2] = v.z; rc.w[3] = v.w;
+      }
       if (lane == 0) {
         const int c = t + wrap;
         if (c < nblk_prev) {
-          while (ld_volatile_s32(prog_in) <= c) __nanosleep(20);
-          __threadfence_block();
+          if (seen <= c) {
+            // first wait: let the producer get K4_LAG blocks ahead so later steps find their block ready
+            const int need = min(c + (t == 0 ? K4_LAG : 1), nblk_prev);
+            while ((seen = ld_volatile_s32(prog_in)) < need) { }   // plain spin: __nanosleep quantises to ~1 us and throttles the whole chain
+            __threadfence_block();
+          }
           const uint4 v = *reinterpret_cast<const uint4*>(brow_in + 8 * c);
           rc.w[0] = v.x; rc.w[1] = v.y; rc.w[2] = v.z; rc.w[3] = v.w;
         }
@@ -163,7 +181,11 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
         const uint4 dv = dn1;
         dn1 = dn2;
         if (b + 2 < nblk) dn2 = __ldg(reinterpret_cast<const uint4*>(Drow) + (b + 2));
-        const unsigned mbyte = (__ldg(Mrow + (b >> 2)) >> ((b & 3) * 8)) & 0xFFu;
+        const unsigned mbyte = (mw >> ((b & 3) * 8)) & 0xFFu;
+        if ((b & 3) == 3) {
+          mw = mwn;
+          if (b + 5 < nblk) mwn = __ldg(Mrow + ((b + 5) >> 2));
+        }
         Grp dg;
         dg.w[0] = dv.x; dg.w[1] = dv.y; dg.w[2] = dv.z; dg.w[3] = dv.w;
         const int x0 = 8 * b - a;
@@ -209,6 +231,7 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
           *reinterpret_cast<volatile int*>(prog_out) = b + 1;
         }
       }
+      xch[(t & 1) * 32 + lane] = make_uint4(g.w[0], g.w[1], g.w[2], g.w[3]);
       tp = rc;
     }
   }
@@ -220,7 +243,7 @@ int delta_wavefront_threads(int max_width, int max_height) {
   if (threads < 32) threads = 32;
   const int pitch = (max_width + 16 + 7) / 8 * 8;
   // keep (nwarps+1) boundary rows within ~200 KB of shared memory
-  while (threads > 32 && (size_t)(threads / 32 + 1) * pitch * sizeof(uint16_t) > 200u * 1024u) threads -= 32;
+  while (threads > 32 && (size_t)(threads / 32 + 1) * pitch * sizeof(uint16_t) + (size_t)(threads / 32) * 1024 > 200u * 1024u) threads -= 32;
   return threads;
 }
 
@@ -230,7 +253,7 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
   const int threads = delta_wavefront_threads(max_width, max_height);
   const int nwarps = threads / 32;
   const int pitch = (max_width + 16 + 7) / 8 * 8;
-  const size_t smem = (size_t)(nwarps + 1) * pitch * sizeof(uint16_t);
+  const size_t smem = (size_t)(nwarps + 1) * pitch * sizeof(uint16_t) + (size_t)nwarps * 1024;
   cudaFuncSetAttribute(k_delta_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_delta_wavefront<<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);
 }

@@ -38,13 +38,14 @@ struct WalkState {
 __global__ void __launch_bounds__(K3_THREADS)
 k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict__ states,
              const uint16_t* __restrict__ tabS, uint16_t* __restrict__ D, uint32_t* __restrict__ M,
-             uint16_t* __restrict__ out) {
+             uint16_t* __restrict__ out, int tab_smem_log) {
   __shared__ uint16_t s_in[IN_N];
   __shared__ uint16_t s_e[OUT_CH];
   __shared__ uint16_t s_p[OUT_CH];
   __shared__ uint32_t s_non[NWIN], s_mark[NWIN];
   __shared__ int s_wprev[NWIN], s_pixbase[NWIN + 1];
   __shared__ WalkState ws;
+  extern __shared__ __align__(16) uint16_t s_tab[];   // tabS of the current unit (when it fits: tab_smem_log >= tableLog)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -63,6 +64,16 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       if (tid == 0) U->status = MIC_E_RLE;
       continue;
     }
+    // Random 2-byte gathers from tabS through L1/L2 move a 32-byte sector per symbol (measured: K3 was
+    // bound by exactly that), so the symbol table is staged in shared memory whenever it fits.
+    const bool tab_in_smem = (int)U->table_log <= tab_smem_log;
+    if (tab_in_smem) {
+      const uint4* src = reinterpret_cast<const uint4*>(Sy);
+      uint4* dst = reinterpret_cast<uint4*>(s_tab);
+      const int n16 = (1 << U->table_log) / 8;
+      for (int i = tid; i < n16; i += K3_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
     // word 0 fixes midCount (rledecompressu16.go:21-30)
     const unsigned sym0 = Sy[st[0]];
     const int depth0 = bit_len16(sym0);
@@ -105,10 +116,18 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
             const int i = i0 + q * K3_THREADS;
             stv[q] = i < nb ? __ldg(st + ipos + i) : 0u;
           }
+          if (tab_in_smem) {
 #pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const int i = i0 + q * K3_THREADS;
-            if (i < nb) s_in[i] = __ldg(Sy + stv[q]);
+            for (int q = 0; q < 8; q++) {
+              const int i = i0 + q * K3_THREADS;
+              if (i < nb) s_in[i] = s_tab[stv[q]];
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int i = i0 + q * K3_THREADS;
+              if (i < nb) s_in[i] = __ldg(Sy + stv[q]);
+            }
           }
         }
         if (tid == 0) { ws.wbase = ipos; ws.wend = ipos + nb; }
@@ -361,9 +380,13 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
 }
 
 void launch_rle_expand(MicUnit* d_units, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
-                       uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int grid, cudaStream_t st) {
+                       uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, cudaStream_t st) {
   if (nunits <= 0) return;
-  k_rle_expand<<<grid, K3_THREADS, 0, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out);
+  // stage tabS in shared memory up to tableLog 14 (32 KB); larger tables are gathered through L1/L2
+  const int tab_log = max_log <= 14 ? max_log : 14;
+  const size_t smem = (size_t)2 << tab_log;
+  cudaFuncSetAttribute(k_rle_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_rle_expand<<<grid, K3_THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log);
 }
 
 }  // namespace micgpu

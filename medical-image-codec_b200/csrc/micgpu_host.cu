@@ -295,7 +295,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   }
   prof_mark(d, "k_rle_expand", st);
   launch_rle_expand(du, nu, (const uint16_t*)d->d_states.p, (const uint16_t*)d->d_tabS.p, (uint16_t*)d->d_D.p,
-                    (uint32_t*)d->d_M.p, (uint16_t*)d_out, std::min(nu, d->sm_count * 8), st);
+                    (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(nu, d->sm_count * 8), st);
   d->launches++;
   if (!d->spatial.empty()) {
     prof_mark(d, "k_delta_wavefront", st);

@@ -181,6 +181,9 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
         const uint4 dv = dn1;
         dn1 = dn2;
         if (b + 2 < nblk) dn2 = __ldg(reinterpret_cast<const uint4*>(Drow) + (b + 2));
+        // every lane streams its own row 16 B at a time; pull whole 128 B lines into L2 two lines ahead
+        // so DRAM sees one burst per line instead of row-buffer-missing sector reads from 256 rows
+        if ((b & 7) == 0 && b + 16 < nblk) asm volatile("prefetch.global.L2 [%0];" ::"l"(Drow + 8 * (b + 16)));
         const unsigned mbyte = (mw >> ((b & 3) * 8)) & 0xFFu;
         if ((b & 3) == 3) {
           mw = mwn;

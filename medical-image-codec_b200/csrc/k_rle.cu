@@ -24,6 +24,7 @@ constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int IN_N = 4096;
 constexpr int OUT_CH = 4096;
 constexpr int NWIN = OUT_CH / 32;
+constexpr int MAXR = 256;   // runs per chunk
 
 struct WalkState {
   int ipos;        // next input symbol to parse
@@ -32,6 +33,7 @@ struct WalkState {
   int kind;        // 0 same, 1 diff
   unsigned value;  // recurring value of a same-run
   int nout;        // elements produced by the last walk
+  int nruns;       // runs listed by the last walk
   int done, err;
 };
 
@@ -44,6 +46,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
   __shared__ uint16_t s_p[OUT_CH];
   __shared__ uint32_t s_non[NWIN], s_mark[NWIN];
   __shared__ int s_wprev[NWIN], s_pixbase[NWIN + 1];
+  __shared__ uint16_t s_run_o[MAXR], s_run_n[MAXR];   // run list of the current chunk: output start, length
+  __shared__ int s_run_src[MAXR];                     // >= 0: first literal in s_in (diff-run); < 0: -(value+1) (same-run)
   __shared__ WalkState ws;
   extern __shared__ __align__(16) uint16_t s_tab[];   // tabS of the current unit (when it fits: tab_smem_log >= tableLog)
 
@@ -146,7 +150,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           if (left < (unsigned long long)budget) budget = (int)left;
           if (budget == 0) done = 1;
         }
-        while (o < budget) {
+        int nr = 0;
+        while (o < budget && nr < MAXR) {
           if (c_rem == 0) {
             if (ip >= nsym) { done = 1; break; }
             if (ip >= we) break;
@@ -161,6 +166,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
             }
           }
           int take = (int)min(c_rem, (unsigned)(budget - o));
+          int src;
           if (kind == 1) {
             const int avail = we - ip;
             if (avail <= 0) {
@@ -168,25 +174,40 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
               break;
             }
             take = min(take, avail);
-            for (int j = lane; j < take; j += 32) s_e[o + j] = s_in[ip - wb + j];
+            src = ip - wb;
             ip += take;
           } else {
-            const uint16_t v16 = (uint16_t)value;
-            for (int j = lane; j < take; j += 32) s_e[o + j] = v16;
+            src = -(int)(value + 1u);
           }
+          if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = src; }
+          nr++;
           o += take;
           c_rem -= (unsigned)take;
         }
-        if (!restage && o == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
+        if (!restage && o == 0 && nr == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
         if (lane == 0) {
           ws.ipos = ip; ws.c_rem = c_rem; ws.kind = kind; ws.value = value;
-          ws.nout = o; ws.done = done; ws.err = err;
+          ws.nout = o; ws.nruns = nr; ws.done = done; ws.err = err;
         }
       }
       __syncthreads();
       const int nout = ws.nout;
       const int done = ws.done;
       if (ws.err) break;
+      // ---------------- B2: expand the listed runs, all threads per run -------
+      {
+        const int nr = ws.nruns;
+        for (int r = 0; r < nr; r++) {
+          const int o = s_run_o[r], n = s_run_n[r], src = s_run_src[r];
+          if (src >= 0) {
+            for (int j = tid; j < n; j += K3_THREADS) s_e[o + j] = s_in[src + j];
+          } else {
+            const uint16_t v16 = (uint16_t)(-(src + 1));
+            for (int j = tid; j < n; j += K3_THREADS) s_e[o + j] = v16;
+          }
+        }
+      }
+      __syncthreads();
 
       if (!spatial) {
         // ---------------- C (RLE kind): straight copy ------------------------

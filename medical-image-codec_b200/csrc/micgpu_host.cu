@@ -162,7 +162,7 @@ int plan_commit(micgpu_decoder* d) {
     d->tab_total += 1ull << u.table_log;
     d->max_log_all = std::max(d->max_log_all, (int)u.table_log);
     if (u.kind == MIC_KIND_SPATIAL) {
-      u.wp = (u.width + 8 + 31) & ~31u;   // room for the 0..7 pixel row phase (mic_unit.h align0)
+      u.wp = (u.width + 8 + 63) & ~63u;   // rows start on 128 B lines;   // room for the 0..7 pixel row phase (mic_unit.h align0)
       u.d_off = d->d_total;
       d->d_total += (unsigned long long)u.wp * u.height;
       u.m_off = d->m_total;

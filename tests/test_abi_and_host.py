@@ -1,0 +1,123 @@
+"""CPU-side checks of the boundary: libmicgpu.so loads and exports every symbol include/micgpu.h declares,
+fails loudly without a GPU (no CPU fallback), and the host-side shard planner agrees across ranks."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "micgpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:micgpu|mic)_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(mic):
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(mic.lib, n), f"libmicgpu.so does not export {n}"
+
+
+def test_twin_signatures_match_reference_headers():
+    """The 8 drop-in symbols keep the reference prototypes (ojph/mic_decompress_c.h:24-49, mic_parallel.h:49-55)."""
+    txt = re.sub(r"\s+", " ", open(os.path.join(ROOT, "include", "micgpu.h")).read())
+    for n in ("two", "four", "eight"):
+        for s in ("", "_simd"):
+            assert f"int mic_decompress_{n}_state{s}(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);" in txt
+    assert "int mic_decompress_parallel(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height, int max_threads);" in txt
+
+
+def test_no_cpu_fallback_without_gpu(mic):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert mic.lib.micgpu_device_count() == 0
+    assert not mic.lib.micgpu_decoder_create(0)
+    assert b"no CUDA device" in mic.lib.micgpu_last_error()
+    out = np.zeros(16, np.uint16)
+    blob = np.zeros(64, np.uint8)
+    rc = mic.lib.micgpu_decompress_single_frame(blob.ctypes.data, blob.size, out.ctypes.data, 4, 4)
+    assert rc == mic.api.E_CUDA
+    with pytest.raises(mic.MicGpuError):
+        mic.DecompressSingleFrame(bytes(64), 4, 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "medical-image-codec_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.replace("CPU oracle", "").replace("touches oracle/", "").lower().replace("the oracle is", ""), f
+    out = subprocess.run(["nm", "-D", os.path.join(pkg, "libmicgpu.so")], capture_output=True, text=True).stdout
+    assert "orc_" not in out
+
+
+def test_partition_by_bytes(synth):
+    import importlib
+
+    shard = importlib.import_module("medical-image-codec_b200.shard")
+    lens = [100, 300, 50, 50, 400, 100, 100, 100]
+    for world in (1, 2, 3, 4, 8, 16):
+        parts = shard.partition_by_bytes(lens, world)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == len(lens)
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    p2 = shard.partition_by_bytes(lens, 2)
+    assert abs(sum(lens[p2[0][0]:p2[0][1]]) - 600) <= 400
+    assert shard.partition_by_bytes([], 4) == [(0, 0)] * 4
+
+
+_GLOO_WORKER = r'''
+import importlib, os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch
+import torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+shard = importlib.import_module("medical-image-codec_b200.shard")
+synth = importlib.import_module("medical-image-codec_b200.synth")
+from oracle.oracle import Oracle
+o = Oracle()
+# every rank derives the same strip table from the same PICS blob and takes its own range
+img = synth.xr_image(5, 211, 160).ravel()
+blob = o.pics_compress(img, 211, 160, int(img.max()), 8, 2)
+w, h, sh, tab = shard.pics_strip_table(blob)
+parts = shard.partition_by_bytes([l for _, l in tab], world)
+lo, hi = parts[rank]
+mine = np.zeros(w * h, np.int64)
+for s in range(lo, hi):
+    off, ln = tab[s]
+    rows = min(sh, h - s * sh)
+    px = o.decompress_single_frame(blob[off:off + ln], w, rows)      # CPU stand-in for the per-rank GPU decode
+    mine[s * sh * w:(s * sh + rows) * w] = px
+owned = torch.zeros(len(tab), dtype=torch.int64)
+owned[lo:hi] = 1
+dist.all_reduce(owned)                                              # test-only check; the data path has no collective
+t = torch.from_numpy(mine)
+dist.all_reduce(t)
+ok = bool((owned == 1).all()) and np.array_equal(t.numpy().astype(np.uint16), img)
+print("RANK", rank, "OK" if ok else "FAIL", parts)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_sharding_two_ranks_gloo(tmp_path):
+    """world_size-2 gloo run of the N>1 path: ranks agree on the partition, own every strip exactly once, and
+    the union of their outputs is the image."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", str(script), ROOT], capture_output=True, text=True, env=env, timeout=170)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == 2

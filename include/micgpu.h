@@ -107,6 +107,29 @@ int micgpu_mic2_decompress(const uint8_t *mic2, size_t len, uint16_t *frames_out
 int micgpu_mic2_decompress_frame(const uint8_t *mic2, size_t len, int frame_idx, uint16_t *pixels_out, size_t cap_px,
                                  int *width, int *height);
 
+/* ---- MIC3 whole-slide containers and MICR RGB payloads ------------------------ */
+#define MICGPU_WSI_MAX_LEVELS 32
+typedef struct micgpu_wsi_info {   /* WSIHeader + WSILevel (wsiformat.go:39-66) */
+  int width, height, tile_w, tile_h, channels, bits_per_sample, color_transform, n_levels;
+  uint64_t total_tiles;
+  int level_w[MICGPU_WSI_MAX_LEVELS], level_h[MICGPU_WSI_MAX_LEVELS];
+  int tiles_x[MICGPU_WSI_MAX_LEVELS], tiles_y[MICGPU_WSI_MAX_LEVELS], first_tile[MICGPU_WSI_MAX_LEVELS];
+} micgpu_wsi_info;
+/* ReadWSIHeader (wsicompress.go:299-305) */
+int micgpu_wsi_read_header(const uint8_t *mic3, size_t len, micgpu_wsi_info *info);
+/* DecompressWSITile (wsicompress.go:175-217): pixels of one tile, edge tiles cropped; RGB8 interleaved,
+ * grey8 or grey16 little-endian bytes. */
+int micgpu_wsi_decompress_tile(const uint8_t *mic3, size_t len, int level, int tile_x, int tile_y, uint8_t *out, size_t cap,
+                               int *width, int *height);
+/* n tiles of one container in one launch sequence (every plane of every tile is one unit). */
+int micgpu_wsi_decompress_tiles(const uint8_t *mic3, size_t len, int n, const int *levels, const int *tile_xs, const int *tile_ys,
+                                uint8_t *const *outs, const size_t *caps, int *widths, int *heights, int *status);
+/* DecompressWSIRegion (wsicompress.go:220-296) */
+int micgpu_wsi_decompress_region(const uint8_t *mic3, size_t len, int level, int x, int y, int w, int h, uint8_t *out, size_t cap,
+                                 int *out_w, int *out_h);
+/* DecompressRGB (rgbcompress.go:31-33) */
+int micgpu_rgb_decompress(const uint8_t *blob, size_t len, int width, int height, uint8_t *rgb_out);
+
 /* ---- drop-in symbols of the reference C twin (same signatures) -------------- */
 /* ojph/mic_decompress_c.h:24-49 */
 int mic_decompress_two_state(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);

@@ -13,6 +13,11 @@ from .api import (  # noqa: F401
     DecompressMultiFrame,
     DecompressParallelStrips,
     DecompressParallelStripsBatch,
+    DecompressRGB,
+    DecompressWSIRegion,
+    DecompressWSITile,
+    DecompressWSITiles,
+    ReadWSIHeader,
     DecompressSingleFrame,
     MicGpuError,
     lib,

@@ -68,6 +68,20 @@ lib.micgpu_pics_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.P
 lib.micgpu_decompress_single_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
 lib.micgpu_mic2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip, _ip, _ip]
 lib.micgpu_mic2_decompress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
+
+
+class WsiInfo(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("tile_w", C.c_int), ("tile_h", C.c_int), ("channels", C.c_int),
+                ("bits_per_sample", C.c_int), ("color_transform", C.c_int), ("n_levels", C.c_int), ("total_tiles", C.c_uint64),
+                ("level_w", C.c_int * 32), ("level_h", C.c_int * 32), ("tiles_x", C.c_int * 32), ("tiles_y", C.c_int * 32),
+                ("first_tile", C.c_int * 32)]
+
+
+lib.micgpu_wsi_read_header.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(WsiInfo)]
+lib.micgpu_wsi_decompress_tile.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_wsi_decompress_tiles.argtypes = [C.c_void_p, C.c_size_t, C.c_int, _ip, _ip, _ip, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip, _ip, _ip]
+lib.micgpu_wsi_decompress_region.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_rgb_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
 for _n in ("two", "four", "eight"):
     for _s in ("", "_simd"):
         getattr(lib, f"mic_decompress_{_n}_state{_s}").argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
@@ -160,6 +174,68 @@ def DecompressFrame(data, frame_idx: int):
     ow, oh = C.c_int(), C.c_int()
     _check(lib.micgpu_mic2_decompress_frame(a.ctypes.data, a.size, frame_idx, out.ctypes.data, out.size, C.byref(ow), C.byref(oh)))
     return out[: w * h].reshape(h, w)
+
+
+def ReadWSIHeader(data) -> dict:
+    """wsicompress.go:299 -> WSIHeader as a dict (Levels: list of (w, h, tilesX, tilesY, firstTileIdx))."""
+    a = _bytes_view(data)
+    info = WsiInfo()
+    _check(lib.micgpu_wsi_read_header(a.ctypes.data, a.size, C.byref(info)))
+    n = info.n_levels
+    return {"Width": info.width, "Height": info.height, "TileWidth": info.tile_w, "TileHeight": info.tile_h,
+            "Channels": info.channels, "BitsPerSample": info.bits_per_sample, "ColorTransform": bool(info.color_transform),
+            "TotalTiles": info.total_tiles,
+            "Levels": [(info.level_w[i], info.level_h[i], info.tiles_x[i], info.tiles_y[i], info.first_tile[i]) for i in range(min(n, 32))]}
+
+
+def _wsi_bpp(hdr) -> int:
+    return hdr["Channels"] * (2 if hdr["BitsPerSample"] == 16 else 1)
+
+
+def DecompressWSITile(data, level: int, tile_x: int, tile_y: int):
+    """wsicompress.go:175 -> (bytes as uint8 array, width, height); edge tiles cropped."""
+    a = _bytes_view(data)
+    hdr = ReadWSIHeader(a)
+    out = np.empty(hdr["TileWidth"] * hdr["TileHeight"] * _wsi_bpp(hdr), np.uint8)
+    w, h = C.c_int(), C.c_int()
+    _check(lib.micgpu_wsi_decompress_tile(a.ctypes.data, a.size, level, tile_x, tile_y, out.ctypes.data, out.size, C.byref(w), C.byref(h)))
+    return out[: w.value * h.value * _wsi_bpp(hdr)], w.value, h.value
+
+
+def DecompressWSITiles(data, tiles):
+    """Batch of (level, tx, ty) tiles of one container in one launch sequence -> list of (bytes, w, h)."""
+    a = _bytes_view(data)
+    hdr = ReadWSIHeader(a)
+    n = len(tiles)
+    cap = hdr["TileWidth"] * hdr["TileHeight"] * _wsi_bpp(hdr)
+    outs = [np.empty(cap, np.uint8) for _ in range(n)]
+    lv = (C.c_int * n)(*[t[0] for t in tiles])
+    tx = (C.c_int * n)(*[t[1] for t in tiles])
+    ty = (C.c_int * n)(*[t[2] for t in tiles])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    cp = (C.c_size_t * n)(*[cap] * n)
+    ws, hs, st = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)()
+    _check(lib.micgpu_wsi_decompress_tiles(a.ctypes.data, a.size, n, lv, tx, ty, op, cp, ws, hs, st))
+    bpp = _wsi_bpp(hdr)
+    return [(outs[i][: ws[i] * hs[i] * bpp], ws[i], hs[i]) for i in range(n)]
+
+
+def DecompressWSIRegion(data, level: int, x: int, y: int, w: int, h: int):
+    """wsicompress.go:220 -> (bytes as uint8 array, width, height) clamped to the level extent."""
+    a = _bytes_view(data)
+    hdr = ReadWSIHeader(a)
+    out = np.empty(max(w, 1) * max(h, 1) * _wsi_bpp(hdr), np.uint8)
+    ow, oh = C.c_int(), C.c_int()
+    _check(lib.micgpu_wsi_decompress_region(a.ctypes.data, a.size, level, x, y, w, h, out.ctypes.data, out.size, C.byref(ow), C.byref(oh)))
+    return out[: ow.value * oh.value * _wsi_bpp(hdr)], ow.value, oh.value
+
+
+def DecompressRGB(data, width: int, height: int) -> np.ndarray:
+    """rgbcompress.go:31 -> interleaved RGB8."""
+    a = _bytes_view(data)
+    out = np.empty(width * height * 3, np.uint8)
+    _check(lib.micgpu_rgb_decompress(a.ctypes.data, a.size, width, height, out.ctypes.data))
+    return out
 
 
 # ---- batch decoder over device-resident buffers -------------------------------------

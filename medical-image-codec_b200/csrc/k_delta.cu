@@ -186,6 +186,12 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
           }
           const uint4 v = *reinterpret_cast<const uint4*>(brow_in + 8 * c);
           rc.w[0] = v.x; rc.w[1] = v.y; rc.w[2] = v.z; rc.w[3] = v.w;
+          if (t == 0 && wrap) {
+            // lane 0 starts one block late relative to the row above when the phase wrapped: its first
+            // window also needs block 0 of that row (the other lanes receive it during their start delay)
+            const uint4 v0 = *reinterpret_cast<const uint4*>(brow_in);
+            tp.w[0] = v0.x; tp.w[1] = v0.y; tp.w[2] = v0.z; tp.w[3] = v0.w;
+          }
         }
       }
       stage(b + K4_RING - 1);

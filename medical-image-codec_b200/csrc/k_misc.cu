@@ -29,3 +29,78 @@ void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int 
 }
 
 }  // namespace micgpu
+
+namespace micgpu {
+
+// ---- MIC3 plane fill: plane modes 0/1/3 (wsicompress.go:487-524) ---------------------------------
+// job.kind 0: constant value; 1: raw little-endian u16 copied from the compressed buffer (unaligned).
+__global__ void __launch_bounds__(256)
+k_plane_fill(const PlaneFillJob* __restrict__ jobs, int njobs, const uint8_t* __restrict__ comp, uint16_t* __restrict__ planes) {
+  for (int j = blockIdx.y; j < njobs; j += gridDim.y) {
+    const PlaneFillJob J = jobs[j];
+    uint16_t* dst = planes + J.plane_off;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    if (J.kind == 0) {
+      const uint16_t v = (uint16_t)J.value;
+      for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.n; i += stride) dst[i] = v;
+    } else {
+      const uint8_t* src = comp + J.comp_off;
+      for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.n; i += stride)
+        dst[i] = (uint16_t)(src[2 * i] | (src[2 * i + 1] << 8));
+    }
+  }
+}
+
+// ---- MIC3 tile finish: planes -> pixels, YCoCg-R inverse, crop / region blit -----------------------
+// Replaces YCoCgRInverse (ycocgr.go:28-35, asm_generic.go:40-53, ycocgRInverseSSSE3/NEON), the planar->RGB
+// interleave (wsicompress.go:466-473), uint16ToBytes (:592-603), cropTile (:558-572) and the row copies of
+// DecompressWSIRegion (:282-291).  One job = one rectangle of one tile.
+__global__ void __launch_bounds__(256)
+k_tile_blit(const TileBlitJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ planes, uint8_t* __restrict__ out) {
+  for (int j = blockIdx.y; j < njobs; j += gridDim.y) {
+    const TileBlitJob J = jobs[j];
+    const unsigned long long npx = (unsigned long long)J.copy_w * J.copy_h;
+    const unsigned long long plane_px = (unsigned long long)J.tile_w * J.tile_h;
+    const uint16_t* p0 = planes + J.plane_off;
+    uint8_t* dst = out + J.dst_off;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+      const unsigned ry = (unsigned)(i / J.copy_w), rx = (unsigned)(i - (unsigned long long)ry * J.copy_w);
+      const unsigned long long s = (unsigned long long)(J.src_y + ry) * J.tile_w + (J.src_x + rx);
+      uint8_t* d = dst + (unsigned long long)ry * J.dst_pitch;
+      if (J.mode == 0 || J.mode == 1) {
+        const int a = p0[s], b = p0[plane_px + s], c = p0[2 * plane_px + s];
+        int r, g, bl;
+        if (J.mode == 0) {                  // YCoCg-R inverse
+          const int co = (int)(short)((b >> 1) ^ -(b & 1)), cg = (int)(short)((c >> 1) ^ -(c & 1));
+          const int t = a - (cg >> 1);
+          g = cg + t;
+          bl = t - (co >> 1);
+          r = co + bl;
+        } else {                            // planar R,G,B
+          r = a; g = b; bl = c;
+        }
+        d[3 * rx] = (uint8_t)r; d[3 * rx + 1] = (uint8_t)g; d[3 * rx + 2] = (uint8_t)bl;
+      } else if (J.mode == 2) {             // grey 8-bit
+        d[rx] = (uint8_t)p0[s];
+      } else {                              // grey 16-bit little endian
+        const unsigned v = p0[s];
+        d[2 * rx] = (uint8_t)v; d[2 * rx + 1] = (uint8_t)(v >> 8);
+      }
+    }
+  }
+}
+
+void launch_plane_fill(const PlaneFillJob* d_jobs, int njobs, const uint8_t* d_comp, uint16_t* d_planes, cudaStream_t st) {
+  if (njobs <= 0) return;
+  dim3 grid(8, njobs < 65535 ? njobs : 65535);
+  k_plane_fill<<<grid, 256, 0, st>>>(d_jobs, njobs, d_comp, d_planes);
+}
+
+void launch_tile_blit(const TileBlitJob* d_jobs, int njobs, const uint16_t* d_planes, uint8_t* d_out, cudaStream_t st) {
+  if (njobs <= 0) return;
+  dim3 grid(8, njobs < 65535 ? njobs : 65535);
+  k_tile_blit<<<grid, 256, 0, st>>>(d_jobs, njobs, d_planes, d_out);
+}
+
+}  // namespace micgpu

@@ -34,6 +34,25 @@ int delta_wavefront_threads(int max_width, int max_height);
 // In-place frame-axis running sum for temporal MIC2 (frames contiguous, fpx pixels each).
 void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int sm_count, cudaStream_t st);
 
+// MIC3 helpers (k_misc.cu)
+struct PlaneFillJob {
+  unsigned long long plane_off;   // element offset in the plane buffer
+  unsigned long long comp_off;    // byte offset of the raw payload (kind 1)
+  unsigned long long n;           // samples
+  unsigned int kind;              // 0 constant, 1 raw little-endian u16
+  unsigned int value;
+};
+struct TileBlitJob {
+  unsigned long long plane_off;   // first plane of the tile (planes are tile_w*tile_h apart)
+  unsigned long long dst_off;     // byte offset of the destination rectangle
+  unsigned int tile_w, tile_h;
+  unsigned int src_x, src_y, copy_w, copy_h;
+  unsigned int dst_pitch;         // bytes per destination row
+  unsigned int mode;              // 0 YCoCg-R -> RGB8, 1 planar RGB -> RGB8, 2 grey8, 3 grey16
+};
+void launch_plane_fill(const PlaneFillJob* d_jobs, int njobs, const uint8_t* d_comp, uint16_t* d_planes, cudaStream_t st);
+void launch_tile_blit(const TileBlitJob* d_jobs, int njobs, const uint16_t* d_planes, uint8_t* d_out, cudaStream_t st);
+
 // ---- small device helpers ---------------------------------------------------
 __device__ __forceinline__ uint32_t ld_u32_unaligned_safe(const uint8_t* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);

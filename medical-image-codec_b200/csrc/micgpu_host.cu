@@ -96,6 +96,7 @@ struct micgpu_decoder {
   bool committed = false;
   int launches = 0;
   DevBuf d_units, d_list, d_tabA, d_tabS, d_states, d_D, d_M, d_k1, d_comp, d_out;
+  DevBuf d_jobs, d_bytes;   // MIC3: fill / blit job tables, byte-typed pixel output
   MicUnit* h_units = nullptr;   // pinned staging copy
   size_t h_units_cap = 0;
   cudaStream_t stream = nullptr;  // used by the host-buffer convenience calls
@@ -108,7 +109,7 @@ struct micgpu_decoder {
   ~micgpu_decoder() {
     cudaSetDevice(device);
     d_units.release(); d_list.release(); d_tabA.release(); d_tabS.release(); d_states.release();
-    d_D.release(); d_M.release(); d_k1.release(); d_comp.release(); d_out.release();
+    d_D.release(); d_M.release(); d_k1.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
     for (auto e : ev) cudaEventDestroy(e);
@@ -735,6 +736,279 @@ int micgpu_mic2_decompress_frame(const uint8_t* mic2, size_t len, int frame_idx,
   return mic2_decode(mic2, len, frame_idx, true, pixels_out, cap_px, width, height, nullptr, nullptr);
 }
 
+}  // extern "C"
+
+// ---- MIC3 / RGB ---------------------------------------------------------------------
+namespace {
+
+struct Mic3Header {
+  int width, height, tile_w, tile_h, channels, bps, ct, nlv;
+  uint64_t total_tiles;
+  size_t lv_off, table_off, data_off;
+};
+struct Mic3Level { int w, h, tx, ty, first; };
+
+uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+// ReadMIC3Header (wsiformat.go:169-227)
+int parse_mic3(const uint8_t* p, size_t len, Mic3Header& h) {
+  if (len < 48) return fail(MICGPU_E_HEADER, "MIC3: file too small");
+  if (memcmp(p, "MIC3", 4) != 0) return fail(MICGPU_E_HEADER, "MIC3: invalid magic");
+  if (rd32(p + 4) != 1) return fail(MICGPU_E_HEADER, "MIC3: unsupported version %u", rd32(p + 4));
+  h.width = (int)rd32(p + 8); h.height = (int)rd32(p + 12); h.tile_w = (int)rd32(p + 16); h.tile_h = (int)rd32(p + 20);
+  h.channels = p[24] | (p[25] << 8); h.bps = p[26]; h.ct = (p[27] & 0x02) != 0;
+  h.nlv = p[28] | (p[29] << 8);
+  h.total_tiles = rd64(p + 32);
+  h.lv_off = 48;
+  if (len < h.lv_off + (size_t)h.nlv * 20) return fail(MICGPU_E_HEADER, "MIC3: truncated level descriptors");
+  h.table_off = h.lv_off + (size_t)h.nlv * 20;
+  if (h.total_tiles > (len - h.table_off) / 16) return fail(MICGPU_E_HEADER, "MIC3: truncated tile offset table");
+  h.data_off = h.table_off + (size_t)h.total_tiles * 16;
+  if (h.tile_w <= 0 || h.tile_h <= 0 || h.width <= 0 || h.height <= 0) return fail(MICGPU_E_HEADER, "MIC3: invalid dimensions");
+  return 0;
+}
+Mic3Level mic3_level(const uint8_t* p, const Mic3Header& h, int l) {
+  const uint8_t* q = p + h.lv_off + (size_t)l * 20;
+  return Mic3Level{(int)rd32(q), (int)rd32(q + 4), (int)rd32(q + 8), (int)rd32(q + 12), (int)rd32(q + 16)};
+}
+// ExtractTileBlob (wsiformat.go:229-241)
+int mic3_tile_blob(const uint8_t* p, size_t len, const Mic3Header& h, long long idx, const uint8_t** blob, size_t* bl) {
+  if (idx < 0 || (uint64_t)idx >= h.total_tiles) return fail(MICGPU_E_HEADER, "MIC3: tile index %lld out of range", idx);
+  const uint64_t o = rd64(p + h.table_off + (size_t)idx * 16), n = rd64(p + h.table_off + (size_t)idx * 16 + 8);
+  if (h.data_off + o + n > len || n > len) return fail(MICGPU_E_HEADER, "MIC3: tile %lld data extends beyond file", idx);
+  *blob = p + h.data_off + o;
+  *bl = (size_t)n;
+  return 0;
+}
+
+struct Blit { unsigned sx, sy, w, h; unsigned long long dst_off; unsigned dst_pitch; };
+struct TileReq {
+  const uint8_t* blob; size_t len;       // host copy of the tile blob
+  int tile_w, tile_h, channels, bps, ct;
+  std::vector<Blit> blits;               // rectangles of the decoded tile to place in the byte output
+  int status = 0;
+};
+
+// decompressTileBlob for a batch of tiles (wsicompress.go:424-484) + the blits that follow it.
+// Output bytes land in d->d_bytes; the caller copies them back.
+int wsi_run_locked(micgpu_decoder* d, std::vector<TileReq>& tiles, size_t out_bytes) {
+  d->units.clear();
+  d->temporal.clear();
+  d->out_need = 0;
+  std::vector<PlaneFillJob> fills;
+  std::vector<TileBlitJob> blits;
+  std::vector<std::pair<int, int>> unit_tile;   // unit -> tile
+  uint64_t ctot = 0, ptot = 0;
+  std::vector<uint64_t> coff(tiles.size());
+  for (size_t t = 0; t < tiles.size(); t++) {
+    TileReq& T = tiles[t];
+    coff[t] = ctot;
+    ctot += (T.len + 63) & ~(size_t)63;
+    const bool rgb = T.channels == 3 && T.bps == 8;
+    if (!rgb && T.channels != 1) { T.status = fail(MICGPU_E_UNSUPPORTED, "MIC3: %d channels at %d bits is not supported", T.channels, T.bps); continue; }
+    const uint64_t px = (uint64_t)T.tile_w * T.tile_h;
+    const int nplanes = rgb ? 3 : 1;
+    const uint8_t* pl[3]; size_t ln[3];
+    if (rgb) {
+      if (T.len < 12) { T.status = fail(MICGPU_E_HEADER, "MIC3: RGB tile blob too small"); continue; }
+      const size_t l0 = rd32(T.blob), l1 = rd32(T.blob + 4), l2 = rd32(T.blob + 8);
+      if (12 + l0 + l1 + l2 > T.len) { T.status = fail(MICGPU_E_HEADER, "MIC3: RGB tile blob truncated"); continue; }
+      pl[0] = T.blob + 12; ln[0] = l0; pl[1] = pl[0] + l0; ln[1] = l1; pl[2] = pl[1] + l1; ln[2] = l2;
+    } else {
+      pl[0] = T.blob; ln[0] = T.len;
+    }
+    const uint64_t plane0 = ptot;
+    ptot += px * nplanes;
+    for (int k = 0; k < nplanes && !T.status; k++) {
+      const uint64_t poff = plane0 + px * k;
+      const uint64_t boff = coff[t] + (uint64_t)(pl[k] - T.blob);
+      if (ln[k] == 0) { T.status = fail(MICGPU_E_HEADER, "empty plane data"); break; }
+      switch (pl[k][0]) {   // decompressWSIPlane (wsicompress.go:487-524)
+        case 0: fills.push_back(PlaneFillJob{poff, 0, px, 0, 0}); break;
+        case 1:
+          if (ln[k] < 3) { T.status = fail(MICGPU_E_HEADER, "constant plane data truncated"); break; }
+          fills.push_back(PlaneFillJob{poff, 0, px, 0, (unsigned)(pl[k][1] | (pl[k][2] << 8))});
+          break;
+        case 2:
+          add_unit_locked(d, pl[k] + 1, ln[k] - 1, boff + 1, MIC_KIND_SPATIAL, (uint32_t)T.tile_w, (uint32_t)T.tile_h, poff);
+          unit_tile.push_back({(int)d->units.size() - 1, (int)t});
+          break;
+        case 3:
+          if (ln[k] < 1 + px * 2) { T.status = fail(MICGPU_E_HEADER, "raw plane data truncated"); break; }
+          fills.push_back(PlaneFillJob{poff, boff + 1, px, 1, 0});
+          break;
+        default: T.status = fail(MICGPU_E_HEADER, "unknown plane mode %d", pl[k][0]);
+      }
+    }
+    if (T.status) continue;
+    const unsigned mode = rgb ? (T.ct ? 0u : 1u) : (T.bps <= 8 ? 2u : 3u);
+    for (const Blit& b : T.blits)
+      blits.push_back(TileBlitJob{plane0, b.dst_off, (unsigned)T.tile_w, (unsigned)T.tile_h, b.sx, b.sy, b.w, b.h, b.dst_pitch, mode});
+  }
+  int rc = plan_commit(d);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if ((rc = d->d_comp.ensure(ctot + 256))) return rc;
+  if ((rc = d->d_out.ensure(std::max<uint64_t>(ptot, 1) * sizeof(uint16_t)))) return rc;
+  if ((rc = d->d_bytes.ensure(std::max<size_t>(out_bytes, 1)))) return rc;
+  const size_t fbytes = fills.size() * sizeof(PlaneFillJob), bbytes = blits.size() * sizeof(TileBlitJob);
+  if ((rc = d->d_jobs.ensure(fbytes + bbytes + 64))) return rc;
+  cudaStream_t st = d->stream;
+  for (size_t t = 0; t < tiles.size(); t++)
+    if (!tiles[t].status) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_comp.p + coff[t], tiles[t].blob, tiles[t].len, cudaMemcpyHostToDevice, st));
+  if (fbytes) CUDA_TRY(cudaMemcpyAsync(d->d_jobs.p, fills.data(), fbytes, cudaMemcpyHostToDevice, st));
+  if (bbytes) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_jobs.p + fbytes, blits.data(), bbytes, cudaMemcpyHostToDevice, st));
+  if ((rc = run_device_locked(d, d->d_comp.p, ctot, d->d_out.p, ptot, st))) return rc;
+  launch_plane_fill((const PlaneFillJob*)d->d_jobs.p, (int)fills.size(), (const uint8_t*)d->d_comp.p, (uint16_t*)d->d_out.p, st);
+  launch_tile_blit((const TileBlitJob*)((uint8_t*)d->d_jobs.p + fbytes), (int)blits.size(), (const uint16_t*)d->d_out.p, (uint8_t*)d->d_bytes.p, st);
+  d->launches += (fills.empty() ? 0 : 1) + (blits.empty() ? 0 : 1);
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> ust(d->units.size());
+  unit_status_locked(d, ust.data(), (int)ust.size(), st);
+  for (auto& ut : unit_tile)
+    if (ust[ut.first] && !tiles[ut.second].status) tiles[ut.second].status = ust[ut.first];
+  return 0;
+}
+
+int bytes_per_pixel(int channels, int bps) { return bps == 16 ? channels * 2 : channels; }
+
+}  // namespace
+
+extern "C" {
+
+int micgpu_wsi_read_header(const uint8_t* mic3, size_t len, micgpu_wsi_info* info) {
+  if (!mic3 || !info) return fail(MICGPU_E_HEADER, "null argument");
+  Mic3Header h;
+  int rc = parse_mic3(mic3, len, h);
+  if (rc) return rc;
+  memset(info, 0, sizeof *info);
+  info->width = h.width; info->height = h.height; info->tile_w = h.tile_w; info->tile_h = h.tile_h;
+  info->channels = h.channels; info->bits_per_sample = h.bps; info->color_transform = h.ct; info->n_levels = h.nlv;
+  info->total_tiles = h.total_tiles;
+  for (int l = 0; l < h.nlv && l < MICGPU_WSI_MAX_LEVELS; l++) {
+    const Mic3Level lv = mic3_level(mic3, h, l);
+    info->level_w[l] = lv.w; info->level_h[l] = lv.h; info->tiles_x[l] = lv.tx; info->tiles_y[l] = lv.ty; info->first_tile[l] = lv.first;
+  }
+  return 0;
+}
+
+int micgpu_wsi_decompress_tiles(const uint8_t* mic3, size_t len, int n, const int* levels, const int* txs, const int* tys,
+                                uint8_t* const* outs, const size_t* caps, int* widths, int* heights, int* status) {
+  if (!mic3 || n < 0) return fail(MICGPU_E_HEADER, "bad argument");
+  if (n == 0) return 0;
+  Mic3Header h;
+  int rc = parse_mic3(mic3, len, h);
+  if (rc) return rc;
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  const int bpp = bytes_per_pixel(h.channels, h.bps);
+  std::vector<TileReq> tiles(n);
+  std::vector<size_t> ooff(n), osz(n);
+  size_t otot = 0;
+  for (int i = 0; i < n; i++) {
+    TileReq& T = tiles[i];
+    T.tile_w = h.tile_w; T.tile_h = h.tile_h; T.channels = h.channels; T.bps = h.bps; T.ct = h.ct;
+    T.blob = mic3; T.len = 0;
+    ooff[i] = otot; osz[i] = 0;
+    if (levels[i] < 0 || levels[i] >= h.nlv) { T.status = fail(MICGPU_E_HEADER, "MIC3: level %d out of range [0, %d)", levels[i], h.nlv); continue; }
+    const Mic3Level lv = mic3_level(mic3, h, levels[i]);
+    if (txs[i] < 0 || txs[i] >= lv.tx || tys[i] < 0 || tys[i] >= lv.ty) { T.status = fail(MICGPU_E_HEADER, "MIC3: tile (%d,%d) out of range for level %d", txs[i], tys[i], levels[i]); continue; }
+    if ((T.status = mic3_tile_blob(mic3, len, h, (long long)lv.first + (long long)tys[i] * lv.tx + txs[i], &T.blob, &T.len))) continue;
+    // edge tiles are cropped to the level extent (wsicompress.go:200-216)
+    const int aw = std::min(h.tile_w, lv.w - txs[i] * h.tile_w), ah = std::min(h.tile_h, lv.h - tys[i] * h.tile_h);
+    if (widths) widths[i] = aw;
+    if (heights) heights[i] = ah;
+    osz[i] = (size_t)aw * ah * bpp;
+    if (osz[i] > caps[i]) { T.status = fail(MICGPU_E_SIZE, "tile %d: output buffer too small", i); osz[i] = 0; continue; }
+    T.blits.push_back(Blit{0, 0, (unsigned)aw, (unsigned)ah, otot, (unsigned)(aw * bpp)});
+    otot += (osz[i] + 15) & ~(size_t)15;
+  }
+  if ((rc = wsi_run_locked(d, tiles, otot))) return rc;
+  int first = 0;
+  for (int i = 0; i < n; i++) {
+    if (!tiles[i].status && osz[i]) CUDA_TRY(cudaMemcpyAsync(outs[i], (uint8_t*)d->d_bytes.p + ooff[i], osz[i], cudaMemcpyDeviceToHost, d->stream));
+    if (status) status[i] = tiles[i].status;
+    if (!first && tiles[i].status) first = tiles[i].status;
+  }
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return first;
+}
+
+int micgpu_wsi_decompress_tile(const uint8_t* mic3, size_t len, int level, int tx, int ty, uint8_t* out, size_t cap, int* width, int* height) {
+  int w = 0, h = 0, st = 0;
+  const int rc = micgpu_wsi_decompress_tiles(mic3, len, 1, &level, &tx, &ty, &out, &cap, &w, &h, &st);
+  if (width) *width = w;
+  if (height) *height = h;
+  return rc;
+}
+
+// DecompressWSIRegion (wsicompress.go:220-296)
+int micgpu_wsi_decompress_region(const uint8_t* mic3, size_t len, int level, int x, int y, int w, int h, uint8_t* out, size_t cap,
+                                 int* out_w, int* out_h) {
+  if (!mic3 || !out) return fail(MICGPU_E_HEADER, "null argument");
+  Mic3Header hd;
+  int rc = parse_mic3(mic3, len, hd);
+  if (rc) return rc;
+  if (level < 0 || level >= hd.nlv) return fail(MICGPU_E_HEADER, "MIC3: level %d out of range [0, %d)", level, hd.nlv);
+  const Mic3Level lv = mic3_level(mic3, hd, level);
+  if (x < 0 || y < 0) return fail(MICGPU_E_HEADER, "MIC3: negative region origin");
+  if (x + w > lv.w) w = lv.w - x;
+  if (y + h > lv.h) h = lv.h - y;
+  if (w <= 0 || h <= 0) return fail(MICGPU_E_HEADER, "MIC3: empty region");
+  const int bpp = bytes_per_pixel(hd.channels, hd.bps);
+  if ((size_t)w * h * bpp > cap) return fail(MICGPU_E_SIZE, "region output buffer too small");
+  if (out_w) *out_w = w;
+  if (out_h) *out_h = h;
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  const int stx = x / hd.tile_w, sty = y / hd.tile_h, etx = (x + w - 1) / hd.tile_w, ety = (y + h - 1) / hd.tile_h;
+  std::vector<TileReq> tiles;
+  for (int ty = sty; ty <= ety; ty++)
+    for (int tx = stx; tx <= etx; tx++) {
+      TileReq T;
+      T.tile_w = hd.tile_w; T.tile_h = hd.tile_h; T.channels = hd.channels; T.bps = hd.bps; T.ct = hd.ct;
+      if ((rc = mic3_tile_blob(mic3, len, hd, (long long)lv.first + (long long)ty * lv.tx + tx, &T.blob, &T.len))) return rc;
+      const int tsx = tx * hd.tile_w, tsy = ty * hd.tile_h;
+      const int tw = std::min(hd.tile_w, lv.w - tsx), th = std::min(hd.tile_h, lv.h - tsy);
+      const int ox0 = std::max(x, tsx), oy0 = std::max(y, tsy), ox1 = std::min(x + w, tsx + tw), oy1 = std::min(y + h, tsy + th);
+      if (ox1 > ox0 && oy1 > oy0)
+        T.blits.push_back(Blit{(unsigned)(ox0 - tsx), (unsigned)(oy0 - tsy), (unsigned)(ox1 - ox0), (unsigned)(oy1 - oy0),
+                               ((unsigned long long)(oy0 - y) * w + (ox0 - x)) * bpp, (unsigned)(w * bpp)});
+      tiles.push_back(std::move(T));
+    }
+  const size_t obytes = (size_t)w * h * bpp;
+  if ((rc = wsi_run_locked(d, tiles, obytes))) return rc;
+  for (auto& T : tiles)
+    if (T.status) return T.status;
+  CUDA_TRY(cudaMemcpyAsync(out, d->d_bytes.p, obytes, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+// DecompressRGB (rgbcompress.go:31-33): one whole-image "tile" with the colour transform on
+int micgpu_rgb_decompress(const uint8_t* blob, size_t len, int width, int height, uint8_t* rgb_out) {
+  if (!blob || !rgb_out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  std::vector<TileReq> tiles(1);
+  TileReq& T = tiles[0];
+  T.blob = blob; T.len = len; T.tile_w = width; T.tile_h = height; T.channels = 3; T.bps = 8; T.ct = 1;
+  T.blits.push_back(Blit{0, 0, (unsigned)width, (unsigned)height, 0, (unsigned)(width * 3)});
+  const size_t obytes = (size_t)width * height * 3;
+  int rc = wsi_run_locked(d, tiles, obytes);
+  if (rc) return rc;
+  if (T.status) return T.status;
+  CUDA_TRY(cudaMemcpyAsync(rgb_out, d->d_bytes.p, obytes, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
 // ---- reference C twin symbols ----------------------------------------------------
 static int twin_frame(const uint8_t* c, size_t n, uint16_t* o, int w, int h, uint8_t magic) {
   // the C twin checks its magic byte and returns -1 (ojph/mic_decompress_c.c:1004-1010)

@@ -55,6 +55,27 @@ def test_ragged_sizes(mic, oracle, w, h, coder):
     assert np.array_equal(got, img)
 
 
+@pytest.mark.parametrize("w", [296, 297, 298, 299, 300, 301, 302, 303])
+@pytest.mark.parametrize("shift", [0, 3, 5])
+def test_row_phase_all_residues(mic, oracle, w, shift):
+    # every W mod 8 (row-to-row phase step of the wavefront) x several output alignments, no zero borders
+    h = 70
+    rng = np.random.default_rng(w * 10 + shift)
+    y, x = np.mgrid[0:h, 0:w]
+    img = (1500 + 3 * x + 5 * y + rng.integers(0, 30, (h, w))).astype(np.uint16)
+    blob = np.frombuffer(oracle.compress_single_frame(img.ravel(), w, h, int(img.max()), 8), np.uint8)
+    dec = mic.Decoder(0)
+    dec.begin()
+    dec.add_unit(blob, 0, 0, w, h, shift)
+    dec.commit()
+    comp = np.zeros(blob.size + 256, np.uint8)
+    comp[: blob.size] = blob
+    out = np.zeros(w * h + shift, np.uint16)
+    dec.run_host(comp, out)
+    assert np.array_equal(out[shift:], img.ravel())
+    dec.close()
+
+
 def test_escapes_and_runs(mic, oracle):
     # sharp edges (escape + literal), literals equal to the delimiter, long constant runs
     w, h = 500, 120

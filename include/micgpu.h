@@ -130,6 +130,12 @@ int micgpu_wsi_decompress_region(const uint8_t *mic3, size_t len, int level, int
 /* DecompressRGB (rgbcompress.go:31-33) */
 int micgpu_rgb_decompress(const uint8_t *blob, size_t len, int width, int height, uint8_t *rgb_out);
 
+/* ---- WaveletV2 streams ---------------------------------------------------------- */
+/* WaveletV2[SIMD]RLEFSEDecompressU16 (waveletfsecompressu16.go:374,493): rows/cols come from the 11-byte header. */
+int micgpu_wavelet_v2_decompress(const uint8_t *blob, size_t len, uint16_t *pixels_out, size_t cap_px, int *rows, int *cols);
+int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t *const *blobs, const size_t *lens, uint16_t *const *outs, const size_t *caps,
+                                       int *rows, int *cols, int *status);
+
 /* ---- drop-in symbols of the reference C twin (same signatures) -------------- */
 /* ojph/mic_decompress_c.h:24-49 */
 int mic_decompress_two_state(const uint8_t *compressed, size_t compressed_len, uint16_t *pixels_out, int width, int height);

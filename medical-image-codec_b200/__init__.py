@@ -18,6 +18,9 @@ from .api import (  # noqa: F401
     DecompressWSITile,
     DecompressWSITiles,
     ReadWSIHeader,
+    WaveletV2DecompressBatch,
+    WaveletV2RLEFSEDecompressU16,
+    WaveletV2SIMDRLEFSEDecompressU16,
     DecompressSingleFrame,
     MicGpuError,
     lib,

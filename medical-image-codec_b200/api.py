@@ -82,6 +82,8 @@ lib.micgpu_wsi_decompress_tile.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_
 lib.micgpu_wsi_decompress_tiles.argtypes = [C.c_void_p, C.c_size_t, C.c_int, _ip, _ip, _ip, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip, _ip, _ip]
 lib.micgpu_wsi_decompress_region.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_rgb_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+lib.micgpu_wavelet_v2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_wavelet_v2_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip, _ip, _ip]
 for _n in ("two", "four", "eight"):
     for _s in ("", "_simd"):
         getattr(lib, f"mic_decompress_{_n}_state{_s}").argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
@@ -236,6 +238,36 @@ def DecompressRGB(data, width: int, height: int) -> np.ndarray:
     out = np.empty(width * height * 3, np.uint8)
     _check(lib.micgpu_rgb_decompress(a.ctypes.data, a.size, width, height, out.ctypes.data))
     return out
+
+
+def WaveletV2RLEFSEDecompressU16(compressed):
+    """waveletfsecompressu16.go:374 (and the SIMD variant :493) -> (pixels[rows*cols] uint16, rows, cols)."""
+    a = _bytes_view(compressed)
+    if a.size < 11:
+        raise MicGpuError(E_HEADER, "compressed data too short")
+    rows, cols = _rd32(a, 0), _rd32(a, 4)
+    out = np.empty(max(rows * cols, 1), np.uint16)
+    r, c = C.c_int(), C.c_int()
+    _check(lib.micgpu_wavelet_v2_decompress(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(r), C.byref(c)))
+    return out[: rows * cols], r.value, c.value
+
+
+WaveletV2SIMDRLEFSEDecompressU16 = WaveletV2RLEFSEDecompressU16
+
+
+def WaveletV2DecompressBatch(blobs):
+    """n WaveletV2 streams in one launch sequence -> list of (pixels, rows, cols)."""
+    views = [_bytes_view(b) for b in blobs]
+    n = len(views)
+    dims = [(_rd32(a, 0), _rd32(a, 4)) for a in views]
+    outs = [np.empty(max(r * c, 1), np.uint16) for r, c in dims]
+    bp = (C.c_void_p * n)(*[a.ctypes.data for a in views])
+    ln = (C.c_size_t * n)(*[a.size for a in views])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    cp = (C.c_size_t * n)(*[o.size for o in outs])
+    rs, cs, st = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)()
+    _check(lib.micgpu_wavelet_v2_decompress_batch(n, bp, ln, op, cp, rs, cs, st))
+    return [(o[: r * c], r, c) for o, (r, c) in zip(outs, dims)]
 
 
 # ---- batch decoder over device-resident buffers -------------------------------------

@@ -53,6 +53,16 @@ struct TileBlitJob {
 void launch_plane_fill(const PlaneFillJob* d_jobs, int njobs, const uint8_t* d_comp, uint16_t* d_planes, cudaStream_t st);
 void launch_tile_blit(const TileBlitJob* d_jobs, int njobs, const uint16_t* d_planes, uint8_t* d_out, cudaStream_t st);
 
+// WaveletV2 decode (k_wavelet.cu)
+struct WaveletGeom {
+  unsigned rows, cols;
+  int levels;                 // levels actually applied (header byte 10)
+  int nseg;                   // 1 + 3*levels subband segments in stream order
+  unsigned seg_start[25], seg_y0[25], seg_x0[25], seg_w[25];
+};
+void launch_wavelet_decode(MicUnit* d_units, const int* d_unit_of_img, int nimg, const uint16_t* d_stream, int* d_flags,
+                           int32_t* d_A, int32_t* d_B, uint16_t* d_px, const WaveletGeom& G, cudaStream_t st);
+
 // ---- small device helpers ---------------------------------------------------
 __device__ __forceinline__ uint32_t ld_u32_unaligned_safe(const uint8_t* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);

@@ -97,6 +97,7 @@ struct micgpu_decoder {
   int launches = 0;
   DevBuf d_units, d_list, d_tabA, d_tabS, d_states, d_D, d_M, d_k1, d_comp, d_out;
   DevBuf d_jobs, d_bytes;   // MIC3: fill / blit job tables, byte-typed pixel output
+  DevBuf d_wA, d_wB, d_wflags;   // WaveletV2: int32 ping-pong planes, escape flags
   MicUnit* h_units = nullptr;   // pinned staging copy
   size_t h_units_cap = 0;
   cudaStream_t stream = nullptr;  // used by the host-buffer convenience calls
@@ -109,7 +110,7 @@ struct micgpu_decoder {
   ~micgpu_decoder() {
     cudaSetDevice(device);
     d_units.release(); d_list.release(); d_tabA.release(); d_tabS.release(); d_states.release();
-    d_D.release(); d_M.release(); d_k1.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release();
+    d_D.release(); d_M.release(); d_k1.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
     for (auto e : ev) cudaEventDestroy(e);
@@ -1004,6 +1005,129 @@ int micgpu_rgb_decompress(const uint8_t* blob, size_t len, int width, int height
   CUDA_TRY(cudaMemcpyAsync(rgb_out, d->d_bytes.p, obytes, cudaMemcpyDeviceToHost, d->stream));
   CUDA_TRY(cudaStreamSynchronize(d->stream));
   return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+}  // extern "C"
+
+// ---- WaveletV2 ---------------------------------------------------------------------
+namespace {
+
+WaveletGeom wavelet_geom(unsigned rows, unsigned cols, int levels) {
+  WaveletGeom G;
+  memset(&G, 0, sizeof G);
+  G.rows = rows; G.cols = cols; G.levels = levels;
+  unsigned nr[10], nc[10];
+  nr[0] = rows; nc[0] = cols;
+  for (int l = 1; l <= levels; l++) { nr[l] = (nr[l - 1] + 1) / 2; nc[l] = (nc[l - 1] + 1) / 2; }
+  unsigned pos = 0;
+  int n = 0;
+  auto add = [&](unsigned y0, unsigned y1, unsigned x0, unsigned x1) {   // collectSubbandOrder (waveletfsecompressu16.go:202-241)
+    G.seg_start[n] = pos; G.seg_y0[n] = y0; G.seg_x0[n] = x0; G.seg_w[n] = x1 > x0 ? x1 - x0 : 1;
+    if (y1 > y0 && x1 > x0) pos += (y1 - y0) * (x1 - x0);
+    n++;
+  };
+  add(0, nr[levels], 0, nc[levels]);
+  for (int l = levels; l >= 1; l--) {
+    add(0, nr[l], nc[l], nc[l - 1]);
+    add(nr[l], nr[l - 1], 0, nc[l]);
+    add(nr[l], nr[l - 1], nc[l], nc[l - 1]);
+  }
+  G.nseg = n;
+  return G;
+}
+
+}  // namespace
+
+extern "C" {
+
+// WaveletV2RLEFSEDecompressU16 / WaveletV2SIMDRLEFSEDecompressU16 (waveletfsecompressu16.go:374-421,493-534) for n streams
+int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs, const size_t* caps,
+                                       int* rows_out, int* cols_out, int* status) {
+  if (n <= 0) return 0;
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  d->units.clear();
+  d->temporal.clear();
+  d->out_need = 0;
+  struct Img { unsigned rows, cols; int levels, unit, st; uint64_t coff, px_off; };
+  std::vector<Img> im(n);
+  uint64_t ctot = 0, stot = 0, ptot = 0;
+  for (int i = 0; i < n; i++) {
+    Img& I = im[i];
+    I.st = 0; I.unit = -1; I.coff = ctot; I.px_off = ptot; I.rows = I.cols = 0; I.levels = 0;
+    ctot += (lens[i] + 63) & ~(size_t)63;
+    if (lens[i] < 11 + 6) { I.st = fail(MICGPU_E_HEADER, "compressed data too short"); continue; }
+    I.rows = rd32(blobs[i]); I.cols = rd32(blobs[i] + 4); I.levels = blobs[i][10];
+    if (rows_out) rows_out[i] = (int)I.rows;
+    if (cols_out) cols_out[i] = (int)I.cols;
+    const uint64_t px = (uint64_t)I.rows * I.cols;
+    if (I.rows == 0 || I.cols == 0 || px > (1ull << 31) || I.levels > 8) { I.st = fail(MICGPU_E_HEADER, "bad wavelet header"); continue; }
+    if (blobs[i][11] != 0xFF || blobs[i][12] != 0x04) { I.st = fail(MICGPU_E_HEADER, "fse4state: missing magic bytes"); continue; }
+    if (px > caps[i]) { I.st = fail(MICGPU_E_SIZE, "image %d: output buffer too small", i); continue; }
+    // coefficient stream: one u16 per coefficient, three per escaped coefficient; the FSE symbol count bounds it
+    const uint64_t count = rd32(blobs[i] + 13);
+    const uint64_t cap = std::min<uint64_t>(3 * px, std::max<uint64_t>(px, 65535ull * count));
+    I.unit = add_unit_locked(d, blobs[i] + 11, lens[i] - 11, I.coff + 11, MIC_KIND_RLE, (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFFFull), 1, stot);
+    stot += (cap + 15) & ~15ull;
+    ptot += px;
+  }
+  int rc = plan_commit(d);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if ((rc = d->d_comp.ensure(ctot + 256))) return rc;
+  if ((rc = d->d_out.ensure(std::max<uint64_t>(stot, 1) * sizeof(uint16_t)))) return rc;
+  if ((rc = d->d_bytes.ensure(std::max<uint64_t>(ptot, 1) * sizeof(uint16_t)))) return rc;
+  if ((rc = d->d_wA.ensure(std::max<uint64_t>(ptot, 1) * sizeof(int32_t)))) return rc;
+  if ((rc = d->d_wB.ensure(std::max<uint64_t>(ptot, 1) * sizeof(int32_t)))) return rc;
+  if ((rc = d->d_wflags.ensure((size_t)n * 2 * sizeof(int) + 64))) return rc;
+  cudaStream_t st = d->stream;
+  for (int i = 0; i < n; i++)
+    if (!im[i].st) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_comp.p + im[i].coff, blobs[i], lens[i], cudaMemcpyHostToDevice, st));
+  if ((rc = run_device_locked(d, d->d_comp.p, ctot, d->d_out.p, stot, st))) return rc;
+  // group images with the same geometry: they share one launch sequence (grid.z = image)
+  std::vector<char> done(n, 0);
+  std::vector<int> uoi(n);
+  int* d_flags = (int*)d->d_wflags.p;
+  int* d_uoi = d_flags + n;
+  for (int i = 0; i < n; i++) {
+    if (done[i] || im[i].st) continue;
+    // images of a group must be contiguous in the plane buffers: collect consecutive equal geometries
+    int j = i, cnt = 0;
+    while (j < n && !im[j].st && im[j].rows == im[i].rows && im[j].cols == im[i].cols && im[j].levels == im[i].levels) {
+      uoi[cnt++] = im[j].unit;
+      done[j] = 1;
+      j++;
+    }
+    const WaveletGeom G = wavelet_geom(im[i].rows, im[i].cols, im[i].levels);
+    CUDA_TRY(cudaMemcpyAsync(d_uoi, uoi.data(), cnt * sizeof(int), cudaMemcpyHostToDevice, st));
+    launch_wavelet_decode((MicUnit*)d->d_units.p, d_uoi, cnt, (const uint16_t*)d->d_out.p, d_flags, (int32_t*)d->d_wA.p + im[i].px_off,
+                          (int32_t*)d->d_wB.p + im[i].px_off, (uint16_t*)d->d_bytes.p + im[i].px_off, G, st);
+    d->launches += 2 + 2 * std::max(1, G.levels);
+    CUDA_TRY(cudaStreamSynchronize(st));   // d_uoi / d_flags are reused by the next group
+  }
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> ust(d->units.size());
+  unit_status_locked(d, ust.data(), (int)ust.size(), st);
+  int first = 0;
+  for (int i = 0; i < n; i++) {
+    if (!im[i].st && im[i].unit >= 0 && ust[im[i].unit]) im[i].st = ust[im[i].unit];
+    if (!im[i].st)
+      CUDA_TRY(cudaMemcpyAsync(outs[i], (uint16_t*)d->d_bytes.p + im[i].px_off, (size_t)im[i].rows * im[i].cols * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    if (status) status[i] = im[i].st;
+    if (!first && im[i].st) first = im[i].st;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (first) fail(first, "wavelet stream decode failed (status %d)", first);
+  return first;
+}
+
+int micgpu_wavelet_v2_decompress(const uint8_t* blob, size_t len, uint16_t* pixels_out, size_t cap_px, int* rows, int* cols) {
+  if (!blob || !pixels_out) return fail(MICGPU_E_HEADER, "null argument");
+  return micgpu_wavelet_v2_decompress_batch(1, &blob, &len, &pixels_out, &cap_px, rows, cols, nullptr);
 }
 
 }  // extern "C"

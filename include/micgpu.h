@@ -32,6 +32,9 @@ extern "C" {
 #define MICGPU_E_RLE (-8)         /* RLE stream malformed / too short */
 #define MICGPU_E_SIZE (-9)        /* output capacity / geometry mismatch */
 #define MICGPU_E_UNSUPPORTED (-10)
+#define MICGPU_E_INCOMPRESSIBLE (-11) /* ErrIncompressible (fseu16.go:33) */
+#define MICGPU_E_USE_RLE (-12)        /* ErrUseRLE (fseu16.go:36) */
+#define MICGPU_E_INTERNAL (-13)       /* FSE normalisation / table construction failed */
 #define MICGPU_E_CUDA (-20)       /* CUDA runtime failure or no device */
 
 /* unit kinds for micgpu_decoder_add_unit */
@@ -135,6 +138,26 @@ int micgpu_rgb_decompress(const uint8_t *blob, size_t len, int width, int height
 int micgpu_wavelet_v2_decompress(const uint8_t *blob, size_t len, uint16_t *pixels_out, size_t cap_px, int *rows, int *cols);
 int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t *const *blobs, const size_t *lens, uint16_t *const *outs, const size_t *caps,
                                        int *rows, int *cols, int *status);
+
+/* ---- encode direction -------------------------------------------------------------- */
+/* Stage calls (used by the parity tests): DeltaRleCompressU16.Compress (deltarlecompressu16.go:24) and
+ * RleCompressU16.Init(len,1,maxValue)+Compress (rlecompressu16.go:15-93). */
+int micgpu_delta_rle_compress(const uint16_t *pixels, int width, int height, uint16_t max_value, uint16_t *out, size_t cap, size_t *out_len);
+int micgpu_rle_compress(const uint16_t *in, size_t n, uint16_t max_value, uint16_t *out, size_t cap, size_t *out_len);
+/* CompressSingleFrame (nstates 2), CompressSingleFrame4State (4), CompressSingleFrame8State (8) with the reference's
+ * fallback ladder (multiframecompress.go:15-93); nstates 1 = Delta+RLE + FSECompressU16.  maxValue is the caller's. */
+int micgpu_compress_single_frame(const uint16_t *pixels, int width, int height, uint16_t max_value, int nstates, uint8_t *out, size_t cap,
+                                 size_t *out_len);
+/* CompressParallelStrips / 4State / 8State (parallelstrips.go:55,128,199); num_strips must be > 0 (GOMAXPROCS is the caller's). */
+int micgpu_pics_compress(const uint16_t *pixels, int width, int height, uint16_t max_value, int num_strips, int nstates, uint8_t *out,
+                         size_t cap, size_t *out_len);
+int micgpu_pics_compress_batch(int n, const uint16_t *const *pixels, int width, int height, const uint16_t *max_values, int num_strips,
+                               int nstates, uint8_t *const *outs, const size_t *caps, size_t *out_lens, int *status);
+void micgpu_encoder_shutdown(void);
+/* ojph/mic_compress_c.h:26-37 (maxValue derived from the pixels, no fallback ladder) */
+int mic_compress_two_state(const uint16_t *pixels, int width, int height, uint8_t *out, size_t out_cap, size_t *out_len);
+int mic_compress_four_state(const uint16_t *pixels, int width, int height, uint8_t *out, size_t out_cap, size_t *out_len);
+int mic_compress_eight_state(const uint16_t *pixels, int width, int height, uint8_t *out, size_t out_cap, size_t *out_len);
 
 /* ---- drop-in symbols of the reference C twin (same signatures) -------------- */
 /* ojph/mic_decompress_c.h:24-49 */

@@ -8,6 +8,13 @@ native library is missing.
 """
 from . import api  # noqa: F401
 from .api import (  # noqa: F401
+    CompressParallelStrips,
+    CompressParallelStripsBatch,
+    CompressSingleFrame,
+    CompressSingleFrame4State,
+    CompressSingleFrame8State,
+    DeltaRleCompress,
+    RleCompress,
     Decoder,
     DecompressFrame,
     DecompressMultiFrame,

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmicgpu.so")
 
 E_HEADER, E_NCOUNT, E_ALLOC, E_DTABLE, E_BITSTREAM, E_RLE, E_SIZE, E_UNSUPPORTED, E_CUDA = -1, -2, -3, -4, -6, -8, -9, -10, -20
+E_INCOMPRESSIBLE, E_USE_RLE, E_INTERNAL = -11, -12, -13
 KIND_SPATIAL, KIND_RLE = 0, 1
 
 
@@ -84,6 +85,15 @@ lib.micgpu_wsi_decompress_region.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.
 lib.micgpu_rgb_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
 lib.micgpu_wavelet_v2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_wavelet_v2_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip, _ip, _ip]
+_szp = C.POINTER(C.c_size_t)
+lib.micgpu_delta_rle_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_rle_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_uint16, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_compress_single_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_pics_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_pics_compress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_int,
+                                           C.POINTER(C.c_void_p), _szp, _szp, _ip]
+for _n in ("two", "four", "eight"):
+    getattr(lib, f"mic_compress_{_n}_state").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
 for _n in ("two", "four", "eight"):
     for _s in ("", "_simd"):
         getattr(lib, f"mic_decompress_{_n}_state{_s}").argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
@@ -268,6 +278,72 @@ def WaveletV2DecompressBatch(blobs):
     rs, cs, st = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)()
     _check(lib.micgpu_wavelet_v2_decompress_batch(n, bp, ln, op, cp, rs, cs, st))
     return [(o[: r * c], r, c) for o, (r, c) in zip(outs, dims)]
+
+
+# ---- encode direction ---------------------------------------------------------------------------
+def _u16(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint16).ravel()
+
+
+def DeltaRleCompress(pixels, width: int, height: int, max_value: int) -> np.ndarray:
+    """DeltaRleCompressU16.Compress (deltarlecompressu16.go:24) -> RLE symbol stream."""
+    a = _u16(pixels)
+    out = np.empty(2 * a.size + a.size // 2 + 64, np.uint16)
+    n = C.c_size_t()
+    _check(lib.micgpu_delta_rle_compress(a.ctypes.data, width, height, max_value, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].copy()
+
+
+def RleCompress(symbols, max_value: int) -> np.ndarray:
+    """RleCompressU16.Init(len,1,maxValue) + Compress (rlecompressu16.go:15-93)."""
+    a = _u16(symbols)
+    out = np.empty(a.size + a.size // 4 + 64, np.uint16)
+    n = C.c_size_t()
+    _check(lib.micgpu_rle_compress(a.ctypes.data, a.size, max_value, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].copy()
+
+
+def CompressSingleFrame(pixels, width: int, height: int, max_value: int, nstates: int = 2) -> bytes:
+    """CompressSingleFrame / 4State / 8State (multiframecompress.go:15,38,67); nstates=1: FSECompressU16 tier only."""
+    a = _u16(pixels)
+    out = np.empty(4 * a.size + 8192, np.uint8)
+    n = C.c_size_t()
+    _check(lib.micgpu_compress_single_frame(a.ctypes.data, width, height, max_value, nstates, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def CompressSingleFrame4State(pixels, width, height, max_value) -> bytes:
+    return CompressSingleFrame(pixels, width, height, max_value, 4)
+
+
+def CompressSingleFrame8State(pixels, width, height, max_value) -> bytes:
+    return CompressSingleFrame(pixels, width, height, max_value, 8)
+
+
+def CompressParallelStrips(pixels, width: int, height: int, max_value: int, num_strips: int, nstates: int = 2) -> bytes:
+    """CompressParallelStrips / 4State / 8State (parallelstrips.go:55,128,199)."""
+    a = _u16(pixels)
+    if a.size != width * height:
+        raise MicGpuError(E_HEADER, f"parallelstrips: pixel count {a.size} != width*height {width * height}")
+    out = np.empty(4 * a.size + 8192 * max(num_strips, 1), np.uint8)
+    n = C.c_size_t()
+    _check(lib.micgpu_pics_compress(a.ctypes.data, width, height, max_value, num_strips, nstates, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def CompressParallelStripsBatch(images, width: int, height: int, max_values, num_strips: int, nstates: int = 2):
+    """n images of one geometry in one launch sequence -> list of PICS blobs."""
+    arrs = [_u16(im) for im in images]
+    n = len(arrs)
+    outs = [np.empty(4 * width * height + 8192 * max(num_strips, 1), np.uint8) for _ in range(n)]
+    pp = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    mv = (C.c_uint16 * n)(*[int(m) for m in max_values])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    cp = (C.c_size_t * n)(*[o.size for o in outs])
+    ol = (C.c_size_t * n)()
+    st = (C.c_int * n)()
+    _check(lib.micgpu_pics_compress_batch(n, pp, width, height, mv, num_strips, nstates, op, cp, ol, st))
+    return [outs[i][: ol[i]].tobytes() for i in range(n)]
 
 
 # ---- batch decoder over device-resident buffers -------------------------------------

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mic_enc.h"
 #include "mic_unit.h"
 
 namespace micgpu {
@@ -62,6 +63,16 @@ struct WaveletGeom {
 };
 void launch_wavelet_decode(MicUnit* d_units, const int* d_unit_of_img, int nimg, const uint16_t* d_stream, int* d_flags,
                            int32_t* d_A, int32_t* d_B, uint16_t* d_px, const WaveletGeom& G, cudaStream_t st);
+
+// Encode side (k_enc_rle.cu, k_enc_fse.cu)
+void launch_enc_delta_rle(MicEncUnit* d_units, int nunits, const uint16_t* d_src, uint16_t* d_V, uint32_t* d_segs, uint16_t* d_S,
+                          int grid, cudaStream_t st);
+void launch_enc_tables(MicEncUnit* d_units, int nunits, const uint16_t* d_S, uint8_t* d_scratch, uint16_t* d_state_tab, uint2* d_sym_tt,
+                       uint8_t* d_hdrs, int grid, cudaStream_t st);
+unsigned long long enc_tables_scratch_per_cta();
+void launch_enc_ans(MicEncUnit* d_units, const int* d_list, int nlist, int nstates, const uint16_t* d_S, const uint16_t* d_state_tab,
+                    const uint2* d_sym_tt, uint32_t* d_T, int sm_count, cudaStream_t st);
+void launch_enc_pack(MicEncUnit* d_units, int nunits, const uint32_t* d_T, const uint8_t* d_hdrs, uint8_t* d_frames, int grid, cudaStream_t st);
 
 // ---- small device helpers ---------------------------------------------------
 __device__ __forceinline__ uint32_t ld_u32_unaligned_safe(const uint8_t* p) {

@@ -15,54 +15,14 @@
 #include <string>
 #include <vector>
 
-#include "../../include/micgpu.h"
+#include "host_common.h"
 #include "mic_device.cuh"
 
 using namespace micgpu;
 
+using namespace micgpu_host;
+
 namespace {
-
-thread_local std::string g_err;
-
-int fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  g_err = buf;
-  return code;
-}
-
-#define CUDA_TRY(expr)                                                                      \
-  do {                                                                                      \
-    cudaError_t _e = (expr);                                                                \
-    if (_e != cudaSuccess) return fail(MICGPU_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
-  } while (0)
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t bytes) {
-    if (bytes <= cap) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
-      p = nullptr;
-      return fail(MICGPU_E_ALLOC, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
-    }
-    cap = want;
-    return 0;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
 
 uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
@@ -427,12 +387,6 @@ micgpu_decoder* default_decoder(int dev) {
   return g_default[dev];
 }
 
-int current_device() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  return dev;
-}
-
 // host comp -> device, run, device -> host
 int run_host_locked(micgpu_decoder* d, const uint8_t* comp, size_t comp_bytes, uint16_t* out, size_t out_elems) {
   CUDA_TRY(cudaSetDevice(d->device));
@@ -456,7 +410,7 @@ int micgpu_device_count(void) {
   return n;
 }
 
-const char* micgpu_last_error(void) { return g_err.c_str(); }
+const char* micgpu_last_error(void) { return err_slot().c_str(); }
 
 void* micgpu_host_alloc(size_t bytes) {
   void* p = nullptr;

@@ -153,6 +153,18 @@ int micgpu_pics_compress(const uint16_t *pixels, int width, int height, uint16_t
                          size_t cap, size_t *out_len);
 int micgpu_pics_compress_batch(int n, const uint16_t *const *pixels, int width, int height, const uint16_t *max_values, int num_strips,
                                int nstates, uint8_t *const *outs, const size_t *caps, size_t *out_lens, int *status);
+/* CompressMultiFrame (multiframecompress.go:179): frames contiguous, independent or temporal (ZigZag residual) mode. */
+int micgpu_mic2_compress(const uint16_t *frames, int width, int height, int nframes, uint16_t max_value, int temporal, uint8_t *out,
+                         size_t cap, size_t *out_len);
+/* WaveletV2[SIMD]RLEFSECompressU16 (waveletfsecompressu16.go:303,427); note the (rows, cols) argument order of the Go API. */
+int micgpu_wavelet_v2_compress(const uint16_t *pixels, int rows, int cols, uint16_t max_value, int levels, uint8_t *out, size_t cap,
+                               size_t *out_len);
+int micgpu_wavelet_v2_compress_batch(int n, const uint16_t *const *pixels, int rows, int cols, const uint16_t *max_values, int levels,
+                                     uint8_t *const *outs, const size_t *caps, size_t *out_lens, int *status);
+/* CompressRGB (rgbcompress.go:25) and CompressWSI (wsicompress.go:27; tile_w/tile_h 0 = 256, pyramid_levels <= 0 = auto). */
+int micgpu_rgb_compress(const uint8_t *rgb, int width, int height, uint8_t *out, size_t cap, size_t *out_len);
+int micgpu_wsi_compress(const uint8_t *pixels, int width, int height, int channels, int bits_per_sample, int tile_w, int tile_h,
+                        int pyramid_levels, uint8_t *out, size_t cap, size_t *out_len);
 void micgpu_encoder_shutdown(void);
 /* ojph/mic_compress_c.h:26-37 (maxValue derived from the pixels, no fallback ladder) */
 int mic_compress_two_state(const uint16_t *pixels, int width, int height, uint8_t *out, size_t out_cap, size_t *out_len);

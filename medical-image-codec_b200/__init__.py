@@ -8,7 +8,13 @@ native library is missing.
 """
 from . import api  # noqa: F401
 from .api import (  # noqa: F401
+    CompressMultiFrame,
     CompressParallelStrips,
+    CompressRGB,
+    CompressWSI,
+    WaveletV2CompressBatch,
+    WaveletV2RLEFSECompressU16,
+    WaveletV2SIMDRLEFSECompressU16,
     CompressParallelStripsBatch,
     CompressSingleFrame,
     CompressSingleFrame4State,

@@ -92,6 +92,12 @@ lib.micgpu_compress_single_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_u
 lib.micgpu_pics_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
 lib.micgpu_pics_compress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_int,
                                            C.POINTER(C.c_void_p), _szp, _szp, _ip]
+lib.micgpu_mic2_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_wavelet_v2_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_wavelet_v2_compress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int,
+                                                 C.POINTER(C.c_void_p), _szp, _szp, _ip]
+lib.micgpu_rgb_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_wsi_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
 for _n in ("two", "four", "eight"):
     getattr(lib, f"mic_compress_{_n}_state").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
 for _n in ("two", "four", "eight"):
@@ -344,6 +350,62 @@ def CompressParallelStripsBatch(images, width: int, height: int, max_values, num
     st = (C.c_int * n)()
     _check(lib.micgpu_pics_compress_batch(n, pp, width, height, mv, num_strips, nstates, op, cp, ol, st))
     return [outs[i][: ol[i]].tobytes() for i in range(n)]
+
+
+def CompressMultiFrame(frames, width: int, height: int, max_value: int, temporal: bool) -> bytes:
+    """multiframecompress.go:179 (frames: array [n, h, w] or list of flat frames)."""
+    a = np.ascontiguousarray(np.asarray(frames), dtype=np.uint16).ravel()
+    n = a.size // (width * height)
+    out = np.empty(4 * a.size + 8192 * max(n, 1), np.uint8)
+    ol = C.c_size_t()
+    _check(lib.micgpu_mic2_compress(a.ctypes.data, width, height, n, max_value, int(bool(temporal)), out.ctypes.data, out.size, C.byref(ol)))
+    return out[: ol.value].tobytes()
+
+
+def WaveletV2RLEFSECompressU16(pixels, rows: int, cols: int, max_value: int, levels: int) -> bytes:
+    """waveletfsecompressu16.go:303 (and the SIMD variant :427)."""
+    a = _u16(pixels)
+    out = np.empty(8 * a.size + 8192, np.uint8)
+    ol = C.c_size_t()
+    _check(lib.micgpu_wavelet_v2_compress(a.ctypes.data, rows, cols, max_value, levels, out.ctypes.data, out.size, C.byref(ol)))
+    return out[: ol.value].tobytes()
+
+
+WaveletV2SIMDRLEFSECompressU16 = WaveletV2RLEFSECompressU16
+
+
+def WaveletV2CompressBatch(images, rows: int, cols: int, max_values, levels: int):
+    arrs = [_u16(im) for im in images]
+    n = len(arrs)
+    outs = [np.empty(8 * rows * cols + 8192, np.uint8) for _ in range(n)]
+    pp = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    mv = (C.c_uint16 * n)(*[int(m) for m in max_values])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    cp = (C.c_size_t * n)(*[o.size for o in outs])
+    ol = (C.c_size_t * n)()
+    st = (C.c_int * n)()
+    _check(lib.micgpu_wavelet_v2_compress_batch(n, pp, rows, cols, mv, levels, op, cp, ol, st))
+    return [outs[i][: ol[i]].tobytes() for i in range(n)]
+
+
+def CompressRGB(rgb, width: int, height: int) -> bytes:
+    """rgbcompress.go:25."""
+    a = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+    out = np.empty(8 * a.size + 8192, np.uint8)
+    ol = C.c_size_t()
+    _check(lib.micgpu_rgb_compress(a.ctypes.data, width, height, out.ctypes.data, out.size, C.byref(ol)))
+    return out[: ol.value].tobytes()
+
+
+def CompressWSI(pixels, width: int, height: int, channels: int = 3, bits_per_sample: int = 8, tile_width: int = 256, tile_height: int = 256,
+                pyramid_levels: int = 0) -> bytes:
+    """wsicompress.go:27 with WSIOptions{TileWidth, TileHeight, PyramidLevels}; ColorTransform defaults on for RGB."""
+    a = np.ascontiguousarray(pixels, dtype=np.uint8).ravel()
+    out = np.empty(8 * a.size + (1 << 20), np.uint8)
+    ol = C.c_size_t()
+    _check(lib.micgpu_wsi_compress(a.ctypes.data, width, height, channels, bits_per_sample, tile_width, tile_height, pyramid_levels,
+                                   out.ctypes.data, out.size, C.byref(ol)))
+    return out[: ol.value].tobytes()
 
 
 # ---- batch decoder over device-resident buffers -------------------------------------

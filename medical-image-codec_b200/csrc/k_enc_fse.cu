@@ -75,7 +75,7 @@ __device__ int normalize_count2(const unsigned* count, int* norm, unsigned symle
     if (c <= low_one) { norm[i] = 1; distributed++; total -= c; continue; }
     norm[i] = NYA;
   }
-  if (distributed >= (1u << tl)) return MIC_ENC_INTERNAL;   // Go underflows toDistribute and spins (see oracle)
+  if (distributed >= (1u << tl)) return MIC_ENC_INTERNAL;   // Go underflows toDistribute and spins for ~2^32 iterations
   unsigned to_distribute = (1u << tl) - distributed;
   if ((total / to_distribute) > low_one) {
     low_one = (total * 3) / (to_distribute * 2);

@@ -15,7 +15,7 @@
 //     m-K*P; a trailing stretch (Flush) uses m instead of m+2.
 //   So: flag segment starts from a 5-symbol neighbourhood, compact them, scan their output sizes, and let one
 //   warp per segment write headers and payload.  tests/test_gpu_encode.py checks the streams word for word
-//   against the oracle on long runs, 2-runs, forced flushes and run/stretch boundaries at every residue.
+//   against the CPU oracle on long runs, 2-runs, forced flushes and run/stretch boundaries at every residue.
 #include "mic_device.cuh"
 #include "mic_enc.h"
 
@@ -130,7 +130,8 @@ k_enc_rle_segments(MicEncUnit* __restrict__ units, int nunits, const uint16_t* _
     if (U->kind == MIC_ENC_RLE) {
       if (threadIdx.x == 0) U->v_len = U->width;
       // rleMaxVal / resMax = max over V when the caller asks for it (multiframecompress.go:194-199)
-      if (U->max_value == 0xFFFFFFFFu) {
+      if (U->max_value >= 0xFFFFFFFEu) {
+        const bool pow2 = U->max_value == 0xFFFFFFFEu;
         const uint16_t* v = src + U->src_off;
         unsigned m = 0;
         for (unsigned i = threadIdx.x; i < U->width; i += E_THREADS) m = max(m, (unsigned)v[i]);
@@ -139,6 +140,7 @@ k_enc_rle_segments(MicEncUnit* __restrict__ units, int nunits, const uint16_t* _
         __syncthreads();
         if (threadIdx.x == 0) {
           for (int w = 1; w < E_THREADS / 32; w++) m = max(m, s_max[w]);
+          if (pow2) { int dep = 32 - __clz(m); if (dep < 1) dep = 1; m = (1u << dep) - 1u; }
           U->max_value = m;
         }
       }

@@ -74,6 +74,24 @@ void launch_enc_ans(MicEncUnit* d_units, const int* d_list, int nlist, int nstat
                     const uint2* d_sym_tt, uint32_t* d_T, int sm_count, cudaStream_t st);
 void launch_enc_pack(MicEncUnit* d_units, int nunits, const uint32_t* d_T, const uint8_t* d_hdrs, uint8_t* d_frames, int grid, cudaStream_t st);
 
+// Encode front ends (k_enc_front.cu)
+struct TilePlaneJob {
+  unsigned long long img_off;     // byte offset of the level image in the image buffer
+  unsigned long long plane_off;   // element offset of the tile's first plane
+  unsigned int img_w, img_h, x0, y0, tile_w, tile_h;
+  unsigned int mode;              // 0 RGB8 -> Y,Co,Cg ; 1 RGB8 -> R,G,B ; 2 grey8 ; 3 grey16
+  unsigned int pad;
+};
+struct GatherJob { unsigned long long src_off, dst_off, len; };
+void launch_temporal_residual(const uint16_t* d_frames, uint16_t* d_res, unsigned long long fpx, int nframes, int sm_count, cudaStream_t st);
+void launch_downsample2x(const uint8_t* d_src, uint8_t* d_dst, unsigned w, unsigned h, unsigned ch, unsigned bytes_per_sample, int sm_count, cudaStream_t st);
+void launch_tile_planes(const TilePlaneJob* d_jobs, int njobs, const uint8_t* d_images, uint16_t* d_planes, cudaStream_t st);
+void launch_plane_stats(const uint16_t* d_planes, const unsigned long long* d_offs, unsigned long long npx, int nplanes, unsigned* d_stats, cudaStream_t st);
+void launch_wavelet_forward(const uint16_t* d_px, int32_t* d_A, int32_t* d_B, int nimg, const WaveletGeom& G, int sm_count, cudaStream_t st);
+void launch_wavelet_pack(const int32_t* d_A, uint16_t* d_V, MicEncUnit* d_units, const int* d_unit_of_img, int nimg, const WaveletGeom& G, cudaStream_t st);
+void launch_gather_bytes(const GatherJob* d_jobs, int njobs, const uint8_t* d_src, uint8_t* d_dst, cudaStream_t st);
+void launch_plane_raw(const GatherJob* d_jobs, int njobs, const uint16_t* d_planes, uint8_t* d_dst, cudaStream_t st);
+
 // ---- small device helpers ---------------------------------------------------
 __device__ __forceinline__ uint32_t ld_u32_unaligned_safe(const uint8_t* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);

@@ -32,9 +32,12 @@ struct MicEncUnit {
   unsigned long long hdr_off;   // byte offset in the ncount-header scratch
   unsigned long long out_off;   // byte offset of this unit's frame in the frame scratch
   unsigned int width, height;   // spatial geometry; RLE kind: width = length of V, height = 1
-  unsigned int max_value;       // caller's maxValue (spatial) / resMax or rleMaxVal (RLE kind); 0xFFFFFFFF: take max(V)
+  unsigned int max_value;       // caller's maxValue (spatial) / resMax or rleMaxVal (RLE kind);
+                                // 0xFFFFFFFF: max(V) (resMax, multiframecompress.go:194-199); 0xFFFFFFFE: (1<<bits.Len16(max(V)))-1,
+                                // depth >= 1 (rleMaxVal, waveletfsecompressu16.go:337-343)
   unsigned int kind;
   unsigned int nstates;         // requested tier 8/4/2/1
+  unsigned int no_ladder;       // 1: a rejected tier is final (WaveletV2 uses FSECompressU16FourState with no fallback)
   unsigned int v_cap, s_cap, out_cap;
   // ---- device-filled ----------------------------------------------------
   unsigned int v_len;           // symbols in V

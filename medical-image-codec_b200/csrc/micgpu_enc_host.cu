@@ -1,6 +1,7 @@
 // micgpu_enc_host.cu -- host side of the encode direction: unit planning, the 8->4->2->1 FSE ladder
 // (multiframecompress.go:15-93), container assembly (parallelstrips.go:55-123, multiframe.go:49-92) and the C ABI.
 #include <algorithm>
+#include <functional>
 #include <mutex>
 #include <vector>
 
@@ -18,13 +19,16 @@ struct micgpu_encoder {
   std::vector<MicEncUnit> units;
   unsigned long long src_total = 0;
   DevBuf d_units, d_list, d_src, d_V, d_S, d_segs, d_T, d_tab, d_tt, d_hdr, d_frames, d_k6;
+  DevBuf d_img, d_planes, d_jobs, d_stats, d_compact, d_wA, d_wB;   // front ends
   MicEncUnit* h_units = nullptr;
   size_t h_units_cap = 0;
   cudaStream_t stream = nullptr;
   int launches = 0;
   ~micgpu_encoder() {
     cudaSetDevice(device);
-    for (DevBuf* b : {&d_units, &d_list, &d_src, &d_V, &d_S, &d_segs, &d_T, &d_tab, &d_tt, &d_hdr, &d_frames, &d_k6}) b->release();
+    for (DevBuf* b : {&d_units, &d_list, &d_src, &d_V, &d_S, &d_segs, &d_T, &d_tab, &d_tt, &d_hdr, &d_frames, &d_k6, &d_img, &d_planes, &d_jobs,
+                      &d_stats, &d_compact, &d_wA, &d_wB})
+      b->release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -106,7 +110,9 @@ void enc_plan(micgpu_encoder* e, EncTotals& T) {
 
 // Runs the whole encode pipeline for e->units whose sources sit in d_src (u16 elements). On return h_units holds the
 // device-filled fields and frames are in e->d_frames at out_off.
-int enc_run(micgpu_encoder* e, const uint16_t* d_src) {
+using EncHook = std::function<void(MicEncUnit*, cudaStream_t)>;
+
+int enc_run(micgpu_encoder* e, const uint16_t* d_src, const EncHook& after_upload = EncHook()) {
   CUDA_TRY(cudaSetDevice(e->device));
   const int nu = (int)e->units.size();
   e->launches = 0;
@@ -136,6 +142,7 @@ int enc_run(micgpu_encoder* e, const uint16_t* d_src) {
   memcpy(e->h_units, e->units.data(), (size_t)nu * sizeof(MicEncUnit));
   CUDA_TRY(cudaMemcpyAsync(e->d_units.p, e->h_units, (size_t)nu * sizeof(MicEncUnit), cudaMemcpyHostToDevice, st));
   MicEncUnit* du = (MicEncUnit*)e->d_units.p;
+  if (after_upload) after_upload(du, st);
   launch_enc_delta_rle(du, nu, d_src, (uint16_t*)e->d_V.p, (uint32_t*)e->d_segs.p, (uint16_t*)e->d_S.p, grid, st);
   launch_enc_tables(du, nu, (const uint16_t*)e->d_S.p, (uint8_t*)e->d_k6.p, (uint16_t*)e->d_tab.p, (uint2*)e->d_tt.p, (uint8_t*)e->d_hdr.p, grid, st);
   e->launches += 5;
@@ -172,7 +179,7 @@ int enc_run(micgpu_encoder* e, const uint16_t* d_src) {
     for (int i : pending) {
       const MicEncUnit& r = e->h_units[i];
       if (r.status != MIC_ENC_OK && r.status != MIC_ENC_CAPACITY && r.status != MIC_ENC_UNSUPPORTED && e->units[i].nstates > 1 &&
-          r.table_log != 0) {   // table_log == 0: the shared front half (histogram / normalisation) failed -> every tier fails the same way
+          !e->units[i].no_ladder && r.table_log != 0) {   // table_log == 0: the shared front half (histogram / normalisation) failed -> every tier fails the same way
         e->units[i] = r;
         e->units[i].nstates = e->units[i].nstates / 2;
         e->units[i].status = MIC_ENC_OK;
@@ -341,6 +348,381 @@ int micgpu_pics_compress_batch(int n, const uint16_t* const* pixels, int width, 
 int micgpu_pics_compress(const uint16_t* pixels, int width, int height, uint16_t max_value, int num_strips, int nstates, uint8_t* out,
                          size_t cap, size_t* out_len) {
   return micgpu_pics_compress_batch(1, &pixels, width, height, &max_value, num_strips, nstates, &out, &cap, out_len, nullptr);
+}
+
+// ---- helpers for container assembly -------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+void put32(std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+void put64(std::vector<uint8_t>& v, uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+
+// Copy the finished frames of units [u0, u1) to the host, compacted on the device first (one D2H instead of one per frame).
+int fetch_frames(micgpu_encoder* e, int u0, int u1, std::vector<std::vector<uint8_t>>& out) {
+  std::vector<GatherJob> jobs;
+  unsigned long long tot = 0;
+  for (int i = u0; i < u1; i++) {
+    const MicEncUnit& r = e->h_units[i];
+    if (r.status == MIC_ENC_OK) { jobs.push_back(GatherJob{r.out_off, tot, r.frame_len}); tot += r.frame_len; }
+  }
+  out.assign(u1 - u0, {});
+  if (jobs.empty()) return 0;
+  int rc;
+  if ((rc = e->d_compact.ensure(tot + 64))) return rc;
+  if ((rc = e->d_jobs.ensure(jobs.size() * sizeof(GatherJob) + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_jobs.p, jobs.data(), jobs.size() * sizeof(GatherJob), cudaMemcpyHostToDevice, e->stream));
+  launch_gather_bytes((const GatherJob*)e->d_jobs.p, (int)jobs.size(), (const uint8_t*)e->d_frames.p, (uint8_t*)e->d_compact.p, e->stream);
+  std::vector<uint8_t> host(tot);
+  CUDA_TRY(cudaMemcpyAsync(host.data(), e->d_compact.p, tot, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  size_t j = 0;
+  for (int i = u0; i < u1; i++) {
+    const MicEncUnit& r = e->h_units[i];
+    if (r.status == MIC_ENC_OK) { out[i - u0].assign(host.begin() + jobs[j].dst_off, host.begin() + jobs[j].dst_off + r.frame_len); j++; }
+  }
+  return 0;
+}
+
+WaveletGeom enc_wavelet_geom(unsigned rows, unsigned cols, int levels) {   // collectSubbandOrder (waveletfsecompressu16.go:202-241)
+  WaveletGeom G;
+  memset(&G, 0, sizeof G);
+  G.rows = rows; G.cols = cols; G.levels = levels;
+  unsigned nr[10], nc[10];
+  nr[0] = rows; nc[0] = cols;
+  for (int l = 1; l <= levels; l++) { nr[l] = (nr[l - 1] + 1) / 2; nc[l] = (nc[l - 1] + 1) / 2; }
+  unsigned pos = 0;
+  int n = 0;
+  auto add = [&](unsigned y0, unsigned y1, unsigned x0, unsigned x1) {
+    G.seg_start[n] = pos; G.seg_y0[n] = y0; G.seg_x0[n] = x0; G.seg_w[n] = x1 > x0 ? x1 - x0 : 1;
+    if (y1 > y0 && x1 > x0) pos += (y1 - y0) * (x1 - x0);
+    n++;
+  };
+  add(0, nr[levels], 0, nc[levels]);
+  for (int l = levels; l >= 1; l--) {
+    add(0, nr[l], nc[l], nc[l - 1]);
+    add(nr[l], nr[l - 1], 0, nc[l]);
+    add(nr[l], nr[l - 1], nc[l], nc[l - 1]);
+  }
+  G.nseg = n;
+  return G;
+}
+
+}  // namespace
+
+extern "C" {
+
+// CompressMultiFrame (multiframecompress.go:179-224) + WriteMIC2 (multiframe.go:49-92)
+int micgpu_mic2_compress(const uint16_t* frames, int width, int height, int nframes, uint16_t max_value, int temporal, uint8_t* out, size_t cap,
+                         size_t* out_len) {
+  if (!frames || !out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  if (nframes <= 0) return fail(MICGPU_E_HEADER, "no frames to compress");
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const unsigned long long fpx = (unsigned long long)width * height;
+  e->units.clear();
+  for (int i = 0; i < nframes; i++) {
+    if (temporal && i > 0)   // compressResidualFrame: RLE(+length words) with resMax, 2-state then 1-state (multiframecompress.go:146-162)
+      enc_add_unit(e, MIC_ENC_RLE, (unsigned long long)nframes * fpx + (unsigned long long)(i - 1) * fpx, (unsigned)fpx, 1, 0xFFFFFFFFu, 2);
+    else
+      enc_add_unit(e, MIC_ENC_SPATIAL, (unsigned long long)i * fpx, (unsigned)width, (unsigned)height, max_value, 2);
+  }
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  const unsigned long long src_elems = (unsigned long long)nframes * fpx * (temporal ? 2 : 1);
+  if ((rc = e->d_src.ensure(src_elems * 2 + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_src.p, frames, (size_t)nframes * fpx * 2, cudaMemcpyHostToDevice, e->stream));
+  if (temporal)
+    launch_temporal_residual((const uint16_t*)e->d_src.p, (uint16_t*)e->d_src.p + (size_t)nframes * fpx, fpx, nframes, e->sm_count, e->stream);
+  if ((rc = enc_run(e, (const uint16_t*)e->d_src.p))) return rc;
+  for (int i = 0; i < nframes; i++)
+    if (e->h_units[i].status != MIC_ENC_OK) {
+      rc = enc_status_to_rc(e->h_units[i].status);
+      return fail(rc, "frame %d: %s", i, micgpu_last_error());
+    }
+  std::vector<std::vector<uint8_t>> blobs;
+  if ((rc = fetch_frames(e, 0, nframes, blobs))) return rc;
+  std::vector<uint8_t> o;
+  o.insert(o.end(), {'M', 'I', 'C', '2'});
+  put32(o, (uint32_t)width); put32(o, (uint32_t)height); put32(o, (uint32_t)nframes);
+  o.push_back((uint8_t)(0x01 | (temporal ? 0x02 : 0)));
+  o.push_back(0); o.push_back(0); o.push_back(0);
+  uint32_t off = 0;
+  for (auto& b : blobs) { put32(o, off); put32(o, (uint32_t)b.size()); off += (uint32_t)b.size(); }
+  for (auto& b : blobs) o.insert(o.end(), b.begin(), b.end());
+  if (o.size() > cap) return fail(MICGPU_E_SIZE, "output buffer too small (%zu needed)", o.size());
+  memcpy(out, o.data(), o.size());
+  if (out_len) *out_len = o.size();
+  return 0;
+}
+
+// WaveletV2RLEFSECompressU16 / WaveletV2SIMDRLEFSECompressU16 (waveletfsecompressu16.go:303-371,427-490) for n images of one geometry
+int micgpu_wavelet_v2_compress_batch(int n, const uint16_t* const* pixels, int rows, int cols, const uint16_t* max_values, int levels,
+                                     uint8_t* const* outs, const size_t* caps, size_t* out_lens, int* status) {
+  if (n <= 0) return 0;
+  if (!pixels || !outs || rows <= 0 || cols <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (levels < 1) levels = 1;
+  if (levels > 8) levels = 8;
+  int applied = levels;
+  {
+    int r = rows, c = cols;
+    for (int l = 0; l < levels; l++) {
+      if (r < 2 || c < 2) { applied = l; break; }
+      r = (r + 1) / 2; c = (c + 1) / 2;
+    }
+  }
+  const unsigned long long px = (unsigned long long)rows * cols;
+  const WaveletGeom G = enc_wavelet_geom((unsigned)rows, (unsigned)cols, applied);
+  e->units.clear();
+  std::vector<int> uoi(n);
+  for (int i = 0; i < n; i++) {
+    // V holds one word per coefficient, three per escaped coefficient
+    const int u = enc_add_unit(e, MIC_ENC_RLE, (unsigned long long)i * 3 * px, (unsigned)std::min<unsigned long long>(3 * px, 0x7FFFFFF0ull), 1, 0xFFFFFFFEu, 4);
+    e->units[u].no_ladder = 1;
+    uoi[i] = u;
+  }
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if ((rc = e->d_img.ensure((size_t)n * px * 2 + 64))) return rc;
+  if ((rc = e->d_wA.ensure((size_t)n * px * 4 + 64))) return rc;
+  if ((rc = e->d_wB.ensure((size_t)n * px * 4 + 64))) return rc;
+  if ((rc = e->d_src.ensure((size_t)n * 3 * px * 2 + 64))) return rc;
+  if ((rc = e->d_stats.ensure((size_t)n * sizeof(int) + 64))) return rc;
+  for (int i = 0; i < n; i++)
+    CUDA_TRY(cudaMemcpyAsync((uint16_t*)e->d_img.p + (size_t)i * px, pixels[i], (size_t)px * 2, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_stats.p, uoi.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  launch_wavelet_forward((const uint16_t*)e->d_img.p, (int32_t*)e->d_wA.p, (int32_t*)e->d_wB.p, n, G, e->sm_count, e->stream);
+  rc = enc_run(e, (const uint16_t*)e->d_src.p, [&](MicEncUnit* du, cudaStream_t st) {
+    launch_wavelet_pack((const int32_t*)e->d_wA.p, (uint16_t*)e->d_src.p, du, (const int*)e->d_stats.p, n, G, st);
+  });
+  if (rc) return rc;
+  std::vector<std::vector<uint8_t>> blobs;
+  if ((rc = fetch_frames(e, 0, n, blobs))) return rc;
+  int first = 0;
+  for (int i = 0; i < n; i++) {
+    int st = 0;
+    if (e->h_units[i].status != MIC_ENC_OK) st = enc_status_to_rc(e->h_units[i].status);
+    else if (11 + blobs[i].size() > caps[i]) st = fail(MICGPU_E_SIZE, "image %d: output buffer too small", i);
+    if (!st) {
+      uint8_t* o = outs[i];
+      const uint32_t r32 = (uint32_t)rows, c32 = (uint32_t)cols;
+      for (int k = 0; k < 4; k++) { o[k] = (uint8_t)(r32 >> (8 * k)); o[4 + k] = (uint8_t)(c32 >> (8 * k)); }
+      o[8] = (uint8_t)max_values[i]; o[9] = (uint8_t)(max_values[i] >> 8);
+      o[10] = (uint8_t)applied;
+      memcpy(o + 11, blobs[i].data(), blobs[i].size());
+      if (out_lens) out_lens[i] = 11 + blobs[i].size();
+    }
+    if (status) status[i] = st;
+    if (!first && st) first = st;
+  }
+  return first;
+}
+
+int micgpu_wavelet_v2_compress(const uint16_t* pixels, int rows, int cols, uint16_t max_value, int levels, uint8_t* out, size_t cap, size_t* out_len) {
+  return micgpu_wavelet_v2_compress_batch(1, &pixels, rows, cols, &max_value, levels, &out, &cap, out_len, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+
+// compressTileBlob for tiles [t0, t1) of a prepared job list (wsicompress.go:312-421): planes -> statistics -> units -> frames -> blobs
+struct TileSpec { unsigned long long img_off; unsigned img_w, img_h, x0, y0; };
+
+int wsi_encode_tiles(micgpu_encoder* e, const std::vector<TileSpec>& tiles, size_t t0, size_t t1, int tile_w, int tile_h, int channels, int bps,
+                     int ct, std::vector<std::vector<uint8_t>>& blobs_out) {
+  const bool rgb = channels == 3 && bps == 8;
+  const int nplanes = rgb ? 3 : 1;
+  const unsigned long long tpx = (unsigned long long)tile_w * tile_h;
+  const size_t nt = t1 - t0;
+  int rc;
+  if ((rc = e->d_planes.ensure(nt * nplanes * tpx * 2 + 64))) return rc;
+  std::vector<TilePlaneJob> jobs(nt);
+  std::vector<unsigned long long> poffs(nt * nplanes);
+  for (size_t i = 0; i < nt; i++) {
+    const TileSpec& T = tiles[t0 + i];
+    jobs[i] = TilePlaneJob{T.img_off, (unsigned long long)i * nplanes * tpx, T.img_w, T.img_h, T.x0, T.y0, (unsigned)tile_w, (unsigned)tile_h,
+                           rgb ? (ct ? 0u : 1u) : (bps <= 8 ? 2u : 3u), 0u};
+    for (int k = 0; k < nplanes; k++) poffs[i * nplanes + k] = (unsigned long long)(i * nplanes + k) * tpx;
+  }
+  const size_t jbytes = jobs.size() * sizeof(TilePlaneJob), obytes = poffs.size() * 8, sbytes = poffs.size() * 2 * sizeof(unsigned);
+  if ((rc = e->d_jobs.ensure(jbytes + obytes + 64))) return rc;
+  if ((rc = e->d_stats.ensure(sbytes + 64))) return rc;
+  cudaStream_t st = e->stream;
+  CUDA_TRY(cudaMemcpyAsync(e->d_jobs.p, jobs.data(), jbytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync((uint8_t*)e->d_jobs.p + jbytes, poffs.data(), obytes, cudaMemcpyHostToDevice, st));
+  launch_tile_planes((const TilePlaneJob*)e->d_jobs.p, (int)nt, (const uint8_t*)e->d_img.p, (uint16_t*)e->d_planes.p, st);
+  launch_plane_stats((const uint16_t*)e->d_planes.p, (const unsigned long long*)((uint8_t*)e->d_jobs.p + jbytes), tpx, (int)poffs.size(),
+                     (unsigned*)e->d_stats.p, st);
+  std::vector<unsigned> stats(poffs.size() * 2);
+  CUDA_TRY(cudaMemcpyAsync(stats.data(), e->d_stats.p, sbytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  // constant planes need their value: it is the plane max (all samples equal)
+  e->units.clear();
+  std::vector<int> unit_of_plane(poffs.size(), -1);
+  for (size_t p = 0; p < poffs.size(); p++) {
+    if (!stats[2 * p + 1]) continue;                                  // constant plane: modes 0 / 1
+    const unsigned mv = std::max(stats[2 * p], 255u);                 // wsicompress.go:398-400
+    unit_of_plane[p] = enc_add_unit(e, MIC_ENC_SPATIAL, poffs[p], (unsigned)tile_w, (unsigned)tile_h, mv, 2);
+  }
+  if (!e->units.empty() && (rc = enc_run(e, (const uint16_t*)e->d_planes.p))) return rc;
+  std::vector<std::vector<uint8_t>> frames;
+  if ((rc = fetch_frames(e, 0, (int)e->units.size(), frames))) return rc;
+  // raw fallback planes (ErrUseRLE / ErrIncompressible -> mode 3, wsicompress.go:403-414)
+  std::vector<GatherJob> raw;
+  std::vector<size_t> raw_plane;
+  unsigned long long rtot = 0;
+  for (size_t p = 0; p < poffs.size(); p++) {
+    const int u = unit_of_plane[p];
+    if (u < 0) continue;
+    const int s = e->h_units[u].status;
+    if (s == MIC_ENC_OK) continue;
+    if (s != MIC_ENC_INCOMPRESSIBLE && s != MIC_ENC_USE_RLE) return fail(enc_status_to_rc(s), "tile %zu plane %zu: FSE compress failed", t0 + p / nplanes, p % nplanes);
+    raw.push_back(GatherJob{poffs[p], rtot, tpx});
+    raw_plane.push_back(p);
+    rtot += tpx * 2;
+  }
+  std::vector<uint8_t> rawhost(rtot);
+  if (!raw.empty()) {
+    if ((rc = e->d_compact.ensure(rtot + 64))) return rc;
+    if ((rc = e->d_jobs.ensure(raw.size() * sizeof(GatherJob) + 64))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->d_jobs.p, raw.data(), raw.size() * sizeof(GatherJob), cudaMemcpyHostToDevice, st));
+    launch_plane_raw((const GatherJob*)e->d_jobs.p, (int)raw.size(), (const uint16_t*)e->d_planes.p, (uint8_t*)e->d_compact.p, st);
+    CUDA_TRY(cudaMemcpyAsync(rawhost.data(), e->d_compact.p, rtot, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  // assemble tile blobs: [Ylen][Colen][Cglen] + plane blobs (wsicompress.go:350-361); grey: the plane blob alone
+  size_t ri = 0;
+  for (size_t i = 0; i < nt; i++) {
+    std::vector<uint8_t> pb[3];
+    for (int k = 0; k < nplanes; k++) {
+      const size_t p = i * nplanes + k;
+      const int u = unit_of_plane[p];
+      if (u < 0) {
+        const unsigned val = stats[2 * p];
+        if (val == 0) pb[k] = {0};
+        else pb[k] = {1, (uint8_t)val, (uint8_t)(val >> 8)};
+      } else if (e->h_units[u].status == MIC_ENC_OK) {
+        pb[k].push_back(2);
+        pb[k].insert(pb[k].end(), frames[u].begin(), frames[u].end());
+      } else {
+        pb[k].push_back(3);
+        pb[k].insert(pb[k].end(), rawhost.begin() + raw[ri].dst_off, rawhost.begin() + raw[ri].dst_off + tpx * 2);
+        ri++;
+      }
+    }
+    std::vector<uint8_t> blob;
+    if (rgb) {
+      for (int k = 0; k < 3; k++) put32(blob, (uint32_t)pb[k].size());
+      for (int k = 0; k < 3; k++) blob.insert(blob.end(), pb[k].begin(), pb[k].end());
+    } else {
+      blob = std::move(pb[0]);
+    }
+    blobs_out.push_back(std::move(blob));
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// CompressRGB (rgbcompress.go:25-27) == compressRGBTileBlob on the whole image, colour transform on
+int micgpu_rgb_compress(const uint8_t* rgb, int width, int height, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!rgb || !out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t bytes = (size_t)width * height * 3;
+  if ((rc = e->d_img.ensure(bytes + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_img.p, rgb, bytes, cudaMemcpyHostToDevice, e->stream));
+  std::vector<TileSpec> tiles{TileSpec{0, (unsigned)width, (unsigned)height, 0, 0}};
+  std::vector<std::vector<uint8_t>> blobs;
+  if ((rc = wsi_encode_tiles(e, tiles, 0, 1, width, height, 3, 8, 1, blobs))) return rc;
+  if (blobs[0].size() > cap) return fail(MICGPU_E_SIZE, "output buffer too small");
+  memcpy(out, blobs[0].data(), blobs[0].size());
+  if (out_len) *out_len = blobs[0].size();
+  return 0;
+}
+
+// CompressWSI (wsicompress.go:27-172) + WriteMIC3 (wsiformat.go:99-165).  pyramid_levels <= 0: autoLevelCount.
+int micgpu_wsi_compress(const uint8_t* pixels, int width, int height, int channels, int bits_per_sample, int tile_w, int tile_h,
+                        int pyramid_levels, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!pixels || !out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  const bool rgb = channels == 3 && bits_per_sample == 8;
+  if (!rgb && channels != 1) return fail(MICGPU_E_UNSUPPORTED, "MIC3: %d channels at %d bits is not supported", channels, bits_per_sample);
+  if (tile_w == 0) tile_w = 256;
+  if (tile_h == 0) tile_h = 256;
+  const int ct = channels == 3 ? 1 : 0;            // WSIOptions.defaults (wsiformat.go:86-97)
+  int nlv = pyramid_levels;
+  if (nlv <= 0) {                                  // autoLevelCount (wsiformat.go:273-285)
+    nlv = 1;
+    int w = width, h = height;
+    while (w > tile_w || h > tile_h) { w /= 2; h /= 2; nlv++; if (w <= 1 && h <= 1) break; }
+  }
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int bpp = bits_per_sample == 16 ? channels * 2 : channels;
+  // level geometry + pyramid on the device (Downsample2xRGB / Grey, wsicompress.go:45-73)
+  struct Lv { int w, h, tx, ty, first; unsigned long long off; };
+  std::vector<Lv> lv;
+  unsigned long long itot = 0;
+  {
+    int w = width, h = height;
+    for (int i = 0; i < nlv; i++) {
+      if (i > 0) {
+        if (lv.back().w / 2 == 0 || lv.back().h / 2 == 0) break;
+        w = lv.back().w / 2; h = lv.back().h / 2;
+      }
+      lv.push_back(Lv{w, h, (w + tile_w - 1) / tile_w, (h + tile_h - 1) / tile_h, 0, itot});
+      itot += ((unsigned long long)w * h * bpp + 255) & ~255ull;
+    }
+  }
+  nlv = (int)lv.size();
+  if ((rc = e->d_img.ensure(itot + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_img.p, pixels, (size_t)width * height * bpp, cudaMemcpyHostToDevice, e->stream));
+  for (int i = 1; i < nlv; i++)
+    launch_downsample2x((const uint8_t*)e->d_img.p + lv[i - 1].off, (uint8_t*)e->d_img.p + lv[i].off, (unsigned)lv[i - 1].w, (unsigned)lv[i - 1].h,
+                        bits_per_sample == 16 ? 1u : (unsigned)channels, bits_per_sample == 16 ? 2u : 1u, e->sm_count, e->stream);
+  std::vector<TileSpec> tiles;
+  int total = 0;
+  for (int l = 0; l < nlv; l++) {
+    lv[l].first = total;
+    for (int ty = 0; ty < lv[l].ty; ty++)
+      for (int tx = 0; tx < lv[l].tx; tx++) tiles.push_back(TileSpec{lv[l].off, (unsigned)lv[l].w, (unsigned)lv[l].h, (unsigned)(tx * tile_w), (unsigned)(ty * tile_h)});
+    total += lv[l].tx * lv[l].ty;
+  }
+  std::vector<std::vector<uint8_t>> blobs;
+  const size_t chunk = std::max<size_t>(1, (size_t)(1ull << 29) / ((size_t)tile_w * tile_h * (rgb ? 3 : 1) * 2 * 24));   // ~0.5 GB of worst-case scratch
+  for (size_t t0 = 0; t0 < tiles.size(); t0 += chunk)
+    if ((rc = wsi_encode_tiles(e, tiles, t0, std::min(tiles.size(), t0 + chunk), tile_w, tile_h, channels, bits_per_sample, ct, blobs))) return rc;
+  std::vector<uint8_t> o;
+  o.insert(o.end(), {'M', 'I', 'C', '3'});
+  put32(o, 1); put32(o, (uint32_t)width); put32(o, (uint32_t)height); put32(o, (uint32_t)tile_w); put32(o, (uint32_t)tile_h);
+  o.push_back((uint8_t)channels); o.push_back((uint8_t)(channels >> 8));
+  o.push_back((uint8_t)bits_per_sample);
+  o.push_back((uint8_t)(0x01 | (ct ? 0x02 : 0)));
+  o.push_back((uint8_t)nlv); o.push_back((uint8_t)(nlv >> 8));
+  o.push_back(0); o.push_back(0);
+  put64(o, (uint64_t)total);
+  put64(o, 0);
+  for (int l = 0; l < nlv; l++) { put32(o, (uint32_t)lv[l].w); put32(o, (uint32_t)lv[l].h); put32(o, (uint32_t)lv[l].tx); put32(o, (uint32_t)lv[l].ty); put32(o, (uint32_t)lv[l].first); }
+  uint64_t off = 0;
+  for (auto& b : blobs) { put64(o, off); put64(o, (uint64_t)b.size()); off += b.size(); }
+  for (auto& b : blobs) o.insert(o.end(), b.begin(), b.end());
+  if (o.size() > cap) return fail(MICGPU_E_SIZE, "output buffer too small (%zu needed)", o.size());
+  memcpy(out, o.data(), o.size());
+  if (out_len) *out_len = o.size();
+  return 0;
 }
 
 // mic_compress_{two,four,eight}_state (ojph/mic_compress_c.h:26-37): the C twin derives maxValue from the pixels

@@ -155,3 +155,75 @@ def test_twin_compress_symbols(mic, oracle, reftwin, synth):
         rc = getattr(mic.lib, f"mic_compress_{name}_state")(img.ctypes.data, w, h, out.ctypes.data, out.size, C.byref(n))
         assert rc == 0
         assert out[: n.value].tobytes() == reftwin.compress(img, w, h, ns)     # byte-identical to the reference binary
+
+
+# ---- containers and front ends ---------------------------------------------------------------------
+@pytest.mark.parametrize("temporal", [False, True])
+def test_mic2_bytes(mic, oracle, synth, temporal):
+    st = synth.tomo_stack(7, 5, 128, 128)
+    got = mic.CompressMultiFrame(st, 128, 128, 1023, temporal)
+    assert got == oracle.mic2_compress(st.ravel(), 128, 128, 1023, temporal)
+    frames, hdr = mic.DecompressMultiFrame(got)
+    assert hdr["Temporal"] == temporal and np.array_equal(frames, st)
+
+
+def test_mic2_larger_temporal(mic, oracle, synth):
+    st = synth.tomo_stack(3, 4, 301, 257)
+    got = mic.CompressMultiFrame(st, 257, 301, 1023, True)
+    assert got == oracle.mic2_compress(st.ravel(), 257, 301, 1023, True)
+
+
+def _field(rows, cols, seed):
+    i = np.arange(rows * cols)
+    y, x = i // cols, i % cols
+    return ((y * 5 + x * 3) % 3000 + (i * 97 + 13 + seed) % 7).astype(np.uint16)
+
+
+@pytest.mark.parametrize("rows,cols,levels", [(64, 96, 3), (96, 64, 5), (128, 128, 5), (127, 129, 4), (256, 512, 8), (3, 2000, 5), (300, 200, 1), (513, 130, 6)])
+def test_wavelet_bytes(mic, oracle, rows, cols, levels):
+    src = _field(rows, cols, 0)
+    got = mic.WaveletV2RLEFSECompressU16(src, rows, cols, 4095, levels)
+    assert got == oracle.wavelet_v2_compress(src, rows, cols, 4095, levels)
+    px, r, c = mic.WaveletV2RLEFSEDecompressU16(got)
+    assert (r, c) == (rows, cols) and np.array_equal(px, src)
+
+
+def test_wavelet_bytes_mammo_and_escapes(mic, oracle, synth):
+    img = synth.mammo_image(1, 1024, 832).ravel()
+    assert mic.WaveletV2SIMDRLEFSECompressU16(img, 1024, 832, int(img.max()), 5) == oracle.wavelet_v2_compress(img, 1024, 832, int(img.max()), 5)
+    rng = np.random.default_rng(3)
+    src = (rng.integers(0, 2, 96 * 96) * 65535).astype(np.uint16)        # coefficients beyond +-32767 -> escape triples
+    assert mic.WaveletV2RLEFSECompressU16(src, 96, 96, 65535, 3) == oracle.wavelet_v2_compress(src, 96, 96, 65535, 3)
+    blobs = mic.WaveletV2CompressBatch([_field(128, 128, s) for s in range(3)], 128, 128, [4095] * 3, 5)
+    for s, b in enumerate(blobs):
+        assert b == oracle.wavelet_v2_compress(_field(128, 128, s), 128, 128, 4095, 5)
+
+
+def test_rgb_bytes(mic, oracle, synth):
+    rgb = synth.wsi_region(5, 1000, 900, 301, 203, 2500, 2000)
+    got = mic.CompressRGB(rgb, 301, 203)
+    assert got == oracle.rgb_compress(rgb.ravel(), 301, 203, True)
+    assert np.array_equal(mic.DecompressRGB(got, 301, 203), rgb.ravel())
+
+
+def test_wsi_bytes(mic, oracle, synth):
+    # tissue edge + white background + constant regions: plane modes 0/1/2, edge-tile zero padding, 3 pyramid levels
+    W, H = 700, 533
+    rgb = synth.wsi_region(11, 900, 700, W, H, 2500, 2000)
+    rgb[400:, :300] = 255
+    rgb[:40, 600:] = 0
+    got = mic.CompressWSI(rgb, W, H)
+    ref = oracle.wsi_compress(rgb.ravel(), W, H, 3, 8, 256, 256, 0)
+    assert got == ref
+    got2 = mic.CompressWSI(rgb, W, H, tile_width=128, tile_height=64, pyramid_levels=2)
+    assert got2 == oracle.wsi_compress(rgb.ravel(), W, H, 3, 8, 128, 64, 2)
+
+
+@pytest.mark.parametrize("bps", [8, 16])
+def test_wsi_grey_bytes(mic, oracle, synth, bps):
+    W, H = 300, 270
+    g = synth.xr_image(4, W, H)
+    px = (g >> 4).astype(np.uint8).tobytes() if bps == 8 else (g >> 3).astype("<u2").tobytes()
+    lv = 0 if bps == 8 else 1
+    got = mic.CompressWSI(np.frombuffer(px, np.uint8), W, H, channels=1, bits_per_sample=bps, tile_width=128, tile_height=128, pyramid_levels=lv)
+    assert got == oracle.wsi_compress(np.frombuffer(px, np.uint8), W, H, 1, bps, 128, 128, lv)

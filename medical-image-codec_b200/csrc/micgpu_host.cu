@@ -379,6 +379,9 @@ int add_mic2_locked(micgpu_decoder* d, const uint8_t* p, size_t len, uint64_t co
 // ---- default per-device contexts for the one-shot calls ---------------------
 std::mutex g_mu;
 micgpu_decoder* g_default[64] = {nullptr};
+constexpr int PIPE_DEPTH = 3;
+std::mutex g_pipe_mu;
+micgpu_decoder* g_pipe[64][PIPE_DEPTH] = {};
 
 micgpu_decoder* default_decoder(int dev) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -430,6 +433,12 @@ void micgpu_shutdown(void) {
     delete d;
     d = nullptr;
   }
+  std::lock_guard<std::mutex> lk2(g_pipe_mu);
+  for (auto& row : g_pipe)
+    for (auto& d : row) {
+      delete d;
+      d = nullptr;
+    }
 }
 
 micgpu_decoder* micgpu_decoder_create(int device) {
@@ -560,56 +569,130 @@ int micgpu_decoder_run_host(micgpu_decoder* d, const uint8_t* comp, size_t comp_
 }
 
 // ---- one-shot container calls --------------------------------------------------
-int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
-                                 const size_t* caps, int* status) {
-  if (n <= 0) return 0;
-  micgpu_decoder* d = default_decoder(current_device());
-  if (!d) return MICGPU_E_CUDA;
-  std::lock_guard<std::mutex> lk(d->mu);
+}  // extern "C"
+
+namespace {
+
+// One in-flight PICS chunk on one decoder: everything is enqueued on d->stream, nothing is waited for.
+struct PicsPending {
+  int i0 = 0, i1 = 0;
+  std::vector<int> first_unit, hdr_rc;
+  bool active = false;
+};
+
+int pics_enqueue(micgpu_decoder* d, int i0, int i1, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
+                 const size_t* caps, PicsPending& P) {
+  const int n = i1 - i0;
   d->units.clear();
   d->temporal.clear();
   d->out_need = 0;
   // layout: blobs back to back (64-byte aligned) in one device buffer; outputs back to back
-  std::vector<uint64_t> coff(n), ooff(n);
-  std::vector<int> first_unit(n + 1, 0), hdr_rc(n, 0);
+  std::vector<uint64_t> coff(n), ooff(n + 1);
+  P.i0 = i0; P.i1 = i1;
+  P.first_unit.assign(n + 1, 0);
+  P.hdr_rc.assign(n, 0);
   uint64_t ctot = 0, otot = 0;
-  for (int i = 0; i < n; i++) {
-    coff[i] = ctot;
-    ooff[i] = otot;
-    first_unit[i] = (int)d->units.size();
+  for (int k = 0; k < n; k++) {
+    const int i = i0 + k;
+    coff[k] = ctot;
+    ooff[k] = otot;
+    P.first_unit[k] = (int)d->units.size();
     int w = 0, h = 0;
-    hdr_rc[i] = add_pics_locked(d, blobs[i], lens[i], ctot, otot, &w, &h);
-    if (!hdr_rc[i] && (size_t)w * h > caps[i]) {
-      hdr_rc[i] = fail(MICGPU_E_SIZE, "image %d: output buffer too small", i);
-      d->units.resize(first_unit[i]);
-    }
-    if (!hdr_rc[i]) otot += (uint64_t)w * h;
-    else d->units.resize(first_unit[i]);
+    P.hdr_rc[k] = add_pics_locked(d, blobs[i], lens[i], ctot, otot, &w, &h);
+    if (!P.hdr_rc[k] && (size_t)w * h > caps[i]) P.hdr_rc[k] = fail(MICGPU_E_SIZE, "image %d: output buffer too small", i);
+    if (!P.hdr_rc[k]) otot += (uint64_t)w * h;
+    else d->units.resize(P.first_unit[k]);
     ctot += (lens[i] + 63) & ~(size_t)63;
   }
-  first_unit[n] = (int)d->units.size();
+  ooff[n] = otot;
+  P.first_unit[n] = (int)d->units.size();
   int rc = plan_commit(d);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(d->device));
   if ((rc = d->d_comp.ensure(ctot + 256))) return rc;
   if ((rc = d->d_out.ensure(std::max<uint64_t>(otot, 1) * sizeof(uint16_t)))) return rc;
-  for (int i = 0; i < n; i++)
-    if (!hdr_rc[i]) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_comp.p + coff[i], blobs[i], lens[i], cudaMemcpyHostToDevice, d->stream));
+  // copies are merged when neighbouring images are also neighbours in host memory (a caller that keeps a batch in one
+  // buffer gets one H2D and one D2H per chunk instead of one per image)
+  for (int k = 0; k < n;) {
+    if (P.hdr_rc[k]) { k++; continue; }
+    int j = k;
+    size_t bytes = lens[i0 + k];
+    while (j + 1 < n && !P.hdr_rc[j + 1] && blobs[i0 + j + 1] == blobs[i0 + j] + (coff[j + 1] - coff[j])) { j++; bytes = (size_t)(coff[j] - coff[k]) + lens[i0 + j]; }
+    CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_comp.p + coff[k], blobs[i0 + k], bytes, cudaMemcpyHostToDevice, d->stream));
+    k = j + 1;
+  }
   if ((rc = run_device_locked(d, d->d_comp.p, ctot, d->d_out.p, otot, d->stream))) return rc;
-  for (int i = 0; i < n; i++) {
-    if (hdr_rc[i]) continue;
-    const uint64_t px = (i + 1 < n ? ooff[i + 1] : otot) - ooff[i];
-    CUDA_TRY(cudaMemcpyAsync(outs[i], (uint16_t*)d->d_out.p + ooff[i], px * sizeof(uint16_t), cudaMemcpyDeviceToHost, d->stream));
+  for (int k = 0; k < n;) {
+    if (P.hdr_rc[k]) { k++; continue; }
+    int j = k;
+    while (j + 1 < n && !P.hdr_rc[j + 1] && outs[i0 + j + 1] == outs[i0 + j] + (ooff[j + 1] - ooff[j])) j++;
+    CUDA_TRY(cudaMemcpyAsync(outs[i0 + k], (uint16_t*)d->d_out.p + ooff[k], (ooff[j + 1] - ooff[k]) * sizeof(uint16_t), cudaMemcpyDeviceToHost, d->stream));
+    k = j + 1;
   }
-  std::vector<int> ust(d->units.size());
-  unit_status_locked(d, ust.data(), (int)ust.size(), d->stream);
-  int first = 0;
-  for (int i = 0; i < n; i++) {
-    int s = hdr_rc[i];
-    for (int u = first_unit[i]; !s && u < first_unit[i + 1]; u++) s = ust[u];   // first failing strip wins (parallelstrips.go:324-328)
-    if (status) status[i] = s;
-    if (!first && s) first = s;
+  if (!d->units.empty())
+    CUDA_TRY(cudaMemcpyAsync(d->h_units, d->d_units.p, d->units.size() * sizeof(MicUnit), cudaMemcpyDeviceToHost, d->stream));
+  P.active = true;
+  return 0;
+}
+
+// Wait for the chunk and fold unit statuses into per-image statuses (first failing strip wins, parallelstrips.go:324-328)
+int pics_finish(micgpu_decoder* d, PicsPending& P, int* status, int* first) {
+  if (!P.active) return 0;
+  P.active = false;
+  CUDA_TRY(cudaSetDevice(d->device));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  const int n = P.i1 - P.i0;
+  for (int k = 0; k < n; k++) {
+    int st = P.hdr_rc[k];
+    for (int u = P.first_unit[k]; !st && u < P.first_unit[k + 1]; u++) st = d->h_units[u].status;
+    if (status) status[P.i0 + k] = st;
+    if (!*first && st) { *first = st; if (st != P.hdr_rc[k]) fail(st, "image %d: strip decode failed (status %d)", P.i0 + k, st); }
   }
+  return 0;
+}
+
+// Extra decoder contexts so that the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap.
+
+micgpu_decoder* pipe_decoder(int dev, int k) {
+  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!g_pipe[dev][k]) g_pipe[dev][k] = micgpu_decoder_create(dev);
+  return g_pipe[dev][k];
+}
+
+}  // namespace
+
+extern "C" {
+
+int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
+                                 const size_t* caps, int* status) {
+  if (n <= 0) return 0;
+  const int dev = current_device();
+  int first = 0, rc;
+  if (n < 16) {
+    micgpu_decoder* d = default_decoder(dev);
+    if (!d) return MICGPU_E_CUDA;
+    std::lock_guard<std::mutex> lk(d->mu);
+    PicsPending P;
+    if ((rc = pics_enqueue(d, 0, n, blobs, lens, outs, caps, P))) return rc;
+    if ((rc = pics_finish(d, P, status, &first))) return rc;
+    return first;
+  }
+  // pipelined: ~8 chunks over PIPE_DEPTH decoder contexts (each with its own stream and scratch)
+  const int chunk = std::max(4, (n + 7) / 8);
+  micgpu_decoder* D[PIPE_DEPTH];
+  PicsPending P[PIPE_DEPTH];
+  for (int k = 0; k < PIPE_DEPTH; k++)
+    if (!(D[k] = pipe_decoder(dev, k))) return MICGPU_E_CUDA;
+  std::unique_lock<std::mutex> l0(D[0]->mu), l1(D[1]->mu), l2(D[2]->mu);
+  int c = 0;
+  for (int i0 = 0; i0 < n; i0 += chunk, c++) {
+    const int k = c % PIPE_DEPTH;
+    if ((rc = pics_finish(D[k], P[k], status, &first))) return rc;
+    if ((rc = pics_enqueue(D[k], i0, std::min(n, i0 + chunk), blobs, lens, outs, caps, P[k]))) return rc;
+  }
+  for (int k = 0; k < PIPE_DEPTH; k++)
+    if ((rc = pics_finish(D[k], P[k], status, &first))) return rc;
   return first;
 }
 

@@ -125,6 +125,21 @@ def test_pics_batch(mic, oracle, synth):
         assert np.array_equal(px, im)
 
 
+def test_pics_batch_pipelined(mic, oracle, synth):
+    # >= 16 images take the chunked path (H2D / kernels / D2H of consecutive chunks overlap on three contexts);
+    # one corrupt image in the middle must be reported without disturbing the others
+    w, h = 211, 160
+    imgs = [synth.xr_image(100 + i, w, h).ravel() for i in range(37)]
+    blobs = [oracle.pics_compress(im, w, h, int(im.max()), 4, (2, 4, 8)[i % 3]) for i, im in enumerate(imgs)]
+    res = mic.DecompressParallelStripsBatch(blobs)
+    for (px, ow, oh), im in zip(res, imgs):
+        assert (ow, oh) == (w, h) and np.array_equal(px, im)
+    bad = list(blobs)
+    bad[20] = bad[20][:200] + bytes(len(bad[20]) - 200)
+    with pytest.raises(mic.MicGpuError):
+        mic.DecompressParallelStripsBatch(bad)
+
+
 @pytest.mark.parametrize("temporal", [False, True])
 def test_mic2(mic, oracle, synth, temporal):
     # 128x128x5 like TestMultiFrame{Independent,Temporal}Roundtrip (multiframe_test.go:149,192)

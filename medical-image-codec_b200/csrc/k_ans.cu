@@ -35,40 +35,52 @@ constexpr int RING_WORDS = 32;    // ring[32] mirrors ring[0] so word pairs neve
 constexpr int RING_STRIDE = 36;   // words reserved per slot (16 B aligned)
 constexpr int HALF_WORDS = 16;
 
-// Exclusive prefix sum and total of nb over the N active lanes of the warp (lanes >= N have
-// exited, so MASK is the warp's whole active mask and each redux is one instruction).
-// NB4: nb <= 15 (tableLog <= 15) -> lane k drops nb into nibble k of ONE word; redux.or hands every
-// lane all counts, the prefix is a masked horizontal nibble sum; the total is a redux.add.
-template <int N, bool NB4>
-__device__ __forceinline__ uint32_t slot_prefix(uint32_t nb, int k, uint32_t* tot) {
+// Exclusive prefix sum and total of nb (<= 16) over the N active lanes of the warp (lanes >= N have exited, so MASK is
+// the warp's whole active mask and each redux is one instruction).  Lane j multiplies its nb by a per-lane constant
+// that replicates it into the 8-bit fields of all lanes k > j; redux.add then delivers EVERY lane's prefix at once
+// (field k of the sum), so the post-processing is one shift and one mask instead of a masked horizontal sum.
+// Field sums stay below 256 (7 * 16).  Fields 0-3 live in word A, fields 4-7 in word B.
+template <int N>
+struct PrefixConsts {
+  uint32_t ca, cb;     // multipliers of this lane for words A and B
+  uint32_t sh;         // shift that extracts this lane's field
+  bool use_b;
+  __device__ explicit PrefixConsts(int k) {
+    ca = 0; cb = 0;
+#pragma unroll
+    for (int f = 0; f < 8; f++) {
+      if (f > k && f < N) {
+        if (f < 4) ca |= 1u << (8 * f);
+        else cb |= 1u << (8 * (f - 4));
+      }
+    }
+    sh = 8u * (unsigned)(k & 3);
+    use_b = k >= 4;
+  }
+};
+
+template <int N>
+__device__ __forceinline__ uint32_t slot_prefix(uint32_t nb, const PrefixConsts<N>& pc, uint32_t* tot) {
   constexpr unsigned MASK = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
   if (N == 1) {
     *tot = nb;
     return 0;
-  } else if (NB4) {
-    const uint32_t r = __reduce_or_sync(MASK, nb << (4 * k));
-    *tot = __reduce_add_sync(MASK, nb);
-    const uint32_t x = r & ((1u << (4 * k)) - 1u);
-    const uint32_t t = (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu);
-    return (t * 0x01010101u) >> 24;
-  } else if (N <= 4) {
-    const uint32_t r = __reduce_or_sync(MASK, nb << (8 * k));
-    *tot = __reduce_add_sync(MASK, nb);
-    return ((r & ((1u << (8 * k)) - 1u)) * 0x01010101u) >> 24;
   } else {
-    const uint32_t r0 = __reduce_or_sync(MASK, k < 4 ? nb << (8 * k) : 0u);
-    const uint32_t r1 = __reduce_or_sync(MASK, k >= 4 ? nb << (8 * (k - 4)) : 0u);
+    const uint32_t a = __reduce_add_sync(MASK, nb * pc.ca);
     *tot = __reduce_add_sync(MASK, nb);
-    const uint32_t m0 = k < 4 ? ((1u << (8 * k)) - 1u) : 0xffffffffu;
-    const uint32_t m1 = k <= 4 ? 0u : ((1u << (8 * (k - 4))) - 1u);
-    return (((r0 & m0) * 0x01010101u) >> 24) + (((r1 & m1) * 0x01010101u) >> 24);
+    uint32_t w = a;
+    if (N > 4) {
+      const uint32_t b = __reduce_add_sync(MASK, nb * pc.cb);
+      w = pc.use_b ? b : a;
+    }
+    return (w >> pc.sh) & 0xFFu;
   }
 }
 
 // One warp = one slot = one unit at a time; only the first N lanes stay alive (lane k owns
 // state k).  The state->state chain is latency bound and a warp issues in order, so throughput
 // comes from having many warps (units) resident per SM, not from filling lanes.
-template <int N, int MODE, bool NB4>
+template <int N, int MODE>
 __global__ void __launch_bounds__(1024)
 k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
              const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots_per_cta) {
@@ -78,6 +90,7 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
   const int slot = threadIdx.x >> 5;
   const int k = threadIdx.x & 31;
   if (k >= N) return;
+  const PrefixConsts<N> pc(k);
 
   const size_t tbytes = MODE == 2 ? 0 : ((size_t)(1u << max_log) * (MODE == 0 ? 4 : 2));
   uint8_t* mytab = smem + (size_t)slot * tbytes;
@@ -216,18 +229,32 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
       // below `shift`, which is remembered in `under` and reported after the loop (reads stay inside the ring).
       int under = 0;
       const uint32_t full = err ? 0u : count / N;
-      for (uint32_t r = 0; r < full; r++, op += N) {
+      // decode step without the ring check
+      auto round_nocheck = [&]() {
         uint32_t nb, ns;
         if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
         else if (MODE == 1) { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); ns = (nx << nb) - S; }
         else { const uint32_t e = __ldg(A + state); nb = e >> 16; ns = e & 0xFFFF; }
         uint32_t tot;
-        const uint32_t before = slot_prefix<N, NB4>(nb, k, &tot);
+        const uint32_t before = slot_prefix<N>(nb, pc, &tot);
         const uint32_t bits = extract(P - (int)before - (int)nb, nb);
         *op = (uint16_t)state;
+        op += N;
         state = ns + bits;
-        advance(tot);
+        P -= (int)tot;
         under |= P - (int)shift;          // sign bit set once P < shift
+      };
+      // The ring is checked once per two rounds: two rounds consume at most 2*N*16 = 256 bits = 8 words, so a top that
+      // just left half h still only reaches words of half h-1 before the next check.
+      uint32_t r = 0;
+      for (; r + 2 <= full; r += 2) {
+        round_nocheck();
+        round_nocheck();
+        advance(0);
+      }
+      if (r < full) {
+        round_nocheck();
+        advance(0);
       }
       const uint32_t tail = err ? 0u : count - full * N;
       if (tail) {
@@ -239,7 +266,7 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
         (void)ns;
         if (!active) nb = 0;
         uint32_t tot;
-        slot_prefix<N, NB4>(nb, k, &tot);
+        slot_prefix<N>(nb, pc, &tot);
         if (active) *op = (uint16_t)state;
         P -= (int)tot;
         under |= P - (int)shift;
@@ -263,13 +290,8 @@ template <int N, int MODE>
 static void launch_one(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, const uint32_t* d_tabA,
                        uint16_t* d_states, int max_log, int slots, int grid, cudaStream_t st) {
   size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
-  if (max_log <= 15) {
-    cudaFuncSetAttribute(k_ans_decode<N, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_ans_decode<N, MODE, true><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
-  } else {
-    cudaFuncSetAttribute(k_ans_decode<N, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_ans_decode<N, MODE, false><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
-  }
+  cudaFuncSetAttribute(k_ans_decode<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_ans_decode<N, MODE><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
 }
 
 template <int N>

@@ -19,7 +19,7 @@
 
 namespace micgpu {
 
-constexpr int K3_THREADS = 128;
+constexpr int K3_THREADS = 256;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int IN_N = 4096;
 constexpr int OUT_CH = 4096;

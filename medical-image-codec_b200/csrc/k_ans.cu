@@ -27,6 +27,9 @@
 // padding and the 1-bit sentinel and reads fields MSB-first walking to byte 0
 // (bitreader.go:26-62).  With the stream viewed as one little-endian integer,
 // a field of n bits read when P bits remain unread is bits [P-n, P).
+#include <cstdlib>
+#include <type_traits>
+
 #include "mic_device.cuh"
 
 namespace micgpu {
@@ -281,9 +284,274 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
   }
 }
 
+
+// ---- packed variant: 32/N units per warp ----------------------------------------------------------------------
+// The one-unit-per-warp kernel above issues every instruction for N of 32 lanes.  With all 2048 strips of the
+// headline batch resident (14 per SM, the shared-memory limit) its round costs 194 cycles of pure dependency chain
+// but 264 cycles measured: 3.5 warps per scheduler x 43 instructions per round queue behind each other
+// (tools/ubench_lat.cu, profiles/README.md).  Here lanes [sub*N, sub*N+N) of a warp own unit `sub`, so the same
+// instruction stream advances 32/N units at once and the schedulers stop being a bottleneck.
+// Cross-lane prefix: partial-mask redux would be serialised by the compiler, and 2 redux per unit do not scale to
+// four units; instead every lane posts its nbBits as one byte in shared memory, reads its unit's N bytes back as
+// one word (pair) and sums the masked bytes with dp4a -- same latency as the redux path (~50 cycles), 8
+// instructions for any number of units per warp.
+template <int N>
+struct ByteMasks {
+  uint32_t lo, hi;      // bytes of lanes j < k in the unit's low / high word
+  __device__ explicit ByteMasks(int k) {
+    lo = 0; hi = 0;
+#pragma unroll
+    for (int f = 0; f < 8; f++) {
+      if (f < k && f < N) {
+        if (f < 4) lo |= 0xFFu << (8 * f);
+        else hi |= 0xFFu << (8 * (f - 4));
+      }
+    }
+  }
+};
+
+template <int N>
+__device__ __forceinline__ uint32_t packed_prefix(uint32_t nb, uint8_t* my_byte, const uint8_t* unit_bytes,
+                                                  const ByteMasks<N>& bm, uint32_t* tot) {
+  *my_byte = (uint8_t)nb;
+  __syncwarp();
+  constexpr uint32_t ONES = 0x01010101u;
+  if (N == 8) {
+    const uint2 v = *reinterpret_cast<const uint2*>(unit_bytes);
+    *tot = __dp4a(v.x, ONES, __dp4a(v.y, ONES, 0u));
+    return __dp4a(v.x & bm.lo, ONES, __dp4a(v.y & bm.hi, ONES, 0u));
+  } else if (N == 4) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(unit_bytes);
+    *tot = __dp4a(v, ONES, 0u);
+    return __dp4a(v & bm.lo, ONES, 0u);
+  } else {
+    const uint32_t v = *reinterpret_cast<const uint16_t*>(unit_bytes);
+    *tot = (v & 0xFFu) + (v >> 8);
+    return v & bm.lo;
+  }
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(1024)
+k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
+                    const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots) {
+  static_assert(N == 2 || N == 4 || N == 8, "packed decode is for the interleaved coders");
+  static_assert(MODE == 0 || MODE == 1, "packed decode keeps its tables in shared memory");
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int PW = HALF_WORDS / N;             // ring words each lane carries for the in-flight half
+  constexpr int HALF_BYTES = HALF_WORDS * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int k = lane % N, sub = lane / N;
+  const int slot = sub * nwarps + warp;          // slots are dealt round-robin over the warps
+  const bool slot_ok = slot < slots;
+  const int sslot = slot_ok ? slot : 0;          // lanes without a slot alias slot 0 and never write
+  const ByteMasks<N> bm(k);
+
+  const size_t tbytes = (size_t)(1u << max_log) * (MODE == 0 ? 4 : 2);
+  uint8_t* mytab = smem + (size_t)sslot * tbytes;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)slots * tbytes) + sslot * RING_STRIDE;
+  uint8_t* xch = smem + (size_t)slots * (tbytes + RING_STRIDE * 4) + warp * 64;   // 2 x 32 B per warp
+  uint8_t* xmine = xch + lane;
+  const uint8_t* xunit = xch + sub * N;
+  const uint32_t* T32 = reinterpret_cast<const uint32_t*>(mytab);
+  const uint16_t* T16 = reinterpret_cast<const uint16_t*>(mytab);
+  uint8_t* ringb = reinterpret_cast<uint8_t*>(ring);
+
+  for (int base = blockIdx.x * slots; base < nlist; base += gridDim.x * slots) {
+    const int li = base + slot;
+    MicUnit* U = nullptr;
+    bool has = false;
+    if (slot_ok && li < nlist) {
+      U = &units[list[li]];
+      has = U->status == MIC_OK;
+    }
+    __syncwarp();
+    int L = 5;
+    uint32_t S = 32, shift = 0, count = 0;
+    int P = 0, cross = -(1 << 30);
+    // ring refill state: `pre` holds the half with index hidx; it replaces the ring half at byte offset roff
+    // (this lane's PW words of it) once the half two above it is dead.
+    uint32_t pre[PW];
+#pragma unroll
+    for (int i = 0; i < PW; i++) pre[i] = 0;
+    const uint32_t* srcp = nullptr;   // this lane's words of half hidx
+    int hidx = -1;
+    uint32_t roff = 0;
+
+    auto load_pre = [&]() {
+      if (hidx >= 0) {
+        if (PW == 2) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(srcp));
+          pre[0] = v.x; pre[1] = v.y;
+        } else {
+#pragma unroll
+          for (int i = 0; i < PW / 4; i++) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(srcp) + i);
+            pre[4 * i] = v.x; pre[4 * i + 1] = v.y; pre[4 * i + 2] = v.z; pre[4 * i + 3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PW; i++) pre[i] = 0;
+      }
+    };
+    auto store_pre = [&]() {
+      if (PW == 2) {
+        *reinterpret_cast<uint2*>(ringb + roff) = make_uint2(pre[0], pre[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < PW / 4; i++)
+          *reinterpret_cast<uint4*>(ringb + roff + 16 * i) = make_uint4(pre[4 * i], pre[4 * i + 1], pre[4 * i + 2], pre[4 * i + 3]);
+      }
+      if (roff == 0) ring[RING_WORDS] = pre[0];   // mirror of ring[0] (lane k == 0, even half)
+      roff ^= HALF_BYTES;
+    };
+    auto step_half = [&]() {   // pre <- next lower half
+      hidx -= 1;
+      srcp -= HALF_WORDS;
+      load_pre();
+    };
+    auto extract = [&](int lo, uint32_t nb) -> uint32_t {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + (((uint32_t)lo >> 3) & 0x7Cu));
+      return __funnelshift_r(w[0], w[1], (uint32_t)lo & 31u) & ((1u << nb) - 1u);
+    };
+
+    int err = 0;
+    uint32_t full = 0;
+    if (has) {
+      L = (int)U->table_log;
+      S = 1u << L;
+      const uint32_t* A = tabA + U->tab_off;
+      if (MODE == 0) {
+        uint4* T4 = reinterpret_cast<uint4*>(mytab);
+        const uint4* A4 = reinterpret_cast<const uint4*>(A);
+        for (uint32_t i = k; i < S / 4; i += N) T4[i] = A4[i];
+      } else {
+        uint2* T2 = reinterpret_cast<uint2*>(mytab);
+        const uint4* A4 = reinterpret_cast<const uint4*>(A);
+#pragma unroll 4
+        for (uint32_t i = k; i < S / 4; i += N) {
+          const uint4 e = A4[i];
+          // nextState = (newState + S) >> nbBits  (inverse of fsedecompressu16.go:250-251)
+          const uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
+          const uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
+          T2[i] = make_uint2(n0 | (n1 << 16), n2 | (n3 << 16));
+        }
+      }
+      const uint8_t* bs = comp + U->comp_off + U->bits_off;
+      const uint32_t blen = U->bits_len;
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(bs);
+      const uint32_t* wbase = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)63);
+      shift = (uint32_t)(addr & 63) * 8;
+      const uint32_t lastb = bs[blen - 1];
+      P = (int)(shift + 8u * (blen - 1) + (31u - __clz(lastb | 1u)));
+      const int cur_half = ((P - 1) >> 5) / HALF_WORDS;
+      cross = cur_half * (HALF_WORDS * 32);      // P <= cross  <=>  the top unread bit left half cur_half
+      count = U->count;
+      if (count > U->sym_cap) err = 2;
+      hidx = cur_half;
+      srcp = wbase + cur_half * HALF_WORDS + k * PW;
+      roff = (uint32_t)((cur_half & 1) * HALF_BYTES + k * PW * 4);
+      load_pre(); store_pre();
+      step_half(); store_pre();
+      step_half();
+    }
+    __syncwarp();
+
+    // Per-unit ring maintenance; P and cross are uniform over a unit's lanes.  Kept short so that it predicates:
+    // with four units per warp some unit crosses a half boundary in every other loop iteration.
+    auto refill = [&](bool guard) {
+      if (P <= cross) {
+        store_pre();                 // the half two above `pre` is dead: overwrite it
+        cross -= HALF_WORDS * 32;
+        step_half();
+        if (k == 0 && hidx >= 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcp - 4 * HALF_WORDS));
+        if (guard && P < (int)shift) full = 0;   // over-read: stop this unit (reads stayed inside the ring)
+      }
+      __syncwarp();
+    };
+
+    uint32_t state = 0;
+    if (has && !err) {
+      const uint32_t tot = (uint32_t)(N * L);
+      if ((uint32_t)P - shift < tot) {
+        err = 1;
+      } else {
+        state = extract(P - (k + 1) * L, (uint32_t)L);
+        P -= (int)tot;
+      }
+    }
+    refill(false);
+    uint16_t* op = states_out + (has ? U->sym_off : 0) + k;
+    const uint32_t full0 = (has && !err) ? count / N : 0u;
+    full = full0;
+    const uint32_t maxfull = __reduce_max_sync(0xffffffffu, full);
+    // The unguarded loop lets an over-reading (corrupt) unit run on to minfull: its reads stay inside the ring and the
+    // table, its writes inside its own sym_cap, and P falls by at most 16 bits per symbol, so it cannot wrap below.
+    uint32_t minfull = min(maxfull, __reduce_min_sync(0xffffffffu, has ? full : 0xffffffffu));
+    if (__any_sync(0xffffffffu, count > (1u << 26))) minfull = 0;
+
+    // ALL: every unit of the warp is inside its stream (no per-round activity test)
+    auto round = [&](auto all_tag, bool act, int buf, int oidx) {
+      constexpr bool ALL = decltype(all_tag)::value;
+      uint32_t nb, ns;
+      if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
+      else { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }   // nx >= 1 (K1)
+      if (!ALL && !act) nb = 0;
+      uint32_t tot;
+      const uint32_t before = packed_prefix<N>(nb, xmine + buf * 32, xunit + buf * 32, bm, &tot);
+      const uint32_t bits = extract(P - (int)before - (int)nb, nb);
+      if (ALL ? has : act) {
+        op[oidx * N] = (uint16_t)state;
+        state = ns + bits;
+      }
+      P -= (int)tot;
+    };
+    // ring check once per two rounds (two rounds consume at most 2*N*16 = 256 bits = half of a ring half)
+    uint32_t r = 0;
+    for (; r + 2 <= minfull; r += 2) {
+      round(std::true_type{}, true, 0, 0);
+      round(std::true_type{}, true, 1, 1);
+      op += 2 * N;
+      refill(false);
+    }
+    if (has && P < (int)shift) full = 0;
+    for (; r + 2 <= maxfull; r += 2) {
+      const bool a0 = r < full, a1 = r + 1 < full;
+      round(std::false_type{}, a0, 0, 0);
+      round(std::false_type{}, a1, 1, 1);
+      op += (a0 ? N : 0) + (a1 ? N : 0);
+      refill(true);
+    }
+    if (r < maxfull) {
+      const bool a0 = r < full;
+      round(std::false_type{}, a0, 0, 0);
+      op += a0 ? N : 0;
+      refill(true);
+    }
+    {
+      const uint32_t tail = (has && !err && full == full0) ? count - full0 * N : 0u;
+      const bool act = (uint32_t)k < tail;
+      uint32_t nb;
+      if (MODE == 0) { nb = T32[state] >> 16; }
+      else { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); }
+      if (!act) nb = 0;
+      uint32_t tot;
+      packed_prefix<N>(nb, xmine + 32, xunit + 32, bm, &tot);
+      if (act) *op = (uint16_t)state;
+      P -= (int)tot;
+      if (has && !err && (P < (int)shift || full != full0)) err = 1;
+    }
+    if (has && k == 0) {
+      U->nsym = count;
+      if (err) U->status = err == 1 ? MIC_E_BITSTREAM : MIC_E_SIZE;
+    }
+  }
+}
+
 size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta) {
   size_t t = smem_mode == 2 ? 0 : ((size_t)(1u << max_log) * (smem_mode == 0 ? 4 : 2));
-  return (size_t)slots_per_cta * (t + RING_STRIDE * 4);
+  return (size_t)slots_per_cta * (t + RING_STRIDE * 4 + 64);   // + the packed kernel's byte-exchange area
 }
 
 template <int N, int MODE>
@@ -294,9 +562,31 @@ static void launch_one(MicUnit* d_units, const int* d_list, int nlist, const uin
   k_ans_decode<N, MODE><<<grid, 32 * slots, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
 }
 
+template <int N, int MODE>
+static void launch_packed(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, const uint32_t* d_tabA,
+                          uint16_t* d_states, int max_log, int slots, int grid, cudaStream_t st) {
+  constexpr int UPW = 32 / N;
+  const int warps = (slots + UPW - 1) / UPW;
+  size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
+  cudaFuncSetAttribute(k_ans_decode_packed<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_ans_decode_packed<N, MODE><<<grid, 32 * warps, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
+}
+
+static bool use_packed() {
+  static const bool v = [] { const char* e = getenv("MICGPU_K2_ONE_UNIT_PER_WARP"); return !(e && e[0] == '1'); }();
+  return v;
+}
+
 template <int N>
 static void launch_n(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, const uint32_t* d_tabA,
                      uint16_t* d_states, int max_log, int mode, int slots, int grid, cudaStream_t st) {
+  if constexpr (N > 1) {
+    if (mode != 2 && use_packed()) {
+      if (mode == 0) launch_packed<N, 0>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);
+      else launch_packed<N, 1>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);
+      return;
+    }
+  }
   if (mode == 0) launch_one<N, 0>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);
   else if (mode == 1) launch_one<N, 1>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);
   else launch_one<N, 2>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, grid, st);

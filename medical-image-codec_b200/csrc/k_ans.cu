@@ -331,6 +331,43 @@ __device__ __forceinline__ uint32_t packed_prefix(uint32_t nb, uint8_t* my_byte,
   }
 }
 
+// Ring maintenance of the packed kernel: straight-line, predicated, and asynchronous.
+// The 128 B ring is four 32 B quarters; stream quarter q lives in slot q & 3.  Reads of one loop iteration (two
+// rounds, at most C = 256 bits) touch [P - C, P).  When the top unread bit leaves quarter qtop, that slot receives
+// quarter qtop - 4 through cp.async (global -> shared, no register and therefore no scoreboard wait in the loop: with
+// four units per warp an LDG result consumed one iteration later stalled the whole warp ~140 cycles per refill,
+// profiles/README.md).  A copy issued at check i is complete for every lane after check i + 2 (wait_group 2 +
+// __syncwarp).  Proof of coverage: after check j the ring (landed or in flight) reaches below P_j + 256 - 1024; the
+// rounds after check i may touch [P_i - C, P_i) and need what was issued up to check i - 2, which reaches below
+// P_(i-2) - 768 <= P_i + 2C - 768 <= P_i - C because 3C <= 768.  Quarters below the start of the stream are never
+// copied: only an over-reading (corrupt) stream looks there; it reads stale ring bytes and is rejected by P < shift.
+template <int N>
+__device__ __forceinline__ void ring_refill_async(int P, int& cross, uint32_t& ra, uint32_t& qo, int& hidx, const uint8_t*& srcp,
+                                                  uint32_t rk, uint32_t ringsa, int pf_min) {
+  constexpr int CP = 32 / N;   // bytes of a quarter each lane copies
+  asm volatile(
+      "{\n\t.reg .pred p, q, pl, pp;\n\t"
+      "setp.le.s32 p, %5, %0;\n\t"
+      "setp.ge.and.s32 pl, %3, 0, p;\n\t"
+      "setp.eq.and.u32 q, %1, %7, pl;\n\t"            // slot 0, lane k == 0: ring word 0 is mirrored at word 32
+      "@pl cp.async.ca.shared.global [%1], [%4], %9;\n\t"
+      "@q cp.async.ca.shared.global [%7+128], [%4], 4;\n\t"
+      "cp.async.commit_group;\n\t"
+      "cp.async.wait_group 2;\n\t"
+      "setp.ge.and.s32 pp, %3, %8, p;\n\t"
+      "@pp prefetch.global.L2 [%4+-256];\n\t"
+      "@p add.s32 %0, %0, -256;\n\t"
+      "@p add.s32 %3, %3, -1;\n\t"
+      "@p add.s64 %4, %4, -32;\n\t"
+      "@p add.s32 %2, %2, -32;\n\t"
+      "@p and.b32 %2, %2, 96;\n\t"
+      "add.s32 %1, %6, %2;\n\t"
+      "}\n"
+      : "+r"(cross), "+r"(ra), "+r"(qo), "+r"(hidx), "+l"(srcp)
+      : "r"(P), "r"(rk), "r"(ringsa), "r"(pf_min), "n"(CP)
+      : "memory");
+}
+
 template <int N, int MODE>
 __global__ void __launch_bounds__(1024)
 k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
@@ -338,24 +375,30 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
   static_assert(N == 2 || N == 4 || N == 8, "packed decode is for the interleaved coders");
   static_assert(MODE == 0 || MODE == 1, "packed decode keeps its tables in shared memory");
   extern __shared__ __align__(16) uint8_t smem[];
-  constexpr int PW = HALF_WORDS / N;             // ring words each lane carries for the in-flight half
-  constexpr int HALF_BYTES = HALF_WORDS * 4;
+  constexpr int CP = 32 / N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int k = lane % N, sub = lane / N;
   const int slot = sub * nwarps + warp;          // slots are dealt round-robin over the warps
   const bool slot_ok = slot < slots;
-  const int sslot = slot_ok ? slot : 0;          // lanes without a slot alias slot 0 and never write
-  const ByteMasks<N> bm(k);
+  const int sslot = slot_ok ? slot : 0;          // lanes without a slot alias slot 0's ring (read-only)
 
+  const ByteMasks<N> bm(k);
   const size_t tbytes = (size_t)(1u << max_log) * (MODE == 0 ? 4 : 2);
   uint8_t* mytab = smem + (size_t)sslot * tbytes;
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)slots * tbytes) + sslot * RING_STRIDE;
-  uint8_t* xch = smem + (size_t)slots * (tbytes + RING_STRIDE * 4) + warp * 64;   // 2 x 32 B per warp
+  uint8_t* xbase = smem + (size_t)slots * (tbytes + RING_STRIDE * 4);
+  // Idle cell: a one-entry table for lanes that own no unit.  With L = 5 the entry decodes to nbBits = 0 and
+  // newState = 0, so such lanes run the same instruction stream without consuming bits or leaving the cell.
+  uint32_t* idle = reinterpret_cast<uint32_t*>(xbase);
+  uint8_t* xch = xbase + 16 + warp * 64;         // byte exchange: 2 x 32 B per warp
   uint8_t* xmine = xch + lane;
   const uint8_t* xunit = xch + sub * N;
-  const uint32_t* T32 = reinterpret_cast<const uint32_t*>(mytab);
-  const uint16_t* T16 = reinterpret_cast<const uint16_t*>(mytab);
-  uint8_t* ringb = reinterpret_cast<uint8_t*>(ring);
+  const uint8_t* ringb = reinterpret_cast<const uint8_t*>(ring);
+  const uint32_t ringsa = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t rk = ringsa + (uint32_t)(k * CP);
+  const int pf_min = k == 0 ? 8 : 0x7fffffff;    // lane 0 of a unit prefetches 8 quarters (256 B) ahead into L2
+  if (threadIdx.x == 0) *idle = MODE == 0 ? 0u : 32u;
+  __syncthreads();
 
   for (int base = blockIdx.x * slots; base < nlist; base += gridDim.x * slots) {
     const int li = base + slot;
@@ -369,48 +412,10 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     int L = 5;
     uint32_t S = 32, shift = 0, count = 0;
     int P = 0, cross = -(1 << 30);
-    // ring refill state: `pre` holds the half with index hidx; it replaces the ring half at byte offset roff
-    // (this lane's PW words of it) once the half two above it is dead.
-    uint32_t pre[PW];
-#pragma unroll
-    for (int i = 0; i < PW; i++) pre[i] = 0;
-    const uint32_t* srcp = nullptr;   // this lane's words of half hidx
+    const uint8_t* srcp = nullptr;    // this lane's bytes of the next quarter to copy (index hidx)
     int hidx = -1;
-    uint32_t roff = 0;
+    uint32_t qo = 0, ra = rk;
 
-    auto load_pre = [&]() {
-      if (hidx >= 0) {
-        if (PW == 2) {
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(srcp));
-          pre[0] = v.x; pre[1] = v.y;
-        } else {
-#pragma unroll
-          for (int i = 0; i < PW / 4; i++) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(srcp) + i);
-            pre[4 * i] = v.x; pre[4 * i + 1] = v.y; pre[4 * i + 2] = v.z; pre[4 * i + 3] = v.w;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < PW; i++) pre[i] = 0;
-      }
-    };
-    auto store_pre = [&]() {
-      if (PW == 2) {
-        *reinterpret_cast<uint2*>(ringb + roff) = make_uint2(pre[0], pre[1]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < PW / 4; i++)
-          *reinterpret_cast<uint4*>(ringb + roff + 16 * i) = make_uint4(pre[4 * i], pre[4 * i + 1], pre[4 * i + 2], pre[4 * i + 3]);
-      }
-      if (roff == 0) ring[RING_WORDS] = pre[0];   // mirror of ring[0] (lane k == 0, even half)
-      roff ^= HALF_BYTES;
-    };
-    auto step_half = [&]() {   // pre <- next lower half
-      hidx -= 1;
-      srcp -= HALF_WORDS;
-      load_pre();
-    };
     auto extract = [&](int lo, uint32_t nb) -> uint32_t {
       const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + (((uint32_t)lo >> 3) & 0x7Cu));
       return __funnelshift_r(w[0], w[1], (uint32_t)lo & 31u) & ((1u << nb) - 1u);
@@ -421,6 +426,34 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     if (has) {
       L = (int)U->table_log;
       S = 1u << L;
+      const uint8_t* bs = comp + U->comp_off + U->bits_off;
+      const uint32_t blen = U->bits_len;
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(bs);
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(addr & ~(uintptr_t)31);
+      shift = (uint32_t)(addr & 31) * 8;         // first data bit in ring coordinates
+      const uint32_t lastb = bs[blen - 1];       // non-zero (checked by K1)
+      P = (int)(shift + 8u * (blen - 1) + (31u - __clz(lastb | 1u)));   // unread bits are [shift, P)
+      const int qtop = (P - 1) >> 8;
+      cross = qtop << 8;                         // P <= cross  <=>  the top unread bit left quarter qtop
+      // quarters qtop .. qtop-3 fill the ring
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int q = qtop - j;
+        if (q >= 0) {
+          const uint32_t dst = rk + (uint32_t)((q & 3) << 5);
+          const uint8_t* src = wbase + (size_t)q * 32 + k * CP;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(CP) : "memory");
+          if (k == 0 && (q & 3) == 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ringsa + 128u), "l"(src) : "memory");
+        }
+      }
+      hidx = qtop - 4;
+      srcp = wbase + (ptrdiff_t)hidx * 32 + k * CP;
+      qo = (uint32_t)((hidx & 3) << 5);
+      ra = rk + qo;
+      count = U->count;
+      if (count > U->sym_cap) err = 2;
+      // ---- stage the decode table while the ring copies fly -----------------------------
       const uint32_t* A = tabA + U->tab_off;
       if (MODE == 0) {
         uint4* T4 = reinterpret_cast<uint4*>(mytab);
@@ -438,36 +471,12 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
           T2[i] = make_uint2(n0 | (n1 << 16), n2 | (n3 << 16));
         }
       }
-      const uint8_t* bs = comp + U->comp_off + U->bits_off;
-      const uint32_t blen = U->bits_len;
-      const uintptr_t addr = reinterpret_cast<uintptr_t>(bs);
-      const uint32_t* wbase = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)63);
-      shift = (uint32_t)(addr & 63) * 8;
-      const uint32_t lastb = bs[blen - 1];
-      P = (int)(shift + 8u * (blen - 1) + (31u - __clz(lastb | 1u)));
-      const int cur_half = ((P - 1) >> 5) / HALF_WORDS;
-      cross = cur_half * (HALF_WORDS * 32);      // P <= cross  <=>  the top unread bit left half cur_half
-      count = U->count;
-      if (count > U->sym_cap) err = 2;
-      hidx = cur_half;
-      srcp = wbase + cur_half * HALF_WORDS + k * PW;
-      roff = (uint32_t)((cur_half & 1) * HALF_BYTES + k * PW * 4);
-      load_pre(); store_pre();
-      step_half(); store_pre();
-      step_half();
     }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-
-    // Per-unit ring maintenance; P and cross are uniform over a unit's lanes.  Kept short so that it predicates:
-    // with four units per warp some unit crosses a half boundary in every other loop iteration.
-    auto refill = [&](bool guard) {
-      if (P <= cross) {
-        store_pre();                 // the half two above `pre` is dead: overwrite it
-        cross -= HALF_WORDS * 32;
-        step_half();
-        if (k == 0 && hidx >= 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcp - 4 * HALF_WORDS));
-        if (guard && P < (int)shift) full = 0;   // over-read: stop this unit (reads stayed inside the ring)
-      }
+    // Per-unit ring maintenance; P and cross are uniform over a unit's lanes.
+    auto refill = [&]() {
+      ring_refill_async<N>(P, cross, ra, qo, hidx, srcp, rk, ringsa, pf_min);
       __syncwarp();
     };
 
@@ -481,17 +490,22 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
         P -= (int)tot;
       }
     }
-    refill(false);
+    refill();
+    const bool live = has && !err;
+    if (!live) { L = 5; S = 32; state = 0; }
+    // lanes without a live unit decode the idle cell
+    const uint32_t* T32 = live ? reinterpret_cast<const uint32_t*>(mytab) : idle;
+    const uint16_t* T16 = live ? reinterpret_cast<const uint16_t*>(mytab) : reinterpret_cast<const uint16_t*>(idle);
     uint16_t* op = states_out + (has ? U->sym_off : 0) + k;
-    const uint32_t full0 = (has && !err) ? count / N : 0u;
+    const uint32_t full0 = live ? count / N : 0u;
     full = full0;
     const uint32_t maxfull = __reduce_max_sync(0xffffffffu, full);
     // The unguarded loop lets an over-reading (corrupt) unit run on to minfull: its reads stay inside the ring and the
     // table, its writes inside its own sym_cap, and P falls by at most 16 bits per symbol, so it cannot wrap below.
-    uint32_t minfull = min(maxfull, __reduce_min_sync(0xffffffffu, has ? full : 0xffffffffu));
+    uint32_t minfull = min(maxfull, __reduce_min_sync(0xffffffffu, live ? full : 0xffffffffu));
     if (__any_sync(0xffffffffu, count > (1u << 26))) minfull = 0;
 
-    // ALL: every unit of the warp is inside its stream (no per-round activity test)
+    // ALL: every live unit of the warp is inside its stream (no per-round activity test)
     auto round = [&](auto all_tag, bool act, int buf, int oidx) {
       constexpr bool ALL = decltype(all_tag)::value;
       uint32_t nb, ns;
@@ -501,36 +515,41 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
       uint32_t tot;
       const uint32_t before = packed_prefix<N>(nb, xmine + buf * 32, xunit + buf * 32, bm, &tot);
       const uint32_t bits = extract(P - (int)before - (int)nb, nb);
-      if (ALL ? has : act) {
+      if (ALL) {
+        if (live) op[oidx * N] = (uint16_t)state;
+        state = ns + bits;
+      } else if (act) {
         op[oidx * N] = (uint16_t)state;
         state = ns + bits;
       }
       P -= (int)tot;
     };
-    // ring check once per two rounds (two rounds consume at most 2*N*16 = 256 bits = half of a ring half)
+    // ring check once per two rounds (two rounds consume at most 2*N*16 = 256 bits = one quarter)
     uint32_t r = 0;
     for (; r + 2 <= minfull; r += 2) {
       round(std::true_type{}, true, 0, 0);
       round(std::true_type{}, true, 1, 1);
       op += 2 * N;
-      refill(false);
+      refill();
     }
-    if (has && P < (int)shift) full = 0;
+    if (live && P < (int)shift) full = 0;
     for (; r + 2 <= maxfull; r += 2) {
       const bool a0 = r < full, a1 = r + 1 < full;
       round(std::false_type{}, a0, 0, 0);
       round(std::false_type{}, a1, 1, 1);
       op += (a0 ? N : 0) + (a1 ? N : 0);
-      refill(true);
+      refill();
+      if (P < (int)shift) full = 0;   // over-read: stop this unit (reads stayed inside the ring)
     }
     if (r < maxfull) {
       const bool a0 = r < full;
       round(std::false_type{}, a0, 0, 0);
       op += a0 ? N : 0;
-      refill(true);
+      refill();
+      if (P < (int)shift) full = 0;
     }
     {
-      const uint32_t tail = (has && !err && full == full0) ? count - full0 * N : 0u;
+      const uint32_t tail = (live && full == full0) ? count - full0 * N : 0u;
       const bool act = (uint32_t)k < tail;
       uint32_t nb;
       if (MODE == 0) { nb = T32[state] >> 16; }
@@ -540,8 +559,9 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
       packed_prefix<N>(nb, xmine + 32, xunit + 32, bm, &tot);
       if (act) *op = (uint16_t)state;
       P -= (int)tot;
-      if (has && !err && (P < (int)shift || full != full0)) err = 1;
+      if (live && (P < (int)shift || full != full0)) err = 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // no copy may land in the ring after the next unit took it over
     if (has && k == 0) {
       U->nsym = count;
       if (err) U->status = err == 1 ? MIC_E_BITSTREAM : MIC_E_SIZE;
@@ -551,7 +571,8 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
 
 size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta) {
   size_t t = smem_mode == 2 ? 0 : ((size_t)(1u << max_log) * (smem_mode == 0 ? 4 : 2));
-  return (size_t)slots_per_cta * (t + RING_STRIDE * 4 + 64);   // + the packed kernel's byte-exchange area
+  // + the packed kernel's idle cell (16 B) and byte-exchange area (64 B per warp; at least 4 slots share a warp)
+  return (size_t)slots_per_cta * (t + RING_STRIDE * 4) + 16 + 64 * (size_t)((slots_per_cta + 3) / 4);
 }
 
 template <int N, int MODE>

@@ -158,9 +158,10 @@ int plan_commit(micgpu_decoder* d) {
     a.max_log = ml;
     const int slots_max = 32;   // one slot per warp, at most 32 warps per CTA
     const int need_per_sm = (n + d->sm_count - 1) / d->sm_count;
-    auto fit = [&](int mode) {
-      size_t per = ans_decode_smem_bytes(ml, mode, 1);
-      return (int)std::min<size_t>(budget / per, 4096);
+    auto fit = [&](int mode) {   // most slots whose tables, rings and exchange area fit one CTA
+      int s = 0;
+      while (s < 64 && ans_decode_smem_bytes(ml, mode, s + 1) <= budget) s++;
+      return s;
     };
     int mode = 0;
     if (fit(0) < std::min(need_per_sm, slots_max)) mode = ml <= 15 && fit(1) > fit(0) ? 1 : 0;

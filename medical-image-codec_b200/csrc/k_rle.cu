@@ -15,6 +15,16 @@
 //      dropped; every other element is one pixel.  Pixels are compacted into
 //      the residual plane D (row pitch wp) and literal pixels set a bit in M.
 // RLE-kind units (temporal residuals, wavelet coefficients) copy s_e to d_out.
+//
+// Instruction economy (the kernel was issue bound at 64 % with 77 thread instructions per symbol, profiles/):
+//   * staging translates eight states per thread step (one 16 B load, eight table reads, one 16 B store);
+//   * s_e is laid out destination-aligned: element o sits at s_e[ph + o] with ph chosen so that an aligned group of
+//     eight elements is an aligned 16 B store in D (D's row phase follows the global pixel index, mic_unit.h);
+//   * the common chunk -- no delimiter value in it -- is written optimistically, 16 B per thread step, with the
+//     delimiter test fused into the same pass; a chunk that turns out to hold a delimiter is redone by the exact
+//     marker/compaction passes (they rewrite the same D range);
+//   * units are handed out through an atomic queue: CTAs are resident five per SM, a static stride left the last
+//     wave half empty.
 #include "mic_device.cuh"
 
 namespace micgpu {
@@ -37,13 +47,14 @@ struct WalkState {
   int done, err;
 };
 
-__global__ void __launch_bounds__(K3_THREADS)
+__global__ void __launch_bounds__(K3_THREADS, 5)
 k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict__ states,
              const uint16_t* __restrict__ tabS, uint16_t* __restrict__ D, uint32_t* __restrict__ M,
-             uint16_t* __restrict__ out, int tab_smem_log) {
-  __shared__ uint16_t s_in[IN_N];
-  __shared__ uint16_t s_e[OUT_CH];
-  __shared__ uint16_t s_p[OUT_CH];
+             uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue) {
+  __shared__ __align__(16) uint16_t s_in[IN_N];
+  __shared__ __align__(16) uint16_t s_e_raw[OUT_CH + 16];
+  __shared__ __align__(16) uint16_t s_p[OUT_CH];
+  __shared__ int s_ui;
   __shared__ uint32_t s_non[NWIN], s_mark[NWIN];
   __shared__ int s_wprev[NWIN], s_pixbase[NWIN + 1];
   __shared__ uint16_t s_run_o[MAXR], s_run_n[MAXR];   // run list of the current chunk: output start, length
@@ -53,9 +64,13 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int ui = blockIdx.x; ui < nunits; ui += gridDim.x) {
-    MicUnit* U = &units[ui];
+  while (true) {
     __syncthreads();
+    if (tid == 0) s_ui = (int)atomicAdd(queue, 1u);
+    __syncthreads();
+    const int ui = s_ui;
+    if (ui >= nunits) break;
+    MicUnit* U = &units[ui];
     if (U->status != MIC_OK) continue;
     const int nsym = (int)U->nsym;
     const uint16_t* st = states + U->sym_off;
@@ -111,30 +126,30 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       const bool restage = first || (wend0 < nsym && wend0 - ipos < IN_N / 2);
       __syncthreads();
       if (restage) {
-        const int nb = min(nsym - ipos, IN_N);
-        // two dependent global loads per symbol (state, then tabS[state], L1-resident): batch 8 of each
-        for (int i0 = tid; i0 < nb; i0 += 8 * K3_THREADS) {
-          unsigned stv[8];
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const int i = i0 + q * K3_THREADS;
-            stv[q] = i < nb ? __ldg(st + ipos + i) : 0u;
-          }
-          if (tab_in_smem) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const int i = i0 + q * K3_THREADS;
-              if (i < nb) s_in[i] = s_tab[stv[q]];
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const int i = i0 + q * K3_THREADS;
-              if (i < nb) s_in[i] = __ldg(Sy + stv[q]);
-            }
-          }
+        // window = [a0, a0 + nb): starts on a 16 B boundary of the state stream (sym_off is a multiple of 16 elements)
+        const int a0 = ipos & ~7;
+        const int nb = min(nsym - a0, IN_N);
+        const uint4* st4 = reinterpret_cast<const uint4*>(st + a0);
+        const int ng = nb >> 3;
+        // eight states per thread step: one 16 B load, eight table reads, one 16 B store
+        for (int v0 = tid; v0 < ng; v0 += 2 * K3_THREADS) {
+          const int v1 = v0 + K3_THREADS;
+          const uint4 sa = __ldg(st4 + v0);
+          uint4 sb = make_uint4(0, 0, 0, 0);
+          if (v1 < ng) sb = __ldg(st4 + v1);
+          auto xl = [&](uint32_t w) -> uint32_t {
+            if (tab_in_smem) return (uint32_t)s_tab[w & 0xFFFFu] | ((uint32_t)s_tab[w >> 16] << 16);
+            return (uint32_t)__ldg(Sy + (w & 0xFFFFu)) | ((uint32_t)__ldg(Sy + (w >> 16)) << 16);
+          };
+          *reinterpret_cast<uint4*>(s_in + 8 * v0) = make_uint4(xl(sa.x), xl(sa.y), xl(sa.z), xl(sa.w));
+          if (v1 < ng) *reinterpret_cast<uint4*>(s_in + 8 * v1) = make_uint4(xl(sb.x), xl(sb.y), xl(sb.z), xl(sb.w));
         }
-        if (tid == 0) { ws.wbase = ipos; ws.wend = ipos + nb; }
+        if (tid < (nb & 7)) {
+          const int i = 8 * ng + tid;
+          const unsigned sv = __ldg(st + a0 + i);
+          s_in[i] = tab_in_smem ? s_tab[sv] : __ldg(Sy + sv);
+        }
+        if (tid == 0) { ws.wbase = a0; ws.wend = a0 + nb; }
       }
       __syncthreads();
       // ---------------- B: header walk + expansion (warp 0) -----------------
@@ -195,15 +210,38 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       const int done = ws.done;
       if (ws.err) break;
       // ---------------- B2: expand the listed runs, all threads per run -------
+      // Destination-aligned layout: element o of the chunk sits at se[o] = s_e_raw[ph + o]; for spatial units ph makes
+      // (index in s_e_raw) == (pixel index + align0) mod 8, so aligned groups of eight are aligned 16 B stores in D.
+      const int skip = (spatial && first) ? 1 : 0;   // element 0 of the stream is maxValue, not a pixel
+      const int ph = spatial ? (int)((pix + align0 + 8u - (unsigned)skip) & 7u) : 0;
+      uint16_t* se = s_e_raw + ph;
       {
         const int nr = ws.nruns;
         for (int r = 0; r < nr; r++) {
           const int o = s_run_o[r], n = s_run_n[r], src = s_run_src[r];
+          // 32-bit destination words; the odd head / tail elements go scalar
+          const int d0 = ph + o, d1 = d0 + n;            // element range in s_e_raw
+          const int w0 = (d0 + 1) >> 1, w1 = d1 >> 1;    // full words [w0, w1)
+          uint32_t* dw = reinterpret_cast<uint32_t*>(s_e_raw);
           if (src >= 0) {
-            for (int j = tid; j < n; j += K3_THREADS) s_e[o + j] = s_in[src + j];
+            const int sh = src - d0;                      // source index = destination index + sh
+            if (tid == 0 && (d0 & 1) && n > 0) s_e_raw[d0] = s_in[d0 + sh];
+            if (tid == 1 && (d1 & 1) && d1 - 1 >= w0 * 2 && n > 0) s_e_raw[d1 - 1] = s_in[d1 - 1 + sh];
+            if ((sh & 1) == 0) {
+              const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_in) + (sh >> 1);
+#pragma unroll 2
+              for (int w = w0 + tid; w < w1; w += K3_THREADS) dw[w] = sw[w];
+            } else {
+#pragma unroll 2
+              for (int w = w0 + tid; w < w1; w += K3_THREADS)
+                dw[w] = (uint32_t)s_in[2 * w + sh] | ((uint32_t)s_in[2 * w + 1 + sh] << 16);
+            }
           } else {
-            const uint16_t v16 = (uint16_t)(-(src + 1));
-            for (int j = tid; j < n; j += K3_THREADS) s_e[o + j] = v16;
+            const uint32_t v16 = (uint32_t)(-(src + 1)) & 0xFFFFu;
+            if (tid == 0 && (d0 & 1) && n > 0) s_e_raw[d0] = (uint16_t)v16;
+            if (tid == 1 && (d1 & 1) && d1 - 1 >= w0 * 2 && n > 0) s_e_raw[d1 - 1] = (uint16_t)v16;
+            const uint32_t v32 = v16 | (v16 << 16);
+            for (int w = w0 + tid; w < w1; w += K3_THREADS) dw[w] = v32;
           }
         }
       }
@@ -212,7 +250,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       if (!spatial) {
         // ---------------- C (RLE kind): straight copy ------------------------
         uint16_t* dst = out + U->out_off + pix;
-        for (int i = tid; i < nout; i += K3_THREADS) dst[i] = s_e[i];
+        for (int i = tid; i < nout; i += K3_THREADS) dst[i] = se[i];
         pix += (unsigned)nout;
         first = false;
         if (done || pix >= outlen) break;
@@ -223,7 +261,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       const bool skip0 = first;  // element 0 of the stream is maxValue, not a pixel
       if (first) {
         if (nout < 1) break;
-        const unsigned maxv = s_e[0];
+        const unsigned maxv = se[0];
         const int depth = bit_len16(maxv);
         if (depth == 0) break;   // reported below as a short stream
         thr = (1u << (depth - 1)) - 1u;
@@ -231,29 +269,70 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         if (tid == 0) { U->thr = thr; U->delim = delim; }
       }
       first = false;
-      // Fast path: no element of the chunk equals the delimiter (and no pending literal), so every
-      // element is a plain pixel and the chunk goes to D without the marker/compaction passes.
-      {
-        bool has = false;
-        for (int i = tid; i < nout; i += K3_THREADS) has |= (s_e[i] == delim) && !(i == 0 && skip0);
-        const int anyd = __syncthreads_or(has ? 1 : 0) | (int)carry_m;
-        if (!anyd) {
-          const int skip = skip0 ? 1 : 0;
-          int n = nout - skip;
-          if (n < 0) n = 0;
-          const int npix_chunk = n;
-          if (pix + (unsigned)n > npx) n = (int)(npx - pix);
-          if (tid < n) {
-            unsigned long long gp = pix + (unsigned)tid;
-            unsigned y = (unsigned)(gp / W), x = (unsigned)(gp - (unsigned long long)y * W);
-            uint16_t* Du = D + U->d_off;
-            for (int i = tid; i < n; i += K3_THREADS) {
-              const unsigned ay = (align0 + (y & 7u) * (W & 7u)) & 7u;
-              Du[(unsigned long long)y * wp + ay + x] = s_e[i + skip];
-              x += K3_THREADS;
-              while (x >= W) { x -= W; y++; }
+      // Optimistic path: if no element of the chunk equals the delimiter (and no literal is pending), every element
+      // is a plain pixel.  The chunk is written to D in aligned groups of eight while the same pass looks for the
+      // delimiter; a chunk that has one is redone below by the exact passes, which rewrite this D range.
+      if (!carry_m) {
+        int n = nout - skip;
+        if (n < 0) n = 0;
+        const int npix_chunk = n;
+        if (pix + (unsigned)n > npx) n = (int)(npx - pix);
+        const int e_lo = ph + skip, e_hi = e_lo + n;          // pixel elements in s_e_raw coordinates
+        const int e_chk = ph + nout;                           // delimiter test covers every element of the chunk
+        const int g0 = e_lo >> 3, g1 = (max(e_hi, e_chk) + 7) >> 3;
+        uint16_t* Du = D + U->d_off;
+        const uint32_t d2 = delim | (delim << 16);
+        bool dirty = false;
+        // pixel index of s_e_raw[0] is pbase (may be "negative" by less than 8 on the first chunk: use signed)
+        const long long pbase = (long long)pix - (long long)e_lo;
+        // (y, x) of the first pixel this thread's group can hold; npx < 2^32 (65535 x 65535), so 32-bit division
+        int g = g0 + tid;
+        unsigned y = 0, x = 0;
+        if (g < g1) {
+          const long long p0 = pbase + 8ll * g;
+          const unsigned pb = p0 > 0 ? (unsigned)p0 : 0u;
+          y = pb / W; x = pb - y * W;
+        }
+        for (; g < g1; g += K3_THREADS) {
+          const int eb = 8 * g;
+          const uint4 v = *reinterpret_cast<const uint4*>(s_e_raw + eb);
+          const long long p0 = pbase + eb;
+          const bool interior = eb >= e_lo && eb + 8 <= e_hi;
+          if (interior && x + 8u <= W) {
+            // zero-halfword test on v ^ delim (exact for 16-bit lanes)
+            const uint32_t a = v.x ^ d2, b = v.y ^ d2, c = v.z ^ d2, d = v.w ^ d2;
+            const uint32_t z = ((a - 0x00010001u) & ~a) | ((b - 0x00010001u) & ~b) | ((c - 0x00010001u) & ~c) | ((d - 0x00010001u) & ~d);
+            dirty |= (z & 0x80008000u) != 0;
+            const unsigned ay = (align0 + (y & 7u) * (W & 7u)) & 7u;
+            *reinterpret_cast<uint4*>(Du + (unsigned long long)y * wp + ay + x) = v;
+          } else {
+            // partial group (chunk edge) or a group that straddles a row end: element by element, (yy, xx) walked
+            const uint16_t* ve = s_e_raw + eb;
+            const int i0 = p0 < 0 ? (int)(-p0) : 0;   // elements before pixel 0 (first chunk only)
+            unsigned yy = y, xx = x;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int e = eb + i;
+              if (e >= e_lo && e < e_chk) dirty |= ve[i] == delim;
+              if (i >= i0) {
+                if (e >= e_lo && e < e_hi) {
+                  const unsigned ay = (align0 + (yy & 7u) * (W & 7u)) & 7u;
+                  Du[(unsigned long long)yy * wp + ay + xx] = ve[i];
+                }
+                if (++xx >= W) { xx = 0; yy++; }
+              }
             }
           }
+          // advance this thread's group by K3_THREADS groups
+          if (W >= 8u * K3_THREADS && p0 >= 0) {
+            x += 8u * K3_THREADS;
+            if (x >= W) { x -= W; y++; }
+          } else {
+            const unsigned pn = (unsigned)(p0 + 8ll * K3_THREADS);
+            y = pn / W; x = pn - y * W;
+          }
+        }
+        if (!__syncthreads_or(dirty ? 1 : 0)) {
           pix += (unsigned)npix_chunk;
           if (done || pix >= npx) break;
           continue;
@@ -264,7 +343,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       for (int w = warp; w < nwin; w += K3_WARPS) {
         const int e = w * 32 + lane;
         const bool valid = e < nout;
-        bool isd = valid && s_e[e] == delim;
+        bool isd = valid && se[e] == delim;
         if (e == 0 && (skip0 || carry_m)) isd = false;   // maxValue / forced literal
         const unsigned non = __ballot_sync(0xffffffffu, !isd);
         if (lane == 0) s_non[w] = non;
@@ -300,7 +379,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       for (int w = warp; w < nwin; w += K3_WARPS) {
         const int e = w * 32 + lane;
         const bool valid = e < nout;
-        bool isd = valid && s_e[e] == delim;
+        bool isd = valid && se[e] == delim;
         if (e == 0 && (skip0 || carry_m)) isd = false;
         const unsigned non = s_non[w];
         const unsigned m = non & (0xffffffffu >> (31 - lane));
@@ -358,7 +437,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           const int pl = s_pixbase[w] + __popc(~mm & vm & ((1u << lane) - 1u));
           const unsigned long long gp = pix + (unsigned)pl;
           if (gp < npx) {
-            s_p[pl] = s_e[e];
+            s_p[pl] = se[e];
             if (prevm) {   // literal pixel (deltarlecompressu16.go:105-106)
               const unsigned y = (unsigned)(gp / W), x = (unsigned)(gp - (unsigned long long)y * W);
               const unsigned pc = ((align0 + (y & 7u) * (W & 7u)) & 7u) + x;   // padded column
@@ -401,13 +480,15 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
 }
 
 void launch_rle_expand(MicUnit* d_units, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
-                       uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, cudaStream_t st) {
+                       uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, unsigned int* d_queue,
+                       cudaStream_t st) {
   if (nunits <= 0) return;
+  cudaMemsetAsync(d_queue, 0, sizeof(unsigned int), st);
   // stage tabS in shared memory up to tableLog 14 (32 KB); larger tables are gathered through L1/L2
   const int tab_log = max_log <= 14 ? max_log : 14;
   const size_t smem = (size_t)2 << tab_log;
   cudaFuncSetAttribute(k_rle_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_rle_expand<<<grid, K3_THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log);
+  k_rle_expand<<<grid, K3_THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue);
 }
 
 }  // namespace micgpu

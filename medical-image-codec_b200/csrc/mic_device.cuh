@@ -25,7 +25,8 @@ size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta);
 // residual plane D (pitch wp) and the literal bit mask M; RLE units write
 // their expanded stream straight to d_out.
 void launch_rle_expand(MicUnit* d_units, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
-                       uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, cudaStream_t st);
+                       uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, unsigned int* d_queue,
+                       cudaStream_t st);
 
 // Inverse avg(top,left) predictor as an anti-diagonal wavefront; one CTA per spatial unit.
 void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,

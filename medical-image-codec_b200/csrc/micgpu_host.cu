@@ -55,7 +55,7 @@ struct micgpu_decoder {
   unsigned long long k1_stride = 0;
   bool committed = false;
   int launches = 0;
-  DevBuf d_units, d_list, d_tabA, d_tabS, d_states, d_D, d_M, d_k1, d_comp, d_out;
+  DevBuf d_units, d_list, d_tabA, d_tabS, d_states, d_D, d_M, d_k1, d_comp, d_out, d_queue;
   DevBuf d_jobs, d_bytes;   // MIC3: fill / blit job tables, byte-typed pixel output
   DevBuf d_wA, d_wB, d_wflags;   // WaveletV2: int32 ping-pong planes, escape flags
   MicUnit* h_units = nullptr;   // pinned staging copy
@@ -70,7 +70,7 @@ struct micgpu_decoder {
   ~micgpu_decoder() {
     cudaSetDevice(device);
     d_units.release(); d_list.release(); d_tabA.release(); d_tabS.release(); d_states.release();
-    d_D.release(); d_M.release(); d_k1.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
+    d_D.release(); d_M.release(); d_k1.release(); d_queue.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
     for (auto e : ev) cudaEventDestroy(e);
@@ -193,6 +193,7 @@ int plan_commit(micgpu_decoder* d) {
   if ((rc = d->d_D.ensure((d->d_total + 64) * sizeof(uint16_t)))) return rc;
   if ((rc = d->d_M.ensure((d->m_total + 64) * sizeof(uint32_t)))) return rc;
   if ((rc = d->d_k1.ensure((size_t)d->k1_grid * d->k1_stride))) return rc;
+  if ((rc = d->d_queue.ensure(256))) return rc;
   if (nu > d->h_units_cap) {
     if (d->h_units) cudaFreeHost(d->h_units);
     d->h_units = nullptr;
@@ -258,7 +259,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   }
   prof_mark(d, "k_rle_expand", st);
   launch_rle_expand(du, nu, (const uint16_t*)d->d_states.p, (const uint16_t*)d->d_tabS.p, (uint16_t*)d->d_D.p,
-                    (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(nu, d->sm_count * 8), st);
+                    (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(nu, d->sm_count * 8), (unsigned int*)d->d_queue.p, st);
   d->launches++;
   if (!d->spatial.empty()) {
     prof_mark(d, "k_delta_wavefront", st);

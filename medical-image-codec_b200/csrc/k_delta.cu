@@ -17,6 +17,8 @@
 // The 8 pixels of a block are unrolled with compile-time register selection: ~11
 // instructions per pixel per warp step versus ~130 for a one-pixel-per-step wavefront
 // (measured, profiles/), at the price of a longer pipeline fill (8 columns of skew per row).
+#include <cstdlib>
+
 #include "mic_device.cuh"
 
 namespace micgpu {
@@ -49,10 +51,12 @@ __device__ __forceinline__ uint32_t grp_get(const Grp& g) {
 }
 
 constexpr int K4_LAG = 2;
-constexpr int K4_RING = 8;    // per-lane cp.async ring depth (blocks of 16 B) for the residual plane
+constexpr int K4_RING_DEFAULT = 8;    // per-lane cp.async ring depth (blocks of 16 B) for the residual plane
+constexpr int K4_MRING = 4;           // literal-mask words (4 blocks each) kept in flight per lane
 
 __device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
+template <int K4_RING>
 __global__ void __launch_bounds__(1024)
 k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist,
                   const uint16_t* __restrict__ D, const uint32_t* __restrict__ M, uint16_t* __restrict__ out,
@@ -152,10 +156,18 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
     // 256 coupled rows of a unit advance at the pace of the slowest lane, so DRAM tail latency must be
     // hidden far deeper than two register-prefetched blocks can (measured: 4.7k cycles per step before).
     uint4* dring = reinterpret_cast<uint4*>(s_brow + (size_t)(nwarps + 1) * brow_pitch) + nwarps * 64 + warp * (K4_RING * 32);
+    // The literal mask travels the same way: word q of the row (blocks 4q..4q+3) is copied when block 4q is staged.
+    // (It used to be a register load two words ahead; with 256 lock-stepped rows that exposed DRAM latency, 20 % of
+    // the kernel's stall samples.)
+    uint32_t* mring = reinterpret_cast<uint32_t*>(dring - warp * (K4_RING * 32) + nwarps * (K4_RING * 32)) + warp * (K4_MRING * 32);
     auto stage = [&](int pb) {
       if (pb >= 0 && pb < nblk) {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(dring + (pb & (K4_RING - 1)) * 32 + lane);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Drow + 8 * pb));
+        if ((pb & 3) == 0) {
+          const unsigned mdst = (unsigned)__cvta_generic_to_shared(mring + ((pb >> 2) & (K4_MRING - 1)) * 32 + lane);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(mdst), "l"(Mrow + (pb >> 2)));
+        }
       }
       asm volatile("cp.async.commit_group;");
     };
@@ -163,8 +175,6 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
     for (int q = 0; q < K4_RING - 1; q++) stage(-s + q);
 
     Grp tp = {{0, 0, 0, 0}}, g = {{0, 0, 0, 0}};
-    unsigned mw = nblk > 0 ? __ldg(Mrow) : 0u;          // literal bits of blocks 4q..4q+3
-    unsigned mwn = nblk > 4 ? __ldg(Mrow + 1) : 0u;
     unsigned left = 0;
     int b = -s;
     int seen = 0;                                       // lane 0: producer progress seen so far
@@ -199,11 +209,7 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
       if (b >= 0 && b < nblk) {
         const Grp tw = rephase(tp, rc, delta);
         const uint4 dv = dring[(b & (K4_RING - 1)) * 32 + lane];
-        const unsigned mbyte = (mw >> ((b & 3) * 8)) & 0xFFu;
-        if ((b & 3) == 3) {
-          mw = mwn;
-          if (b + 5 < nblk) mwn = __ldg(Mrow + ((b + 5) >> 2));
-        }
+        const unsigned mbyte = (mring[((b >> 2) & (K4_MRING - 1)) * 32 + lane] >> ((b & 3) * 8)) & 0xFFu;
         Grp dg;
         dg.w[0] = dv.x; dg.w[1] = dv.y; dg.w[2] = dv.z; dg.w[3] = dv.w;
         const int x0 = 8 * b - a;
@@ -255,13 +261,19 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
   }
 }
 
+static int k4_ring() {
+  static const int v = [] { const char* e = getenv("MICGPU_K4_RING"); return e && atoi(e) == 4 ? 4 : K4_RING_DEFAULT; }();
+  return v;
+}
+static size_t k4_warp_bytes() { return 1024 + (size_t)k4_ring() * 512 + K4_MRING * 128; }
+
 int delta_wavefront_threads(int max_width, int max_height) {
   int threads = (max_height - 1 + 31) / 32 * 32;   // row 0 is handled by the prologue scan
   if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
   const int pitch = (max_width + 16 + 7) / 8 * 8;
   // keep (nwarps+1) boundary rows within ~200 KB of shared memory
-  while (threads > 32 && (size_t)(threads / 32 + 1) * pitch * sizeof(uint16_t) + (size_t)(threads / 32) * (1024 + K4_RING * 512) > 200u * 1024u) threads -= 32;
+  while (threads > 32 && (size_t)(threads / 32 + 1) * pitch * sizeof(uint16_t) + (size_t)(threads / 32) * k4_warp_bytes() > 200u * 1024u) threads -= 32;
   return threads;
 }
 
@@ -271,9 +283,14 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
   const int threads = delta_wavefront_threads(max_width, max_height);
   const int nwarps = threads / 32;
   const int pitch = (max_width + 16 + 7) / 8 * 8;
-  const size_t smem = (size_t)(nwarps + 1) * pitch * sizeof(uint16_t) + (size_t)nwarps * (1024 + K4_RING * 512);
-  cudaFuncSetAttribute(k_delta_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_delta_wavefront<<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);
+  const size_t smem = (size_t)(nwarps + 1) * pitch * sizeof(uint16_t) + (size_t)nwarps * k4_warp_bytes();
+  if (k4_ring() == 4) {
+    cudaFuncSetAttribute(k_delta_wavefront<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_delta_wavefront<4><<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);
+  } else {
+    cudaFuncSetAttribute(k_delta_wavefront<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_delta_wavefront<8><<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);
+  }
 }
 
 }  // namespace micgpu

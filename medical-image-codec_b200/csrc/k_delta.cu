@@ -13,7 +13,9 @@
 //   * rows are addressed in "padded" coordinates p = a_y + x with a_y the 8-pixel phase of
 //     the OUTPUT row address, so every block is one aligned 16 B load of the residual plane D
 //     (K3 writes D with the same phase) and one aligned 16 B store of pixels;
-//   * warps chain through one shared-memory boundary row each, gated by a block counter.
+//   * warps chain through a K4_NB-block shared-memory ring each, handed over with full/empty mbarriers: the consumer
+//     sleeps in mbarrier.try_wait instead of polling a counter (the polling loop was 29 % of all issued instructions
+//     and the per-warp boundary rows kept residency at two CTAs per SM, profiles/README.md).
 // The 8 pixels of a block are unrolled with compile-time register selection: ~11
 // instructions per pixel per warp step versus ~130 for a one-pixel-per-step wavefront
 // (measured, profiles/), at the price of a longer pipeline fill (8 columns of skew per row).
@@ -50,19 +52,39 @@ __device__ __forceinline__ uint32_t grp_get(const Grp& g) {
   return (J & 1) ? (g.w[J >> 1] >> 16) : (g.w[J >> 1] & 0xFFFFu);
 }
 
-constexpr int K4_LAG = 2;
-constexpr int K4_RING_DEFAULT = 8;    // per-lane cp.async ring depth (blocks of 16 B) for the residual plane
+constexpr int K4_NB = 8;      // blocks in a warp-to-warp boundary ring
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint32_t bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// blocks (suspended by the hardware, not spinning on issue slots) until the phase of the given parity completed
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "MBW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"   // suspend-time hint: wake on completion
+      "@!p bra MBW_%=;\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+constexpr int K4_RING_DEFAULT = 4;    // per-lane cp.async ring depth (blocks of 16 B) for the residual plane
 constexpr int K4_MRING = 4;           // literal-mask words (4 blocks each) kept in flight per lane
 
-__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 template <int K4_RING>
 __global__ void __launch_bounds__(1024)
 k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist,
                   const uint16_t* __restrict__ D, const uint32_t* __restrict__ M, uint16_t* __restrict__ out,
                   int brow_pitch) {
-  extern __shared__ __align__(16) uint16_t s_brow[];  // (nwarps+1) boundary rows, padded coordinates, then the exchange slots
-  __shared__ int s_prog[33];                          // s_prog[w+1]: blocks finished by warp w's last lane
+  // dynamic shared memory: row_in | row_out (full rows, padded coordinates) | boundary rings | exchange slots |
+  // residual ring | mask ring | mbarriers
+  extern __shared__ __align__(16) uint16_t s_brow[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -109,15 +131,25 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
     }
   }
 
+  uint4* bring_all = reinterpret_cast<uint4*>(s_brow + 2 * (size_t)brow_pitch);        // nwarps rings of K4_NB blocks
+  uint4* xch_all = bring_all + nwarps * K4_NB;
+  uint4* dring_all = xch_all + nwarps * 64;
+  uint32_t* mring_all = reinterpret_cast<uint32_t*>(dring_all + nwarps * (K4_RING * 32));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mring_all + nwarps * (K4_MRING * 32));   // [warp][full K4_NB | empty K4_NB]
+  const uint32_t bars_sa = (uint32_t)__cvta_generic_to_shared(bars);
+
   const int rows_per_pass = (int)blockDim.x;
   const int passes = (H - 1 + rows_per_pass - 1) / rows_per_pass;
   for (int p = 0; p < passes; p++) {
     const int y = 1 + p * rows_per_pass + tid;
     const int wy0 = 1 + p * rows_per_pass + warp * 32;   // first row of this warp
     __syncthreads();
-    if (p > 0)
-      for (int i = tid; i < brow_pitch; i += blockDim.x) s_brow[i] = s_brow[(size_t)nwarps * brow_pitch + i];
-    if (tid <= nwarps) s_prog[tid] = tid == 0 ? 0x7fffffff : 0;
+    if (p > 0) {
+      for (int i = tid; i < brow_pitch; i += blockDim.x) s_brow[i] = s_brow[(size_t)brow_pitch + i];
+      if (tid < nwarps * 2 * K4_NB) mbar_inval(bars_sa + 8u * tid);
+      __syncthreads();
+    }
+    if (tid < nwarps * 2 * K4_NB) mbar_init(bars_sa + 8u * tid, 1u);
     __syncthreads();
     if (wy0 >= H) continue;   // whole warp idle this pass (still reaches the barriers above)
 
@@ -135,10 +167,14 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
     }
     const int T = __reduce_max_sync(0xffffffffu, s + nblk);
 
-    const uint16_t* brow_in = s_brow + (size_t)warp * brow_pitch;
-    uint16_t* brow_out = s_brow + (size_t)(warp + 1) * brow_pitch;
-    const int* prog_in = &s_prog[warp];
-    int* prog_out = &s_prog[warp + 1];
+    // input of lane 0: warp 0 reads the full row (row 0 / last row of the previous pass), the others their ring
+    const uint16_t* row_in = s_brow;
+    uint16_t* row_out = s_brow + brow_pitch;
+    const uint4* ring_in = bring_all + warp * K4_NB;
+    const uint32_t full_in = bars_sa + (uint32_t)warp * (2 * K4_NB * 8), empty_in = full_in + K4_NB * 8;
+    const bool chained = warp + 1 < nwarps && wy0 + 32 < H;   // a warp below consumes this warp's last row
+    uint4* ring_out = bring_all + (warp + 1) * K4_NB;
+    const uint32_t full_out = bars_sa + (uint32_t)(warp + 1) * (2 * K4_NB * 8), empty_out = full_out + K4_NB * 8;
 
     const size_t yr = (size_t)(row_active ? y : 1);
     const uint16_t* Drow = Du + yr * wp;
@@ -148,18 +184,18 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
 
     // lane -> lane+1 hand-over of the finished block through shared memory (double buffered):
     // one 16 B store, one warp barrier and one 16 B load per step instead of four shuffles
-    uint4* xch = reinterpret_cast<uint4*>(s_brow + (size_t)(nwarps + 1) * brow_pitch) + warp * 64;
+    uint4* xch = xch_all + warp * 64;
     xch[lane] = make_uint4(0, 0, 0, 0);
     xch[32 + lane] = make_uint4(0, 0, 0, 0);
 
     // Residual blocks are staged K4_RING-1 steps ahead with cp.async (LDGSTS) into a per-lane ring: the
     // 256 coupled rows of a unit advance at the pace of the slowest lane, so DRAM tail latency must be
     // hidden far deeper than two register-prefetched blocks can (measured: 4.7k cycles per step before).
-    uint4* dring = reinterpret_cast<uint4*>(s_brow + (size_t)(nwarps + 1) * brow_pitch) + nwarps * 64 + warp * (K4_RING * 32);
+    uint4* dring = dring_all + warp * (K4_RING * 32);
     // The literal mask travels the same way: word q of the row (blocks 4q..4q+3) is copied when block 4q is staged.
     // (It used to be a register load two words ahead; with 256 lock-stepped rows that exposed DRAM latency, 20 % of
     // the kernel's stall samples.)
-    uint32_t* mring = reinterpret_cast<uint32_t*>(dring - warp * (K4_RING * 32) + nwarps * (K4_RING * 32)) + warp * (K4_MRING * 32);
+    uint32_t* mring = mring_all + warp * (K4_MRING * 32);
     auto stage = [&](int pb) {
       if (pb >= 0 && pb < nblk) {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(dring + (pb & (K4_RING - 1)) * 32 + lane);
@@ -177,7 +213,6 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
     Grp tp = {{0, 0, 0, 0}}, g = {{0, 0, 0, 0}};
     unsigned left = 0;
     int b = -s;
-    int seen = 0;                                       // lane 0: producer progress seen so far
     for (int t = 0; t < T; t++, b++) {
       __syncwarp();
       Grp rc;
@@ -188,20 +223,27 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
       if (lane == 0) {
         const int c = t + wrap;
         if (c < nblk_prev) {
-          if (seen <= c) {
-            // first wait: let the producer get K4_LAG blocks ahead so later steps find their block ready
-            const int need = min(c + (t == 0 ? K4_LAG : 1), nblk_prev);
-            while ((seen = ld_volatile_s32(prog_in)) < need) { }   // plain spin: __nanosleep quantises to ~1 us and throttles the whole chain
-            __threadfence_block();
-          }
-          const uint4 v = *reinterpret_cast<const uint4*>(brow_in + 8 * c);
-          rc.w[0] = v.x; rc.w[1] = v.y; rc.w[2] = v.z; rc.w[3] = v.w;
-          if (t == 0 && wrap) {
+          uint4 v;
+          if (warp == 0) {
+            v = *reinterpret_cast<const uint4*>(row_in + 8 * c);
             // lane 0 starts one block late relative to the row above when the phase wrapped: its first
             // window also needs block 0 of that row (the other lanes receive it during their start delay)
-            const uint4 v0 = *reinterpret_cast<const uint4*>(brow_in);
-            tp.w[0] = v0.x; tp.w[1] = v0.y; tp.w[2] = v0.z; tp.w[3] = v0.w;
+            if (t == 0 && wrap) {
+              const uint4 v0 = *reinterpret_cast<const uint4*>(row_in);
+              tp.w[0] = v0.x; tp.w[1] = v0.y; tp.w[2] = v0.z; tp.w[3] = v0.w;
+            }
+          } else {
+            const int slot = c & (K4_NB - 1);
+            mbar_wait(full_in + 8u * slot, (unsigned)(c / K4_NB) & 1u);   // blocks arrive in order: block c implies 0..c
+            v = ring_in[slot];
+            if (t == 0 && wrap) {
+              const uint4 v0 = ring_in[0];
+              tp.w[0] = v0.x; tp.w[1] = v0.y; tp.w[2] = v0.z; tp.w[3] = v0.w;
+              mbar_arrive(empty_in);
+            }
+            mbar_arrive(empty_in + 8u * slot);
           }
+          rc.w[0] = v.x; rc.w[1] = v.y; rc.w[2] = v.z; rc.w[3] = v.w;
         }
       }
       stage(b + K4_RING - 1);
@@ -250,9 +292,14 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
           g.w[2] = v[4] | (v[5] << 16); g.w[3] = v[6] | (v[7] << 16);
         }
         if (lane == 31) {
-          *reinterpret_cast<uint4*>(brow_out + 8 * b) = make_uint4(g.w[0], g.w[1], g.w[2], g.w[3]);
-          __threadfence_block();
-          *reinterpret_cast<volatile int*>(prog_out) = b + 1;
+          if (chained) {
+            const int slot = b & (K4_NB - 1);
+            mbar_wait(empty_out + 8u * slot, ((unsigned)(b / K4_NB) & 1u) ^ 1u);   // slot consumed K4_NB blocks ago
+            ring_out[slot] = make_uint4(g.w[0], g.w[1], g.w[2], g.w[3]);
+            mbar_arrive(full_out + 8u * slot);
+          } else {
+            *reinterpret_cast<uint4*>(row_out + 8 * b) = make_uint4(g.w[0], g.w[1], g.w[2], g.w[3]);
+          }
         }
       }
       xch[(t & 1) * 32 + lane] = make_uint4(g.w[0], g.w[1], g.w[2], g.w[3]);
@@ -262,10 +309,10 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
 }
 
 static int k4_ring() {
-  static const int v = [] { const char* e = getenv("MICGPU_K4_RING"); return e && atoi(e) == 4 ? 4 : K4_RING_DEFAULT; }();
+  static const int v = [] { const char* e = getenv("MICGPU_K4_RING"); return e && atoi(e) == 8 ? 8 : K4_RING_DEFAULT; }();
   return v;
 }
-static size_t k4_warp_bytes() { return 1024 + (size_t)k4_ring() * 512 + K4_MRING * 128; }
+static size_t k4_warp_bytes() { return K4_NB * 16 + 1024 + (size_t)k4_ring() * 512 + K4_MRING * 128 + 2 * K4_NB * 8; }
 
 int delta_wavefront_threads(int max_width, int max_height) {
   int threads = (max_height - 1 + 31) / 32 * 32;   // row 0 is handled by the prologue scan
@@ -273,7 +320,7 @@ int delta_wavefront_threads(int max_width, int max_height) {
   if (threads < 32) threads = 32;
   const int pitch = (max_width + 16 + 7) / 8 * 8;
   // keep (nwarps+1) boundary rows within ~200 KB of shared memory
-  while (threads > 32 && (size_t)(threads / 32 + 1) * pitch * sizeof(uint16_t) + (size_t)(threads / 32) * k4_warp_bytes() > 200u * 1024u) threads -= 32;
+  while (threads > 32 && 2 * (size_t)pitch * sizeof(uint16_t) + (size_t)(threads / 32) * k4_warp_bytes() > 200u * 1024u) threads -= 32;
   return threads;
 }
 
@@ -283,7 +330,7 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
   const int threads = delta_wavefront_threads(max_width, max_height);
   const int nwarps = threads / 32;
   const int pitch = (max_width + 16 + 7) / 8 * 8;
-  const size_t smem = (size_t)(nwarps + 1) * pitch * sizeof(uint16_t) + (size_t)nwarps * k4_warp_bytes();
+  const size_t smem = 2 * (size_t)pitch * sizeof(uint16_t) + (size_t)nwarps * k4_warp_bytes();
   if (k4_ring() == 4) {
     cudaFuncSetAttribute(k_delta_wavefront<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_delta_wavefront<4><<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);

@@ -15,7 +15,7 @@
 namespace micgpu {
 
 constexpr int K1_THREADS = 128;
-constexpr int K1_WIN = 16384;  // bytes of ncount header staged in shared memory
+constexpr int K1_WIN = 8192;   // bytes of ncount header staged in shared memory (8 KB keeps 16 CTAs per SM resident)
 
 struct BlockScan {
   // exclusive scan of one u32 per thread over K1_THREADS threads

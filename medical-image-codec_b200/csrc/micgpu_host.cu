@@ -176,8 +176,10 @@ int plan_commit(micgpu_decoder* d) {
   }
   // ---- K1 scratch ------------------------------------------------------------
   const unsigned long long per_cta = 18ull << d->max_log_all;
-  int g1 = std::min<int>((int)d->units.size(), d->sm_count * 8);
-  const unsigned long long k1_budget = 256ull << 20;
+  // one CTA per unit while they all fit in one wave (16 CTAs of 128 threads per SM): the serial ncount parse of a
+  // unit is ~0.6 ms on its own, so a second wave doubles the kernel
+  int g1 = std::min<int>((int)d->units.size(), d->sm_count * 16);
+  const unsigned long long k1_budget = 1024ull << 20;
   if ((unsigned long long)g1 * per_cta > k1_budget) g1 = (int)std::max<unsigned long long>(d->sm_count / 2, k1_budget / per_cta);
   g1 = std::max(1, std::min<int>(g1, (int)d->units.size()));
   d->k1_grid = g1;

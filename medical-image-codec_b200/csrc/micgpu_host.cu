@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -383,7 +384,7 @@ int add_mic2_locked(micgpu_decoder* d, const uint8_t* p, size_t len, uint64_t co
 // ---- default per-device contexts for the one-shot calls ---------------------
 std::mutex g_mu;
 micgpu_decoder* g_default[64] = {nullptr};
-constexpr int PIPE_DEPTH = 3;
+constexpr int PIPE_DEPTH = 6;
 std::mutex g_pipe_mu;
 micgpu_decoder* g_pipe[64][PIPE_DEPTH] = {};
 
@@ -582,11 +583,28 @@ struct PicsPending {
   int i0 = 0, i1 = 0;
   std::vector<int> first_unit, hdr_rc;
   bool active = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // MICGPU_TRACE: start, H2D done, kernels done, D2H done
+  double t_enq0 = 0, t_enq1 = 0;
 };
+
+bool trace_on() {
+  static const bool v = [] { const char* e = getenv("MICGPU_TRACE"); return e && e[0] == '1'; }();
+  return v;
+}
+double host_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+void trace_mark(PicsPending& P, int k, cudaStream_t st) {
+  if (!trace_on()) return;
+  if (!P.ev[k]) cudaEventCreate(&P.ev[k]);
+  cudaEventRecord(P.ev[k], st);
+}
 
 int pics_enqueue(micgpu_decoder* d, int i0, int i1, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
                  const size_t* caps, PicsPending& P) {
   const int n = i1 - i0;
+  P.t_enq0 = trace_on() ? host_ms() : 0;
   d->units.clear();
   d->temporal.clear();
   d->out_need = 0;
@@ -617,6 +635,7 @@ int pics_enqueue(micgpu_decoder* d, int i0, int i1, const uint8_t* const* blobs,
   if ((rc = d->d_out.ensure(std::max<uint64_t>(otot, 1) * sizeof(uint16_t)))) return rc;
   // copies are merged when neighbouring images are also neighbours in host memory (a caller that keeps a batch in one
   // buffer gets one H2D and one D2H per chunk instead of one per image)
+  trace_mark(P, 0, d->stream);
   for (int k = 0; k < n;) {
     if (P.hdr_rc[k]) { k++; continue; }
     int j = k;
@@ -625,7 +644,9 @@ int pics_enqueue(micgpu_decoder* d, int i0, int i1, const uint8_t* const* blobs,
     CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_comp.p + coff[k], blobs[i0 + k], bytes, cudaMemcpyHostToDevice, d->stream));
     k = j + 1;
   }
+  trace_mark(P, 1, d->stream);
   if ((rc = run_device_locked(d, d->d_comp.p, ctot, d->d_out.p, otot, d->stream))) return rc;
+  trace_mark(P, 2, d->stream);
   for (int k = 0; k < n;) {
     if (P.hdr_rc[k]) { k++; continue; }
     int j = k;
@@ -635,6 +656,8 @@ int pics_enqueue(micgpu_decoder* d, int i0, int i1, const uint8_t* const* blobs,
   }
   if (!d->units.empty())
     CUDA_TRY(cudaMemcpyAsync(d->h_units, d->d_units.p, d->units.size() * sizeof(MicUnit), cudaMemcpyDeviceToHost, d->stream));
+  trace_mark(P, 3, d->stream);
+  P.t_enq1 = trace_on() ? host_ms() : 0;
   P.active = true;
   return 0;
 }
@@ -644,7 +667,16 @@ int pics_finish(micgpu_decoder* d, PicsPending& P, int* status, int* first) {
   if (!P.active) return 0;
   P.active = false;
   CUDA_TRY(cudaSetDevice(d->device));
+  const double t_w0 = trace_on() ? host_ms() : 0;
   CUDA_TRY(cudaStreamSynchronize(d->stream));
+  if (trace_on() && P.ev[0]) {
+    float h2d = 0, ker = 0, d2h = 0;
+    cudaEventElapsedTime(&h2d, P.ev[0], P.ev[1]);
+    cudaEventElapsedTime(&ker, P.ev[1], P.ev[2]);
+    cudaEventElapsedTime(&d2h, P.ev[2], P.ev[3]);
+    fprintf(stderr, "[micgpu trace] images %d-%d: host enqueue %.2f ms (at %.2f), device h2d %.2f kernels %.2f d2h %.2f ms, host waited %.2f ms (until %.2f)\n",
+            P.i0, P.i1, P.t_enq1 - P.t_enq0, P.t_enq0, h2d, ker, d2h, host_ms() - t_w0, host_ms());
+  }
   const int n = P.i1 - P.i0;
   for (int k = 0; k < n; k++) {
     int st = P.hdr_rc[k];
@@ -682,13 +714,16 @@ int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_
     if ((rc = pics_finish(d, P, status, &first))) return rc;
     return first;
   }
-  // pipelined: ~8 chunks over PIPE_DEPTH decoder contexts (each with its own stream and scratch)
-  const int chunk = std::max(4, (n + 7) / 8);
+  // Pipelined: ~16 chunks over PIPE_DEPTH decoder contexts (each with its own stream and scratch).  The ANS stage of a
+  // chunk takes the same ~7.6 ms whether it holds 100 or 2000 strips (it is bound by the serial chain of one strip), and
+  // a chunk's D2H copy is shorter than that, so several chunks must be computing at once to keep the PCIe link busy.
+  const int chunk = std::max(4, (n + 15) / 16);
   micgpu_decoder* D[PIPE_DEPTH];
   PicsPending P[PIPE_DEPTH];
   for (int k = 0; k < PIPE_DEPTH; k++)
     if (!(D[k] = pipe_decoder(dev, k))) return MICGPU_E_CUDA;
-  std::unique_lock<std::mutex> l0(D[0]->mu), l1(D[1]->mu), l2(D[2]->mu);
+  std::unique_lock<std::mutex> locks[PIPE_DEPTH];
+  for (int k = 0; k < PIPE_DEPTH; k++) locks[k] = std::unique_lock<std::mutex>(D[k]->mu);
   int c = 0;
   for (int i0 = 0; i0 < n; i0 += chunk, c++) {
     const int k = c % PIPE_DEPTH;

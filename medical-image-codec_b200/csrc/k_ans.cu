@@ -343,15 +343,16 @@ __device__ __forceinline__ uint32_t packed_prefix(uint32_t nb, uint8_t* my_byte,
 // copied: only an over-reading (corrupt) stream looks there; it reads stale ring bytes and is rejected by P < shift.
 template <int N>
 __device__ __forceinline__ void ring_refill_async(int P, int& cross, uint32_t& ra, uint32_t& qo, int& hidx, const uint8_t*& srcp,
-                                                  uint32_t rk, uint32_t ringsa, int pf_min) {
+                                                  uint32_t rk, uint32_t mir, int pf_min) {
   constexpr int CP = 32 / N;   // bytes of a quarter each lane copies
   asm volatile(
       "{\n\t.reg .pred p, q, pl, pp;\n\t"
       "setp.le.s32 p, %5, %0;\n\t"
       "setp.ge.and.s32 pl, %3, 0, p;\n\t"
-      "setp.eq.and.u32 q, %1, %7, pl;\n\t"            // slot 0, lane k == 0: ring word 0 is mirrored at word 32
+      "setp.eq.and.u32 q, %2, 0, pl;\n\t"            // slot 0: ring words 0..3 are mirrored at words 32..35
+      "setp.ne.and.u32 q, %7, 0, q;\n\t"
       "@pl cp.async.ca.shared.global [%1], [%4], %9;\n\t"
-      "@q cp.async.ca.shared.global [%7+128], [%4], 4;\n\t"
+      "@q cp.async.ca.shared.global [%1+128], [%4], %9;\n\t"
       "cp.async.commit_group;\n\t"
       "cp.async.wait_group 2;\n\t"
       "setp.ge.and.s32 pp, %3, %8, p;\n\t"
@@ -364,14 +365,14 @@ __device__ __forceinline__ void ring_refill_async(int P, int& cross, uint32_t& r
       "add.s32 %1, %6, %2;\n\t"
       "}\n"
       : "+r"(cross), "+r"(ra), "+r"(qo), "+r"(hidx), "+l"(srcp)
-      : "r"(P), "r"(rk), "r"(ringsa), "r"(pf_min), "n"(CP)
+      : "r"(P), "r"(rk), "r"(mir), "r"(pf_min), "n"(CP)
       : "memory");
 }
 
 template <int N, int MODE>
 __global__ void __launch_bounds__(1024)
 k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
-                    const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots) {
+                    const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots, int use_window) {
   static_assert(N == 2 || N == 4 || N == 8, "packed decode is for the interleaved coders");
   static_assert(MODE == 0 || MODE == 1, "packed decode keeps its tables in shared memory");
   extern __shared__ __align__(16) uint8_t smem[];
@@ -397,6 +398,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
   const uint32_t ringsa = (uint32_t)__cvta_generic_to_shared(ring);
   const uint32_t rk = ringsa + (uint32_t)(k * CP);
   const int pf_min = k == 0 ? 8 : 0x7fffffff;    // lane 0 of a unit prefetches 8 quarters (256 B) ahead into L2
+  const uint32_t mir = k * CP < 16 ? 1u : 0u;    // this lane's bytes of quarter 0 belong to ring words 0..3 (mirrored)
   if (threadIdx.x == 0) *idle = MODE == 0 ? 0u : 32u;
   __syncthreads();
 
@@ -443,8 +445,8 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
           const uint32_t dst = rk + (uint32_t)((q & 3) << 5);
           const uint8_t* src = wbase + (size_t)q * 32 + k * CP;
           asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(CP) : "memory");
-          if (k == 0 && (q & 3) == 0)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ringsa + 128u), "l"(src) : "memory");
+          if (mir && (q & 3) == 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + 128u), "l"(src), "n"(CP) : "memory");
         }
       }
       hidx = qtop - 4;
@@ -476,7 +478,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     __syncwarp();
     // Per-unit ring maintenance; P and cross are uniform over a unit's lanes.
     auto refill = [&]() {
-      ring_refill_async<N>(P, cross, ra, qo, hidx, srcp, rk, ringsa, pf_min);
+      ring_refill_async<N>(P, cross, ra, qo, hidx, srcp, rk, mir, pf_min);
       __syncwarp();
     };
 
@@ -524,13 +526,51 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
       }
       P -= (int)tot;
     };
+    // Hot loop: the five ring words that can hold this round's fields ([P - 128, P) plus word alignment) are loaded
+    // into registers as soon as P is known, i.e. before the table lookup of the round, so the bit extraction after
+    // the prefix exchange is a register select + funnel shift instead of an address computation and a shared-memory
+    // load on the state -> state chain (-24 cycles per round, tools/ubench_lat.cu).
+    uint32_t W0 = 0, W1 = 0, W2 = 0, W3 = 0, W4 = 0, Pb = 0;
+    auto load_window = [&]() {
+      const uint32_t wl = (((uint32_t)(P - 1)) >> 5) - 4u;     // lowest word of the window
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + ((wl & 31u) << 2));
+      W0 = w[0]; W1 = w[1]; W2 = w[2]; W3 = w[3]; W4 = w[4];    // words 32..35 mirror 0..3: no wrap inside the window
+      Pb = (uint32_t)P - (wl << 5);                            // P relative to the window, in (128, 160]
+    };
+    auto round_win = [&](int buf, int oidx) {
+      uint32_t nb, ns;
+      if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
+      else { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }   // nx >= 1 (K1)
+      uint32_t tot;
+      const uint32_t before = packed_prefix<N>(nb, xmine + buf * 32, xunit + buf * 32, bm, &tot);
+      const uint32_t rel = Pb - before - nb;                   // bit offset of the field inside the window
+      const bool j0 = rel & 32u, j1 = rel & 64u, j2 = rel & 128u;
+      const uint32_t a0 = j0 ? W1 : W0, a1 = j0 ? W3 : W2, b0 = j0 ? W2 : W1, b1 = j0 ? W4 : W3;
+      const uint32_t a = j1 ? a1 : a0, hi = j1 ? b1 : b0;
+      const uint32_t lw = j2 ? W4 : a;                         // word 4 holds its field entirely: hi is irrelevant there
+      const uint32_t bits = __funnelshift_r(lw, hi, rel) & ((1u << nb) - 1u);
+      if (live) op[oidx * N] = (uint16_t)state;
+      state = ns + bits;
+      P -= (int)tot;
+    };
     // ring check once per two rounds (two rounds consume at most 2*N*16 = 256 bits = one quarter)
     uint32_t r = 0;
-    for (; r + 2 <= minfull; r += 2) {
-      round(std::true_type{}, true, 0, 0);
-      round(std::true_type{}, true, 1, 1);
-      op += 2 * N;
-      refill();
+    if (use_window) {
+      for (; r + 2 <= minfull; r += 2) {
+        load_window();          // after the ring check of the previous iteration (its copies are then guaranteed)
+        round_win(0, 0);
+        load_window();
+        round_win(1, 1);
+        op += 2 * N;
+        refill();
+      }
+    } else {
+      for (; r + 2 <= minfull; r += 2) {
+        round(std::true_type{}, true, 0, 0);
+        round(std::true_type{}, true, 1, 1);
+        op += 2 * N;
+        refill();
+      }
     }
     if (live && P < (int)shift) full = 0;
     for (; r + 2 <= maxfull; r += 2) {
@@ -590,7 +630,8 @@ static void launch_packed(MicUnit* d_units, const int* d_list, int nlist, const 
   const int warps = (slots + UPW - 1) / UPW;
   size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
   cudaFuncSetAttribute(k_ans_decode_packed<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_ans_decode_packed<N, MODE><<<grid, 32 * warps, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
+  static const int win = [] { const char* e = getenv("MICGPU_K2_WINDOW"); return e ? atoi(e) : 1; }();
+  k_ans_decode_packed<N, MODE><<<grid, 32 * warps, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, win);
 }
 
 static bool use_packed() {

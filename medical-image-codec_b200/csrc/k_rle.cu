@@ -216,32 +216,35 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       const int ph = spatial ? (int)((pix + align0 + 8u - (unsigned)skip) & 7u) : 0;
       uint16_t* se = s_e_raw + ph;
       {
+        // one warp per run: the per-run set-up is paid once instead of by all eight warps (the kernel is issue bound;
+        // with ~6 runs per chunk the set-up was 30 % of all instructions), the copy itself is the same work either way
         const int nr = ws.nruns;
-        for (int r = 0; r < nr; r++) {
+        uint32_t* dw = reinterpret_cast<uint32_t*>(s_e_raw);
+        for (int r = warp; r < nr; r += K3_WARPS) {
           const int o = s_run_o[r], n = s_run_n[r], src = s_run_src[r];
           // 32-bit destination words; the odd head / tail elements go scalar
           const int d0 = ph + o, d1 = d0 + n;            // element range in s_e_raw
           const int w0 = (d0 + 1) >> 1, w1 = d1 >> 1;    // full words [w0, w1)
-          uint32_t* dw = reinterpret_cast<uint32_t*>(s_e_raw);
           if (src >= 0) {
             const int sh = src - d0;                      // source index = destination index + sh
-            if (tid == 0 && (d0 & 1) && n > 0) s_e_raw[d0] = s_in[d0 + sh];
-            if (tid == 1 && (d1 & 1) && d1 - 1 >= w0 * 2 && n > 0) s_e_raw[d1 - 1] = s_in[d1 - 1 + sh];
+            if (lane == 0 && (d0 & 1) && n > 0) s_e_raw[d0] = s_in[d0 + sh];
+            if (lane == 1 && (d1 & 1) && d1 - 1 >= w0 * 2 && n > 0) s_e_raw[d1 - 1] = s_in[d1 - 1 + sh];
             if ((sh & 1) == 0) {
               const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_in) + (sh >> 1);
-#pragma unroll 2
-              for (int w = w0 + tid; w < w1; w += K3_THREADS) dw[w] = sw[w];
+#pragma unroll 4
+              for (int w = w0 + lane; w < w1; w += 32) dw[w] = sw[w];
             } else {
-#pragma unroll 2
-              for (int w = w0 + tid; w < w1; w += K3_THREADS)
+#pragma unroll 4
+              for (int w = w0 + lane; w < w1; w += 32)
                 dw[w] = (uint32_t)s_in[2 * w + sh] | ((uint32_t)s_in[2 * w + 1 + sh] << 16);
             }
           } else {
             const uint32_t v16 = (uint32_t)(-(src + 1)) & 0xFFFFu;
-            if (tid == 0 && (d0 & 1) && n > 0) s_e_raw[d0] = (uint16_t)v16;
-            if (tid == 1 && (d1 & 1) && d1 - 1 >= w0 * 2 && n > 0) s_e_raw[d1 - 1] = (uint16_t)v16;
+            if (lane == 0 && (d0 & 1) && n > 0) s_e_raw[d0] = (uint16_t)v16;
+            if (lane == 1 && (d1 & 1) && d1 - 1 >= w0 * 2 && n > 0) s_e_raw[d1 - 1] = (uint16_t)v16;
             const uint32_t v32 = v16 | (v16 << 16);
-            for (int w = w0 + tid; w < w1; w += K3_THREADS) dw[w] = v32;
+#pragma unroll 4
+            for (int w = w0 + lane; w < w1; w += 32) dw[w] = v32;
           }
         }
       }

@@ -50,7 +50,7 @@ struct WalkState {
 __global__ void __launch_bounds__(K3_THREADS, 5)
 k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict__ states,
              const uint16_t* __restrict__ tabS, uint16_t* __restrict__ D, uint32_t* __restrict__ M,
-             uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue) {
+             uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue, int ubase) {
   __shared__ __align__(16) uint16_t s_in[IN_N];
   __shared__ __align__(16) uint16_t s_e_raw[OUT_CH + 16];
   __shared__ __align__(16) uint16_t s_p[OUT_CH];
@@ -70,7 +70,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     __syncthreads();
     const int ui = s_ui;
     if (ui >= nunits) break;
-    MicUnit* U = &units[ui];
+    MicUnit* U = &units[ubase + ui];
     if (U->status != MIC_OK) continue;
     const int nsym = (int)U->nsym;
     const uint16_t* st = states + U->sym_off;
@@ -482,7 +482,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
   }
 }
 
-void launch_rle_expand(MicUnit* d_units, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
+void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
                        uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, unsigned int* d_queue,
                        cudaStream_t st) {
   if (nunits <= 0) return;
@@ -491,7 +491,7 @@ void launch_rle_expand(MicUnit* d_units, int nunits, const uint16_t* d_states, c
   const int tab_log = max_log <= 14 ? max_log : 14;
   const size_t smem = (size_t)2 << tab_log;
   cudaFuncSetAttribute(k_rle_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_rle_expand<<<grid, K3_THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue);
+  k_rle_expand<<<grid, K3_THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue, ubase);
 }
 
 }  // namespace micgpu

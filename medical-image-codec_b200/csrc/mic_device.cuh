@@ -24,7 +24,8 @@ size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta);
 // RLE expand (+ escape split for spatial units).  Spatial units produce the
 // residual plane D (pitch wp) and the literal bit mask M; RLE units write
 // their expanded stream straight to d_out.
-void launch_rle_expand(MicUnit* d_units, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
+// Units [ubase, ubase + nunits) are handed to the CTAs through the atomic counter *d_queue (reset by the launcher).
+void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
                        uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, unsigned int* d_queue,
                        cudaStream_t st);
 

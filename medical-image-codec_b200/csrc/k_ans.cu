@@ -297,14 +297,14 @@ k_ans_decode(MicUnit* __restrict__ units, const int* __restrict__ list, int nlis
 // instructions for any number of units per warp.
 template <int N>
 struct ByteMasks {
-  uint32_t lo, hi;      // bytes of lanes j < k in the unit's low / high word
+  uint32_t lo, hi;      // 0x01 in the bytes of lanes j < k of the unit's low / high word (dp4a multipliers)
   __device__ explicit ByteMasks(int k) {
     lo = 0; hi = 0;
 #pragma unroll
     for (int f = 0; f < 8; f++) {
       if (f < k && f < N) {
-        if (f < 4) lo |= 0xFFu << (8 * f);
-        else hi |= 0xFFu << (8 * (f - 4));
+        if (f < 4) lo |= 0x01u << (8 * f);
+        else hi |= 0x01u << (8 * (f - 4));
       }
     }
   }
@@ -319,15 +319,15 @@ __device__ __forceinline__ uint32_t packed_prefix(uint32_t nb, uint8_t* my_byte,
   if (N == 8) {
     const uint2 v = *reinterpret_cast<const uint2*>(unit_bytes);
     *tot = __dp4a(v.x, ONES, __dp4a(v.y, ONES, 0u));
-    return __dp4a(v.x & bm.lo, ONES, __dp4a(v.y & bm.hi, ONES, 0u));
+    return __dp4a(v.x, bm.lo, __dp4a(v.y, bm.hi, 0u));   // the per-lane multiplier selects the lanes below this one
   } else if (N == 4) {
     const uint32_t v = *reinterpret_cast<const uint32_t*>(unit_bytes);
     *tot = __dp4a(v, ONES, 0u);
-    return __dp4a(v & bm.lo, ONES, 0u);
+    return __dp4a(v, bm.lo, 0u);
   } else {
     const uint32_t v = *reinterpret_cast<const uint16_t*>(unit_bytes);
     *tot = (v & 0xFFu) + (v >> 8);
-    return v & bm.lo;
+    return (v & 0xFFu) * bm.lo;
   }
 }
 

@@ -758,6 +758,8 @@ int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_
   // Pipelined: ~16 chunks over PIPE_DEPTH decoder contexts (each with its own stream and scratch).  The ANS stage of a
   // chunk takes the same ~7.6 ms whether it holds 100 or 2000 strips (it is bound by the serial chain of one strip), and
   // a chunk's D2H copy is shorter than that, so several chunks must be computing at once to keep the PCIe link busy.
+  // The first chunks are small and grow geometrically: the first D2H copy cannot start before one ANS pass (~8 ms)
+  // has finished, whatever the chunk holds, so a small head chunk gets the PCIe link busy ~6 ms earlier.
   const int chunk = std::max(4, (n + 15) / 16);
   micgpu_decoder* D[PIPE_DEPTH];
   PicsPending P[PIPE_DEPTH];
@@ -765,11 +767,14 @@ int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_
     if (!(D[k] = pipe_decoder(dev, k))) return MICGPU_E_CUDA;
   std::unique_lock<std::mutex> locks[PIPE_DEPTH];
   for (int k = 0; k < PIPE_DEPTH; k++) locks[k] = std::unique_lock<std::mutex>(D[k]->mu);
-  int c = 0;
-  for (int i0 = 0; i0 < n; i0 += chunk, c++) {
+  int c = 0, size = std::max(2, chunk / 4);
+  for (int i0 = 0; i0 < n; c++) {
     const int k = c % PIPE_DEPTH;
+    const int i1 = std::min(n, i0 + size);
     if ((rc = pics_finish(D[k], P[k], status, &first))) return rc;
-    if ((rc = pics_enqueue(D[k], i0, std::min(n, i0 + chunk), blobs, lens, outs, caps, P[k]))) return rc;
+    if ((rc = pics_enqueue(D[k], i0, i1, blobs, lens, outs, caps, P[k]))) return rc;
+    i0 = i1;
+    size = std::min(chunk, size * 2);
   }
   for (int k = 0; k < PIPE_DEPTH; k++)
     if ((rc = pics_finish(D[k], P[k], status, &first))) return rc;

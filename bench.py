@@ -354,6 +354,8 @@ def run_ours(args, rank, local_rank, world):
             "pipeline_achieved": round(alg_bytes / (ms_dev * 1e-3) / 1e9, 2),
             "pipeline_frac": round(alg_bytes / (ms_dev * 1e-3) / 1e9 / peak, 4),
             "stages_ms": {k: round(v, 4) for k, v in acc.items()},
+            "stages_note": "per-kernel CUDA-event times of a separate profiling pass that runs the kernels back to back on one "
+                           "stream; the timed step overlaps the K3/K4 launches of four unit ranges on their own streams",
         }
         cpu = None if args.quick else cpu_baseline_sample(args, nst)
         line = {

@@ -210,7 +210,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": round(gbs, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -374,7 +374,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -429,7 +429,29 @@ def cpu_baseline_sample(args, nst):
             "single_thread_GBps": round(raw_per / st / 1e9, 4)}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner there) get stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -179,3 +179,46 @@ def test_corrupt_streams_report_errors(mic, oracle, synth):
         mic.DecompressSingleFrame(trunc + b"\x00", w, h)       # zero last byte: bitreader.go:33-36
     with pytest.raises(mic.MicGpuError):
         mic.DecompressParallelStrips(b"PICX" + bytes(40))
+
+
+def test_packed_warp_mixed_units_and_statuses(mic, oracle, synth):
+    """Units of different length, state count and health share the lanes of one ANS warp (32/N units per warp):
+    healthy images must decode exactly and every damaged one must report its own status (parallelstrips.go:324-328)."""
+    import ctypes as C
+
+    shapes = [(97, 33), (300, 200), (64, 64), (211, 160), (1000, 37), (128, 128), (257, 129), (40, 300)]
+    imgs, blobs, dims = [], [], []
+    for i in range(24):
+        w, h = shapes[i % len(shapes)]
+        im = synth.xr_image(500 + i, w, h).ravel()
+        imgs.append(im); dims.append((w, h))
+        blobs.append(bytearray(oracle.pics_compress(im, w, h, int(im.max()), (1, 2, 4, 3)[i % 4], 8 if i % 3 else 4)))
+    damaged = {5: "truncate", 11: "flip", 18: "count"}
+    for i, how in damaged.items():
+        b = blobs[i]
+        ns = int.from_bytes(b[12:16], "little")
+        hdr = 20 + 8 * ns
+        off0, len0 = int.from_bytes(b[20:24], "little"), int.from_bytes(b[24:28], "little")
+        f0 = hdr + off0
+        if how == "truncate":       # strip 0 loses the tail of its bitstream (length field kept consistent, last byte non-zero)
+            b[24:28] = (len0 // 2).to_bytes(4, "little")
+            b[f0 + len0 // 2 - 1] |= 1
+        elif how == "flip":         # bits flipped inside the ncount header / first payload bytes
+            for k in range(8, 24):
+                b[f0 + k] ^= 0x5A
+        else:                       # symbol count of the frame prefix raised: the decoder must stop at the end of the stream
+            c = int.from_bytes(b[f0 + 2:f0 + 6], "little")
+            b[f0 + 2:f0 + 6] = (c + 4096).to_bytes(4, "little")
+    n = len(blobs)
+    views = [np.frombuffer(bytes(b), np.uint8) for b in blobs]
+    outs = [np.zeros(w * h, np.uint16) for (w, h) in dims]
+    bp = (C.c_void_p * n)(*[v.ctypes.data for v in views]); ln = (C.c_size_t * n)(*[v.size for v in views])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs]); cp = (C.c_size_t * n)(*[o.size for o in outs])
+    st = (C.c_int * n)()
+    rc = mic.lib.micgpu_pics_decompress_batch(n, bp, ln, op, cp, st)
+    assert rc != 0                                   # first failing image is reported
+    for i in range(n):
+        if i in damaged:
+            assert st[i] != 0, f"image {i} ({damaged[i]}) was accepted"
+        else:
+            assert st[i] == 0 and np.array_equal(outs[i], imgs[i]), f"healthy image {i} disturbed"

@@ -399,7 +399,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
   const uint32_t rk = ringsa + (uint32_t)(k * CP);
   const int pf_min = k == 0 ? 8 : 0x7fffffff;    // lane 0 of a unit prefetches 8 quarters (256 B) ahead into L2
   const uint32_t mir = k * CP < 16 ? 1u : 0u;    // this lane's bytes of quarter 0 belong to ring words 0..3 (mirrored)
-  if (threadIdx.x == 0) *idle = MODE == 0 ? 0u : 32u;
+  if (threadIdx.x == 0) { idle[0] = MODE == 0 ? 0u : 32u; idle[1] = 0u; }   // [1]: the idle cell of the direct 16-bit format
   __syncthreads();
 
   for (int base = blockIdx.x * slots; base < nlist; base += gridDim.x * slots) {
@@ -425,6 +425,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
 
     int err = 0;
     uint32_t full = 0;
+    bool d16_ok = true;
     if (has) {
       L = (int)U->table_log;
       S = 1u << L;
@@ -462,16 +463,36 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
         const uint4* A4 = reinterpret_cast<const uint4*>(A);
         for (uint32_t i = k; i < S / 4; i += N) T4[i] = A4[i];
       } else {
+        // Direct 16-bit cells: nbBits in the low nibble, newState >> nbBits above it (newState is a multiple of
+        // 2^nbBits).  They fit while newState >> nbBits < 4096, i.e. for every table up to tableLog 12 and for tableLog 13
+        // unless one symbol holds more than 3/4 of the table; nbBits is then one AND away from the cell instead of a
+        // find-leading-one (18 cycles on the state chain, tools/ubench_lat.cu).
         uint2* T2 = reinterpret_cast<uint2*>(mytab);
         const uint4* A4 = reinterpret_cast<const uint4*>(A);
+        uint32_t wide = 0;
 #pragma unroll 4
         for (uint32_t i = k; i < S / 4; i += N) {
           const uint4 e = A4[i];
-          // nextState = (newState + S) >> nbBits  (inverse of fsedecompressu16.go:250-251)
-          const uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
-          const uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
-          T2[i] = make_uint2(n0 | (n1 << 16), n2 | (n3 << 16));
+          const uint32_t d0 = (e.x & 0xFFFF) >> (e.x >> 16), d1 = (e.y & 0xFFFF) >> (e.y >> 16);
+          const uint32_t d2 = (e.z & 0xFFFF) >> (e.z >> 16), d3 = (e.w & 0xFFFF) >> (e.w >> 16);
+          wide |= d0 | d1 | d2 | d3;
+          T2[i] = make_uint2((d0 << 4) | (e.x >> 16) | (((d1 << 4) | (e.y >> 16)) << 16), (d2 << 4) | (e.z >> 16) | (((d3 << 4) | (e.w >> 16)) << 16));
         }
+        d16_ok = wide < 4096u && L <= 15;
+      }
+    }
+    // one cell format per warp: the direct one if every unit of the warp allows it, else nextState cells for all of them
+    const bool d16 = MODE == 1 && __all_sync(0xffffffffu, !has || d16_ok);
+    if (MODE == 1 && !d16 && has) {
+      uint2* T2 = reinterpret_cast<uint2*>(mytab);
+      const uint4* A4 = reinterpret_cast<const uint4*>(tabA + U->tab_off);
+#pragma unroll 4
+      for (uint32_t i = k; i < S / 4; i += N) {
+        const uint4 e = A4[i];
+        // nextState = (newState + S) >> nbBits  (inverse of fsedecompressu16.go:250-251)
+        const uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
+        const uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
+        T2[i] = make_uint2(n0 | (n1 << 16), n2 | (n3 << 16));
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -497,7 +518,19 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     if (!live) { L = 5; S = 32; state = 0; }
     // lanes without a live unit decode the idle cell
     const uint32_t* T32 = live ? reinterpret_cast<const uint32_t*>(mytab) : idle;
-    const uint16_t* T16 = live ? reinterpret_cast<const uint16_t*>(mytab) : reinterpret_cast<const uint16_t*>(idle);
+    const uint16_t* T16 = live ? reinterpret_cast<const uint16_t*>(mytab) : reinterpret_cast<const uint16_t*>(idle + (d16 ? 1 : 0));
+    // one table cell -> (nbBits, newState); the format is uniform over the warp
+    auto cell = [&](auto fmt, uint32_t st, uint32_t& nb, uint32_t& ns) {
+      constexpr int F = decltype(fmt)::value;   // 0: u32 cells, 1: nextState cells, 2: direct 16-bit cells
+      if (F == 0) { const uint32_t e = T32[st]; nb = e >> 16; ns = e & 0xFFFF; }
+      else if (F == 1) { const uint32_t nx = T16[st]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }   // nx >= 1 (K1)
+      else { const uint32_t e = T16[st]; nb = e & 15u; ns = (e >> 4) << nb; }
+    };
+    auto cell_rt = [&](uint32_t st, uint32_t& nb, uint32_t& ns) {
+      if (MODE == 0) cell(std::integral_constant<int, 0>{}, st, nb, ns);
+      else if (d16) cell(std::integral_constant<int, 2>{}, st, nb, ns);
+      else cell(std::integral_constant<int, 1>{}, st, nb, ns);
+    };
     uint16_t* op = states_out + (has ? U->sym_off : 0) + k;
     const uint32_t full0 = live ? count / N : 0u;
     full = full0;
@@ -511,8 +544,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     auto round = [&](auto all_tag, bool act, int buf, int oidx) {
       constexpr bool ALL = decltype(all_tag)::value;
       uint32_t nb, ns;
-      if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
-      else { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }   // nx >= 1 (K1)
+      cell_rt(state, nb, ns);
       if (!ALL && !act) nb = 0;
       uint32_t tot;
       const uint32_t before = packed_prefix<N>(nb, xmine + buf * 32, xunit + buf * 32, bm, &tot);
@@ -537,10 +569,9 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
       W0 = w[0]; W1 = w[1]; W2 = w[2]; W3 = w[3]; W4 = w[4];    // words 32..35 mirror 0..3: no wrap inside the window
       Pb = (uint32_t)P - (wl << 5);                            // P relative to the window, in (128, 160]
     };
-    auto round_win = [&](int buf, int oidx) {
+    auto round_win = [&](auto fmt, int buf, int oidx) {
       uint32_t nb, ns;
-      if (MODE == 0) { const uint32_t e = T32[state]; nb = e >> 16; ns = e & 0xFFFF; }
-      else { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }   // nx >= 1 (K1)
+      cell(fmt, state, nb, ns);
       uint32_t tot;
       const uint32_t before = packed_prefix<N>(nb, xmine + buf * 32, xunit + buf * 32, bm, &tot);
       const uint32_t rel = Pb - before - nb;                   // bit offset of the field inside the window
@@ -556,14 +587,19 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     // ring check once per two rounds (two rounds consume at most 2*N*16 = 256 bits = one quarter)
     uint32_t r = 0;
     if (use_window) {
-      for (; r + 2 <= minfull; r += 2) {
-        load_window();          // after the ring check of the previous iteration (its copies are then guaranteed)
-        round_win(0, 0);
-        load_window();
-        round_win(1, 1);
-        op += 2 * N;
-        refill();
-      }
+      auto hot = [&](auto fmt) {
+        for (; r + 2 <= minfull; r += 2) {
+          load_window();          // after the ring check of the previous iteration (its copies are then guaranteed)
+          round_win(fmt, 0, 0);
+          load_window();
+          round_win(fmt, 1, 1);
+          op += 2 * N;
+          refill();
+        }
+      };
+      if (MODE == 0) hot(std::integral_constant<int, 0>{});
+      else if (d16) hot(std::integral_constant<int, 2>{});
+      else hot(std::integral_constant<int, 1>{});
     } else {
       for (; r + 2 <= minfull; r += 2) {
         round(std::true_type{}, true, 0, 0);
@@ -591,9 +627,8 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     {
       const uint32_t tail = (live && full == full0) ? count - full0 * N : 0u;
       const bool act = (uint32_t)k < tail;
-      uint32_t nb;
-      if (MODE == 0) { nb = T32[state] >> 16; }
-      else { const uint32_t nx = T16[state]; nb = (uint32_t)L - (31u - __clz(nx | 1u)); }
+      uint32_t nb, ns_unused;
+      cell_rt(state, nb, ns_unused);
       if (!act) nb = 0;
       uint32_t tot;
       packed_prefix<N>(nb, xmine + 32, xunit + 32, bm, &tot);

@@ -72,6 +72,16 @@ int micgpu_decoder_add_pics(micgpu_decoder *d, const uint8_t *pics, size_t len, 
 /* Add every frame of an independent-mode MIC2 container (multiframecompress.go:227-262). */
 int micgpu_decoder_add_mic2(micgpu_decoder *d, const uint8_t *mic2, size_t len, uint64_t comp_off, uint64_t out_off,
                             int *width, int *height, int *frames, int *temporal);
+/* Add frames [first_frame, first_frame + frame_count) of a MIC2 container: the shard of one rank when a stack is spread
+ * over GPUs (frame offsets come from the container's own table, multiframe.go:72-78).  Frame first_frame
+ * lands at out_off.  Independent mode: nothing else to do.  Temporal mode (multiframecompress.go:236-258): a range that
+ * starts at frame 0 decodes to pixels; a later range decodes to running sums relative to a ZERO carry, and the caller
+ * finishes it with micgpu_temporal_add_carry once it has the absolute last frame of the previous range -- the only
+ * exchange step of the whole path, and it is associative: carry(r) = sum of the last frames of ranges < r (mod 2^16). */
+int micgpu_decoder_add_mic2_range(micgpu_decoder *d, const uint8_t *mic2, size_t len, uint64_t comp_off, uint64_t out_off,
+                                  int first_frame, int frame_count, int *width, int *height, int *frames, int *temporal);
+/* d_frames[f][i] += d_carry[i] (mod 2^16) for nframes frames of frame_px pixels, both in device memory. */
+int micgpu_temporal_add_carry(void *d_frames, const void *d_carry, uint64_t frame_px, int nframes, void *cuda_stream);
 /* Size scratch for the plan.  Must be called after the last add_*. */
 int micgpu_decoder_commit(micgpu_decoder *d);
 int micgpu_decoder_unit_count(const micgpu_decoder *d);

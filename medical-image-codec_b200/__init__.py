@@ -36,5 +36,6 @@ from .api import (  # noqa: F401
     WaveletV2SIMDRLEFSEDecompressU16,
     DecompressSingleFrame,
     MicGpuError,
+    temporal_add_carry,
     lib,
 )

@@ -56,6 +56,8 @@ lib.micgpu_decoder_begin.argtypes = [C.c_void_p]
 lib.micgpu_decoder_add_unit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64]
 lib.micgpu_decoder_add_pics.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, _ip, _ip]
 lib.micgpu_decoder_add_mic2.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, _ip, _ip, _ip, _ip]
+lib.micgpu_decoder_add_mic2_range.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _ip, _ip, _ip, _ip]
+lib.micgpu_temporal_add_carry.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
 lib.micgpu_decoder_commit.argtypes = [C.c_void_p]
 lib.micgpu_decoder_unit_count.argtypes = [C.c_void_p]
 lib.micgpu_decoder_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -105,6 +107,11 @@ for _n in ("two", "four", "eight"):
         getattr(lib, f"mic_decompress_{_n}_state{_s}").argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
 lib.mic_decompress_parallel.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int]
 lib.mic_decompress_parallel_scalar.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int]
+
+
+def temporal_add_carry(d_frames_ptr: int, d_carry_ptr: int, frame_px: int, nframes: int, stream_ptr: int = 0):
+    """frames[f] += carry (mod 2^16) on device pointers: the exchange step of a sharded temporal MIC2 stack."""
+    _check(lib.micgpu_temporal_add_carry(d_frames_ptr, d_carry_ptr, frame_px, nframes, stream_ptr))
 
 
 def last_error() -> str:
@@ -451,6 +458,14 @@ class Decoder:
         a = _bytes_view(blob)
         w, h, n, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib.micgpu_decoder_add_mic2(self._h, a.ctypes.data, a.size, comp_off, out_off, C.byref(w), C.byref(h), C.byref(n), C.byref(t)))
+        return w.value, h.value, n.value, bool(t.value)
+
+    def add_mic2_range(self, blob, comp_off: int, out_off: int, first_frame: int, frame_count: int):
+        """Frames [first_frame, first_frame + frame_count) of a MIC2 stack (one rank's shard); see include/micgpu.h."""
+        a = _bytes_view(blob)
+        w, h, n, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib.micgpu_decoder_add_mic2_range(self._h, a.ctypes.data, a.size, comp_off, out_off, first_frame, frame_count,
+                                                 C.byref(w), C.byref(h), C.byref(n), C.byref(t)))
         return w.value, h.value, n.value, bool(t.value)
 
     def commit(self):

@@ -7,11 +7,18 @@ namespace micgpu {
 // multiframecompress.go:236-258).  frame 0 holds pixels, frames 1..n-1 hold
 // ZigZag residuals; out_f = out_{f-1} + UnZigZag(res_f) mod 2^16 is a running
 // sum along the frame axis, kept in a register per pixel (in place).
+// first_is_residual: the group is a frame range that starts inside a temporal stack (a shard of it): frame 0 is a
+// residual too and the sums are relative to a zero carry; k_temporal_add_carry finishes them once the carry frame
+// (the absolute last frame of the previous shard) is known.
 __global__ void __launch_bounds__(256)
-k_temporal_accumulate(uint16_t* __restrict__ frames, unsigned long long fpx, int nframes) {
+k_temporal_accumulate(uint16_t* __restrict__ frames, unsigned long long fpx, int nframes, int first_is_residual) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < fpx; i += stride) {
     unsigned v = frames[i];
+    if (first_is_residual) {
+      v = ((v >> 1) ^ (0u - (v & 1u))) & 0xFFFFu;
+      frames[i] = (uint16_t)v;
+    }
     for (int f = 1; f < nframes; f++) {
       const unsigned r = frames[(unsigned long long)f * fpx + i];
       const unsigned diff = (r >> 1) ^ (0u - (r & 1u));   // UnZigZag (deltazigzagcompressu16.go:113-116)
@@ -21,11 +28,33 @@ k_temporal_accumulate(uint16_t* __restrict__ frames, unsigned long long fpx, int
   }
 }
 
-void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int sm_count, cudaStream_t st) {
-  if (nframes <= 1 || fpx == 0) return;
+void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int first_is_residual, int sm_count,
+                                cudaStream_t st) {
+  if ((nframes <= 1 && !first_is_residual) || fpx == 0 || nframes <= 0) return;
   unsigned long long blocks = (fpx + 255) / 256;
   if (blocks > (unsigned long long)sm_count * 8) blocks = (unsigned long long)sm_count * 8;
-  k_temporal_accumulate<<<(unsigned)blocks, 256, 0, st>>>(d_frames, fpx, nframes);
+  k_temporal_accumulate<<<(unsigned)blocks, 256, 0, st>>>(d_frames, fpx, nframes, first_is_residual);
+}
+
+// frames[f][i] += carry[i]  (mod 2^16): the one exchange step of a temporal stack sharded over GPUs
+__global__ void __launch_bounds__(256)
+k_temporal_add_carry(uint16_t* __restrict__ frames, const uint16_t* __restrict__ carry, unsigned long long fpx, int nframes) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < fpx; i += stride) {
+    const unsigned c = carry[i];
+    for (int f = 0; f < nframes; f++) {
+      const unsigned long long at = (unsigned long long)f * fpx + i;
+      frames[at] = (uint16_t)(frames[at] + c);
+    }
+  }
+}
+
+void launch_temporal_add_carry(uint16_t* d_frames, const uint16_t* d_carry, unsigned long long fpx, int nframes, int sm_count,
+                               cudaStream_t st) {
+  if (nframes <= 0 || fpx == 0) return;
+  unsigned long long blocks = (fpx + 255) / 256;
+  if (blocks > (unsigned long long)sm_count * 8) blocks = (unsigned long long)sm_count * 8;
+  k_temporal_add_carry<<<(unsigned)blocks, 256, 0, st>>>(d_frames, d_carry, fpx, nframes);
 }
 
 }  // namespace micgpu

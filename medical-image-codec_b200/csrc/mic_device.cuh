@@ -35,7 +35,11 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
 int delta_wavefront_threads(int max_width, int max_height);
 
 // In-place frame-axis running sum for temporal MIC2 (frames contiguous, fpx pixels each).
-void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int sm_count, cudaStream_t st);
+void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int first_is_residual, int sm_count,
+                                cudaStream_t st);
+// frames[f] += carry (mod 2^16) for a shard of a temporal stack decoded relative to a zero carry
+void launch_temporal_add_carry(uint16_t* d_frames, const uint16_t* d_carry, unsigned long long fpx, int nframes, int sm_count,
+                               cudaStream_t st);
 
 // MIC3 helpers (k_misc.cu)
 struct PlaneFillJob {

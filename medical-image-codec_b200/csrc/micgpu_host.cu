@@ -36,6 +36,7 @@ struct AnsPlan {
 struct TemporalGroup {
   unsigned long long out_off, fpx;
   int nframes;
+  int first_is_residual;   // the group is a shard that starts inside the stack (sums relative to a zero carry)
 };
 
 }  // namespace
@@ -313,7 +314,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   }
   for (const TemporalGroup& t : d->temporal) {
     prof_mark(d, "k_temporal_accumulate", st);
-    launch_temporal_accumulate((uint16_t*)d_out + t.out_off, t.fpx, t.nframes, d->sm_count, st);
+    launch_temporal_accumulate((uint16_t*)d_out + t.out_off, t.fpx, t.nframes, t.first_is_residual, d->sm_count, st);
     d->launches++;
   }
   prof_mark(d, "end", st);
@@ -405,12 +406,14 @@ int parse_mic2(const uint8_t* p, size_t len, Mic2Header& mh) {
 }
 
 int add_mic2_locked(micgpu_decoder* d, const uint8_t* p, size_t len, uint64_t comp_off, uint64_t out_off, int last_frame,
-                    Mic2Header& mh) {
+                    Mic2Header& mh, int first_frame = 0) {
   int rc = parse_mic2(p, len, mh);
   if (rc) return rc;
   const unsigned long long fpx = (unsigned long long)mh.w * mh.h;
   const int nf = last_frame < 0 ? mh.n : std::min(mh.n, last_frame + 1);
-  for (int i = 0; i < nf; i++) {
+  if (first_frame < 0 || first_frame > nf) return fail(MICGPU_E_HEADER, "MIC2: frame range starts at %d of %d", first_frame, nf);
+  out_off -= (uint64_t)first_frame * fpx;   // frame i lands at out_off + (i - first_frame) * fpx
+  for (int i = first_frame; i < nf; i++) {
     const size_t o = rd32(p + 20 + (size_t)i * 8), l = rd32(p + 24 + (size_t)i * 8);
     if (mh.data_off + o + l > len) return fail(MICGPU_E_HEADER, "MIC2: frame %d data extends beyond file", i);
     const bool residual = mh.temporal && i > 0;
@@ -418,7 +421,9 @@ int add_mic2_locked(micgpu_decoder* d, const uint8_t* p, size_t len, uint64_t co
     add_unit_locked(d, p + mh.data_off + o, l, comp_off + mh.data_off + o, residual ? MIC_KIND_RLE : MIC_KIND_SPATIAL,
                     residual ? (uint32_t)fpx : (uint32_t)mh.w, residual ? 1u : (uint32_t)mh.h, out_off + (uint64_t)i * fpx);
   }
-  if (mh.temporal && nf > 1) d->temporal.push_back(TemporalGroup{out_off, fpx, nf});
+  const int count = nf - first_frame;
+  if (mh.temporal && (count > 1 || (count == 1 && first_frame > 0)))
+    d->temporal.push_back(TemporalGroup{out_off + (uint64_t)first_frame * fpx, fpx, count, first_frame > 0 ? 1 : 0});
   return 0;
 }
 
@@ -554,6 +559,32 @@ int micgpu_decoder_add_mic2(micgpu_decoder* d, const uint8_t* mic2, size_t len, 
   if (height) *height = mh.h;
   if (frames) *frames = mh.n;
   if (temporal) *temporal = mh.temporal;
+  return 0;
+}
+
+int micgpu_decoder_add_mic2_range(micgpu_decoder* d, const uint8_t* mic2, size_t len, uint64_t comp_off, uint64_t out_off,
+                                  int first_frame, int frame_count, int* width, int* height, int* frames, int* temporal) {
+  if (!d || !mic2) return fail(MICGPU_E_HEADER, "null argument");
+  if (first_frame < 0 || frame_count < 0) return fail(MICGPU_E_HEADER, "MIC2: negative frame range");
+  std::lock_guard<std::mutex> lk(d->mu);
+  Mic2Header mh;
+  int rc = add_mic2_locked(d, mic2, len, comp_off, out_off, first_frame + frame_count - 1, mh, first_frame);
+  if (rc) return rc;
+  if (first_frame + frame_count > mh.n) return fail(MICGPU_E_HEADER, "MIC2: frame range %d+%d exceeds %d frames", first_frame, frame_count, mh.n);
+  if (width) *width = mh.w;
+  if (height) *height = mh.h;
+  if (frames) *frames = mh.n;
+  if (temporal) *temporal = mh.temporal;
+  return 0;
+}
+
+int micgpu_temporal_add_carry(void* d_frames, const void* d_carry, uint64_t frame_px, int nframes, void* cuda_stream) {
+  if (!d_frames || !d_carry) return fail(MICGPU_E_HEADER, "null argument");
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  launch_temporal_add_carry((uint16_t*)d_frames, (const uint16_t*)d_carry, frame_px, nframes, sms, (cudaStream_t)cuda_stream);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

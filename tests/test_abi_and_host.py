@@ -121,3 +121,64 @@ def test_sharding_two_ranks_gloo(tmp_path):
                         "--master-port", "29613", str(script), ROOT], capture_output=True, text=True, env=env, timeout=170)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("OK") == 2
+
+
+_GLOO_TEMPORAL_WORKER = r'''
+import importlib, os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch
+import torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+shard = importlib.import_module("medical-image-codec_b200.shard")
+synth = importlib.import_module("medical-image-codec_b200.synth")
+from oracle.oracle import Oracle
+o = Oracle()
+# a temporal MIC2 stack; every rank reads the same frame table and takes a contiguous range balanced by bytes
+st = synth.tomo_stack(3, 7, 96, 80)
+blob = o.mic2_compress(st.ravel(), 96, 80, 1023, True)
+w, h, n, temporal, tab = shard.mic2_frame_table(blob)
+assert temporal and n == 7
+lo, hi = shard.partition_by_bytes([l for _, l in tab], world)[rank]
+fpx = w * h
+# CPU stand-in for the per-rank GPU decode (micgpu_decoder_add_mic2_range): absolute pixels for the range that starts at
+# frame 0, running sums of UnZigZag(residual) relative to a ZERO carry for a later range
+full = o.mic2_decompress(blob)[0].reshape(n, fpx).astype(np.uint16)
+local = full[lo:hi].copy()
+if lo > 0:
+    local = (local - full[lo - 1]).astype(np.uint16)
+# the one exchange step: all-gather the last local frame of every rank, exclusive scan mod 2^16
+last = torch.from_numpy((local[-1] if hi > lo else np.zeros(fpx, np.uint16)).astype(np.int16))
+carry = shard.mic2_temporal_carry(shard.all_gather_last_frames(dist, last), rank)
+if carry is not None:
+    local = (local + carry.numpy().astype(np.uint16)).astype(np.uint16)
+ok = np.array_equal(local, full[lo:hi]) and np.array_equal(full.reshape(-1), st.ravel())
+print("RANK", rank, "OK" if ok else "FAIL", (lo, hi))
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_temporal_carry_two_ranks_gloo(tmp_path):
+    """The path's one exchange step (SURVEY 8(e)): a temporal MIC2 stack cut across two ranks needs the carry frame of the
+    earlier range; all_gather of one frame per rank + exclusive scan mod 2^16 reproduces the serial decode."""
+    script = tmp_path / "worker_t.py"
+    script.write_text(_GLOO_TEMPORAL_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29614")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29614", str(script), ROOT], capture_output=True, text=True, env=env, timeout=170)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == 2
+
+
+def test_temporal_carry_is_an_exclusive_scan():
+    import importlib
+
+    shard = importlib.import_module("medical-image-codec_b200.shard")
+    rng = np.random.default_rng(3)
+    lasts = rng.integers(0, 65536, size=(4, 50)).astype(np.uint16)
+    assert shard.mic2_temporal_carry(lasts, 0) is None
+    for r in range(1, 4):
+        want = lasts[:r].astype(np.uint64).sum(axis=0).astype(np.uint16)      # mod 2^16
+        assert np.array_equal(shard.mic2_temporal_carry(lasts, r), want)

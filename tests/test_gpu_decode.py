@@ -126,7 +126,7 @@ def test_pics_batch(mic, oracle, synth):
 
 
 def test_pics_batch_pipelined(mic, oracle, synth):
-    # >= 16 images take the chunked path (H2D / kernels / D2H of consecutive chunks overlap on three contexts);
+    # >= 16 images take the chunked path (H2D / kernels / D2H of consecutive chunks overlap on several decoder contexts);
     # one corrupt image in the middle must be reported without disturbing the others
     w, h = 211, 160
     imgs = [synth.xr_image(100 + i, w, h).ravel() for i in range(37)]
@@ -222,3 +222,45 @@ def test_packed_warp_mixed_units_and_statuses(mic, oracle, synth):
             assert st[i] != 0, f"image {i} ({damaged[i]}) was accepted"
         else:
             assert st[i] == 0 and np.array_equal(outs[i], imgs[i]), f"healthy image {i} disturbed"
+
+
+@pytest.mark.parametrize("cuts", [(0, 3, 7), (0, 1, 4, 7), (0, 7, 7)])
+def test_mic2_temporal_sharded_ranges(mic, oracle, synth, cuts):
+    """a temporal stack cut into frame ranges (one per rank) decodes range by range -- relative sums for a
+    range that starts inside the stack -- and the carry exchange (exclusive scan of each range's last frame, then
+    micgpu_temporal_add_carry) reproduces the serial decode bit for bit.  The ranges run one after the other on this GPU."""
+    import importlib
+
+    import torch
+
+    shard = importlib.import_module("medical-image-codec_b200.shard")
+    w, h, nf = 96, 80, 7
+    st = synth.tomo_stack(3, nf, w, h)
+    blob = np.frombuffer(oracle.mic2_compress(st.ravel(), w, h, 1023, True), np.uint8)
+    fpx = w * h
+    d_comp = torch.zeros(blob.size + 256, dtype=torch.uint8, device="cuda")
+    d_comp[: blob.size] = torch.from_numpy(blob.copy()).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    outs, lasts = [], []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        d_out = torch.zeros(max(hi - lo, 1) * fpx, dtype=torch.int16, device="cuda")
+        if hi > lo:
+            dec = mic.Decoder(0)
+            dec.begin()
+            assert dec.add_mic2_range(blob, 0, 0, lo, hi - lo) == (w, h, nf, True)
+            dec.commit()
+            dec.run_device(d_comp.data_ptr(), blob.size, d_out.data_ptr(), (hi - lo) * fpx, stream)
+            assert not any(dec.unit_status(stream))
+            dec.close()
+            lasts.append(d_out[(hi - lo - 1) * fpx:(hi - lo) * fpx].clone())
+        else:
+            lasts.append(torch.zeros(fpx, dtype=torch.int16, device="cuda"))   # an empty range carries nothing
+        outs.append((lo, hi, d_out))
+    stacked = torch.stack(lasts)
+    for r, (lo, hi, d_out) in enumerate(outs):
+        carry = shard.mic2_temporal_carry(stacked, r)
+        if carry is not None and hi > lo:
+            mic.temporal_add_carry(d_out.data_ptr(), carry.contiguous().data_ptr(), fpx, hi - lo, stream)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint16)[: (hi - lo) * fpx]
+        assert np.array_equal(got, st[lo:hi].ravel()), f"range {lo}:{hi}"

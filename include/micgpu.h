@@ -86,7 +86,7 @@ int micgpu_temporal_add_carry(void *d_frames, const void *d_carry, uint64_t fram
 int micgpu_decoder_commit(micgpu_decoder *d);
 int micgpu_decoder_unit_count(const micgpu_decoder *d);
 /* Decode the planned batch.  d_comp: device buffer holding the streams
- * (64-byte aligned, readable for comp_bytes + 128 bytes); d_out: device buffer
+ * (64-byte aligned, readable for comp_bytes + 256 bytes); d_out: device buffer
  * of out_elems uint16.  cuda_stream: a cudaStream_t (NULL = default stream).
  * Asynchronous with respect to the host. */
 int micgpu_decoder_run_device(micgpu_decoder *d, const void *d_comp, size_t comp_bytes, void *d_out, size_t out_elems,

@@ -152,7 +152,15 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         if (tid == 0) { ws.wbase = a0; ws.wend = a0 + nb; }
       }
       __syncthreads();
+      // Destination-aligned layout: element o of the chunk sits at se[o] = s_e_raw[ph + o]; for spatial units ph makes
+      // (index in s_e_raw) == (pixel index + align0) mod 8, so aligned groups of eight are aligned 16 B stores in D.
+      const int skip = (spatial && first) ? 1 : 0;   // element 0 of the stream is maxValue, not a pixel
+      const int ph = spatial ? (int)((pix + align0 + 8u - (unsigned)skip) & 7u) : 0;
+      uint16_t* se = s_e_raw + ph;
       // ---------------- B: header walk + expansion (warp 0) -----------------
+      // Runs of up to 32 elements are expanded right here by the walking warp (one predicated load + store); only longer
+      // runs go to the run list for B2.  Run-heavy streams (temporal residuals: a run every ~5 elements) otherwise hit the
+      // 256-entry list limit after ~1000 outputs and paid the per-chunk barriers four times per 4096 elements.
       if (warp == 0) {
         int ip = ws.ipos;
         const int wb = ws.wbase, we = ws.wend;
@@ -194,12 +202,20 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           } else {
             src = -(int)(value + 1u);
           }
-          if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = src; }
-          nr++;
+          if (take <= 32) {
+            if (lane < take) {
+              uint16_t v = (uint16_t)value;
+              if (kind == 1) v = s_in[src + lane];
+              se[o + lane] = v;
+            }
+          } else {
+            if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = src; }
+            nr++;
+          }
           o += take;
           c_rem -= (unsigned)take;
         }
-        if (!restage && o == 0 && nr == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
+        if (!restage && o == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
         if (lane == 0) {
           ws.ipos = ip; ws.c_rem = c_rem; ws.kind = kind; ws.value = value;
           ws.nout = o; ws.nruns = nr; ws.done = done; ws.err = err;
@@ -209,12 +225,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       const int nout = ws.nout;
       const int done = ws.done;
       if (ws.err) break;
-      // ---------------- B2: expand the listed runs, all threads per run -------
-      // Destination-aligned layout: element o of the chunk sits at se[o] = s_e_raw[ph + o]; for spatial units ph makes
-      // (index in s_e_raw) == (pixel index + align0) mod 8, so aligned groups of eight are aligned 16 B stores in D.
-      const int skip = (spatial && first) ? 1 : 0;   // element 0 of the stream is maxValue, not a pixel
-      const int ph = spatial ? (int)((pix + align0 + 8u - (unsigned)skip) & 7u) : 0;
-      uint16_t* se = s_e_raw + ph;
+      // ---------------- B2: expand the listed (long) runs, one warp per run ----
       {
         // one warp per run: the per-run set-up is paid once instead of by all eight warps (the kernel is issue bound;
         // with ~6 runs per chunk the set-up was 30 % of all instructions), the copy itself is the same work either way

@@ -139,13 +139,31 @@ int enc_run(micgpu_encoder* e, const uint16_t* d_src, const EncHook& after_uploa
     e->h_units_cap = (size_t)nu + nu / 4 + 16;
   }
   cudaStream_t st = e->stream;
+  // MICGPU_DEBUG_SYNC=1: synchronise after every launch group and name the one that faulted
+  static const bool dbg = [] { const char* v = getenv("MICGPU_DEBUG_SYNC"); return v && v[0] == '1'; }();
+  auto chk = [&](const char* what) -> int {
+    if (!dbg) return 0;
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(MICGPU_E_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+    return 0;
+  };
   memcpy(e->h_units, e->units.data(), (size_t)nu * sizeof(MicEncUnit));
   CUDA_TRY(cudaMemcpyAsync(e->d_units.p, e->h_units, (size_t)nu * sizeof(MicEncUnit), cudaMemcpyHostToDevice, st));
   MicEncUnit* du = (MicEncUnit*)e->d_units.p;
   if (after_upload) after_upload(du, st);
+  if (dbg) {   // poison every scratch buffer so that a read of something no kernel wrote misbehaves the same way in every process
+    cudaMemsetAsync(e->d_V.p, 0xFF, (T.v + 64) * 2, st); cudaMemsetAsync(e->d_S.p, 0xFF, (T.s + 64) * 2, st);
+    cudaMemsetAsync(e->d_segs.p, 0xFF, (T.seg + 64) * 8, st); cudaMemsetAsync(e->d_T.p, 0xFF, (T.t + 64) * 4, st);
+    cudaMemsetAsync(e->d_tab.p, 0xFF, (T.tab + 64) * 2, st); cudaMemsetAsync(e->d_tt.p, 0xFF, (T.tt + 64) * 8, st);
+    cudaMemsetAsync(e->d_hdr.p, 0xFF, T.hdr + 64, st); cudaMemsetAsync(e->d_frames.p, 0xFF, T.out + 64, st);
+  }
+  if ((rc = chk("upload"))) return rc;
   launch_enc_delta_rle(du, nu, d_src, (uint16_t*)e->d_V.p, (uint32_t*)e->d_segs.p, (uint16_t*)e->d_S.p, grid, st);
+  if ((rc = chk("k_enc_delta / k_enc_rle_*"))) return rc;
   launch_enc_tables(du, nu, (const uint16_t*)e->d_S.p, (uint8_t*)e->d_k6.p, (uint16_t*)e->d_tab.p, (uint2*)e->d_tt.p, (uint8_t*)e->d_hdr.p, grid, st);
   e->launches += 5;
+  if ((rc = chk("k_enc_tables"))) return rc;
   // FSE tiers: a unit rejected at its tier (ErrIncompressible / ErrUseRLE / any error) is retried one tier down, like
   // CompressSingleFrame8State -> 4State -> 2State -> FSECompressU16 (multiframecompress.go:67-93)
   std::vector<int> pending(nu);
@@ -169,8 +187,10 @@ int enc_run(micgpu_encoder* e, const uint16_t* d_src, const EncHook& after_uploa
       }
       off += lists[g].size();
     }
+    if ((rc = chk("k_enc_ans"))) return rc;
     launch_enc_pack(du, nu, (const uint32_t*)e->d_T.p, (const uint8_t*)e->d_hdr.p, (uint8_t*)e->d_frames.p, grid, st);
     e->launches++;
+    if ((rc = chk("k_enc_pack"))) return rc;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(e->h_units, e->d_units.p, (size_t)nu * sizeof(MicEncUnit), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

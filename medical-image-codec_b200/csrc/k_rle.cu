@@ -158,9 +158,9 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       const int ph = spatial ? (int)((pix + align0 + 8u - (unsigned)skip) & 7u) : 0;
       uint16_t* se = s_e_raw + ph;
       // ---------------- B: header walk + expansion (warp 0) -----------------
-      // Runs of up to 32 elements are expanded right here by the walking warp (one predicated load + store); only longer
-      // runs go to the run list for B2.  Run-heavy streams (temporal residuals: a run every ~5 elements) otherwise hit the
-      // 256-entry list limit after ~1000 outputs and paid the per-chunk barriers four times per 4096 elements.
+      // The walk is the serial part: ~200 cycles per run.  Run-heavy streams (temporal residuals: a run every ~5
+      // elements, 1.25 M runs per tomo frame) are bound by it -- 86 % of the kernel's samples are the other warps waiting
+      // at the barrier below (profiles/README.md); expanding short runs inside the walk did not change that.
       if (warp == 0) {
         int ip = ws.ipos;
         const int wb = ws.wbase, we = ws.wend;
@@ -202,20 +202,12 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           } else {
             src = -(int)(value + 1u);
           }
-          if (take <= 32) {
-            if (lane < take) {
-              uint16_t v = (uint16_t)value;
-              if (kind == 1) v = s_in[src + lane];
-              se[o + lane] = v;
-            }
-          } else {
-            if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = src; }
-            nr++;
-          }
+          if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = src; }
+          nr++;
           o += take;
           c_rem -= (unsigned)take;
         }
-        if (!restage && o == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
+        if (!restage && o == 0 && nr == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
         if (lane == 0) {
           ws.ipos = ip; ws.c_rem = c_rem; ws.kind = kind; ws.value = value;
           ws.nout = o; ws.nruns = nr; ws.done = done; ws.err = err;

@@ -27,7 +27,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("MICGPU_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     subprocess.check_call(cmd)
     return LIB
 

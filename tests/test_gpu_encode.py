@@ -227,3 +227,27 @@ def test_wsi_grey_bytes(mic, oracle, synth, bps):
     lv = 0 if bps == 8 else 1
     got = mic.CompressWSI(np.frombuffer(px, np.uint8), W, H, channels=1, bits_per_sample=bps, tile_width=128, tile_height=128, pyramid_levels=lv)
     assert got == oracle.wsi_compress(np.frombuffer(px, np.uint8), W, H, 1, bps, 128, 128, lv)
+
+
+def test_uncodable_stream_fails_like_the_reference(mic, oracle):
+    """A temporal residual with more distinct symbols than FSE table cells cannot be coded by the reference either
+    (normalizeCount2 underflows, fsecompressu16.go:582-667; the oracle reports it as an internal error).  The GPU
+    encoder must report an error on every tier of the 8->4->2->1 ladder instead of retrying on tables it never built
+    (that retry used to read outside the state table)."""
+    rng = np.random.default_rng(5)
+    w, h = 24, 25
+    n = w * h
+    k = int(rng.integers(150, 400))
+    vals = rng.integers(0, 1000, k)
+    d = vals[rng.integers(0, k, n)]
+    f0 = rng.integers(2000, 3000, n).astype(np.uint16)
+    f1 = (f0.astype(np.int64) + d - 500).astype(np.uint16)
+    st = np.stack([f0, f1])
+    with pytest.raises(Exception):
+        oracle.mic2_compress(st.ravel(), w, h, 4095, True)
+    for _ in range(3):      # repeated: the encoder context must stay usable after the failure
+        with pytest.raises(mic.MicGpuError):
+            mic.CompressMultiFrame(st, w, h, 4095, True)
+    y, x = np.mgrid[0:64, 0:64]
+    good = np.stack([(1000 + 3 * x + 5 * y + rng.integers(0, 8, (64, 64))).astype(np.uint16) for _ in range(2)])
+    assert mic.CompressMultiFrame(good, 64, 64, 4095, True) == oracle.mic2_compress(good.ravel(), 64, 64, 4095, True)

@@ -372,7 +372,7 @@ __device__ __forceinline__ void ring_refill_async(int P, int& cross, uint32_t& r
 template <int N, int MODE>
 __global__ void __launch_bounds__(1024)
 k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
-                    const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots, int use_window) {
+                    const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots) {
   static_assert(N == 2 || N == 4 || N == 8, "packed decode is for the interleaved coders");
   static_assert(MODE == 0 || MODE == 1, "packed decode keeps its tables in shared memory");
   extern __shared__ __align__(16) uint8_t smem[];
@@ -384,8 +384,11 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
   const int sslot = slot_ok ? slot : 0;          // lanes without a slot alias slot 0's ring (read-only)
 
   const ByteMasks<N> bm(k);
-  const size_t tbytes = (size_t)(1u << max_log) * (MODE == 0 ? 4 : 2);
+  // tableLog 16 in 2-byte cells: nextState needs 17 bits; the top one lives in a bit array behind the cells
+  const bool l16 = MODE == 1 && max_log == 16;
+  const size_t tbytes = (size_t)(1u << max_log) * (MODE == 0 ? 4 : 2) + (l16 ? (1u << 16) / 8 : 0);
   uint8_t* mytab = smem + (size_t)sslot * tbytes;
+  uint32_t* myflags = reinterpret_cast<uint32_t*>(mytab + ((size_t)2 << max_log));
   uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)slots * tbytes) + sslot * RING_STRIDE;
   uint8_t* xbase = smem + (size_t)slots * (tbytes + RING_STRIDE * 4);
   // Idle cell: a one-entry table for lanes that own no unit.  With L = 5 the entry decodes to nbBits = 0 and
@@ -399,7 +402,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
   const uint32_t rk = ringsa + (uint32_t)(k * CP);
   const int pf_min = k == 0 ? 8 : 0x7fffffff;    // lane 0 of a unit prefetches 8 quarters (256 B) ahead into L2
   const uint32_t mir = k * CP < 16 ? 1u : 0u;    // this lane's bytes of quarter 0 belong to ring words 0..3 (mirrored)
-  if (threadIdx.x == 0) { idle[0] = MODE == 0 ? 0u : 32u; idle[1] = 0u; }   // [1]: the idle cell of the direct 16-bit format
+  if (threadIdx.x == 0) { idle[0] = MODE == 0 ? 0u : 32u; idle[1] = 0u; idle[2] = 0u; }   // [1]: idle cell of the direct format, [2]: idle flag word
   __syncthreads();
 
   for (int base = blockIdx.x * slots; base < nlist; base += gridDim.x * slots) {
@@ -479,10 +482,13 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
           T2[i] = make_uint2((d0 << 4) | (e.x >> 16) | (((d1 << 4) | (e.y >> 16)) << 16), (d2 << 4) | (e.z >> 16) | (((d3 << 4) | (e.w >> 16)) << 16));
         }
         d16_ok = wide < 4096u && L <= 15;
+        if (l16)
+          for (uint32_t j = k; j < (1u << 16) / 32; j += N) myflags[j] = 0;
       }
     }
     // one cell format per warp: the direct one if every unit of the warp allows it, else nextState cells for all of them
     const bool d16 = MODE == 1 && __all_sync(0xffffffffu, !has || d16_ok);
+    __syncwarp();   // the first staging pass (and the zeroed flag words) is visible to every lane of the unit
     if (MODE == 1 && !d16 && has) {
       uint2* T2 = reinterpret_cast<uint2*>(mytab);
       const uint4* A4 = reinterpret_cast<const uint4*>(tabA + U->tab_off);
@@ -492,7 +498,11 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
         // nextState = (newState + S) >> nbBits  (inverse of fsedecompressu16.go:250-251)
         const uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
         const uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
-        T2[i] = make_uint2(n0 | (n1 << 16), n2 | (n3 << 16));
+        T2[i] = make_uint2((n0 & 0xFFFF) | (n1 << 16), (n2 & 0xFFFF) | (n3 << 16));
+        if (l16) {
+          const uint32_t hi = (n0 >> 16) | ((n1 >> 16) << 1) | ((n2 >> 16) << 2) | ((n3 >> 16) << 3);
+          if (hi) atomicOr(&myflags[i >> 3], hi << ((i & 7u) * 4));
+        }
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -519,11 +529,17 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     // lanes without a live unit decode the idle cell
     const uint32_t* T32 = live ? reinterpret_cast<const uint32_t*>(mytab) : idle;
     const uint16_t* T16 = live ? reinterpret_cast<const uint16_t*>(mytab) : reinterpret_cast<const uint16_t*>(idle + (d16 ? 1 : 0));
+    const uint32_t* FL = live ? myflags : idle + 2;
     // one table cell -> (nbBits, newState); the format is uniform over the warp
     auto cell = [&](auto fmt, uint32_t st, uint32_t& nb, uint32_t& ns) {
       constexpr int F = decltype(fmt)::value;   // 0: u32 cells, 1: nextState cells, 2: direct 16-bit cells
       if (F == 0) { const uint32_t e = T32[st]; nb = e >> 16; ns = e & 0xFFFF; }
-      else if (F == 1) { const uint32_t nx = T16[st]; nb = (uint32_t)L - (31u - __clz(nx)); ns = (nx << nb) - S; }   // nx >= 1 (K1)
+      else if (F == 1) {
+        uint32_t nx = T16[st];
+        if (l16) nx |= ((FL[st >> 5] >> (st & 31u)) & 1u) << 16;
+        nb = (uint32_t)L - (31u - __clz(nx));    // nx >= 1 (K1)
+        ns = (nx << nb) - S;
+      }
       else { const uint32_t e = T16[st]; nb = e & 15u; ns = (e >> 4) << nb; }
     };
     auto cell_rt = [&](uint32_t st, uint32_t& nb, uint32_t& ns) {
@@ -586,7 +602,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
     };
     // ring check once per two rounds (two rounds consume at most 2*N*16 = 256 bits = one quarter)
     uint32_t r = 0;
-    if (use_window) {
+    {
       auto hot = [&](auto fmt) {
         for (; r + 2 <= minfull; r += 2) {
           load_window();          // after the ring check of the previous iteration (its copies are then guaranteed)
@@ -600,13 +616,6 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
       if (MODE == 0) hot(std::integral_constant<int, 0>{});
       else if (d16) hot(std::integral_constant<int, 2>{});
       else hot(std::integral_constant<int, 1>{});
-    } else {
-      for (; r + 2 <= minfull; r += 2) {
-        round(std::true_type{}, true, 0, 0);
-        round(std::true_type{}, true, 1, 1);
-        op += 2 * N;
-        refill();
-      }
     }
     if (live && P < (int)shift) full = 0;
     for (; r + 2 <= maxfull; r += 2) {
@@ -646,6 +655,7 @@ k_ans_decode_packed(MicUnit* __restrict__ units, const int* __restrict__ list, i
 
 size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta) {
   size_t t = smem_mode == 2 ? 0 : ((size_t)(1u << max_log) * (smem_mode == 0 ? 4 : 2));
+  if (smem_mode == 1 && max_log == 16) t += (1u << 16) / 8;   // bit 16 of nextState, one bit per cell (packed kernel only)
   // + the packed kernel's idle cell (16 B) and byte-exchange area (64 B per warp; at least 4 slots share a warp)
   return (size_t)slots_per_cta * (t + RING_STRIDE * 4) + 16 + 64 * (size_t)((slots_per_cta + 3) / 4);
 }
@@ -665,8 +675,7 @@ static void launch_packed(MicUnit* d_units, const int* d_list, int nlist, const 
   const int warps = (slots + UPW - 1) / UPW;
   size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
   cudaFuncSetAttribute(k_ans_decode_packed<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  static const int win = [] { const char* e = getenv("MICGPU_K2_WINDOW"); return e ? atoi(e) : 1; }();
-  k_ans_decode_packed<N, MODE><<<grid, 32 * warps, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, win);
+  k_ans_decode_packed<N, MODE><<<grid, 32 * warps, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
 }
 
 static bool use_packed() {

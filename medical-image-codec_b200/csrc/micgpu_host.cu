@@ -176,7 +176,8 @@ int plan_commit(micgpu_decoder* d) {
       return s;
     };
     int mode = 0;
-    if (fit(0) < std::min(need_per_sm, slots_max)) mode = ml <= 15 && fit(1) > fit(0) ? 1 : 0;
+    // 2-byte cells hold tableLog <= 15; the packed kernel (N > 1) adds a bit array for tableLog 16
+    if (fit(0) < std::min(need_per_sm, slots_max)) mode = (ml <= 15 || (ml == 16 && a.nstates > 1)) && fit(1) > fit(0) ? 1 : 0;
     if (fit(mode) < 1) mode = 2;
     a.mode = mode;
     int slots = std::min(slots_max, std::max(1, std::min(fit(mode), need_per_sm)));

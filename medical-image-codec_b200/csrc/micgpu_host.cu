@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <mutex>
@@ -65,9 +66,9 @@ struct micgpu_decoder {
   cudaStream_t stream = nullptr;  // used by the host-buffer convenience calls
   // K3 -> K4 run as PARTS independent unit ranges on their own streams: both kernels are latency bound at under half
   // of the issue slots, so the wavefront of one range fills gaps of the run expansion of the next (measured: -3 %)
-  static constexpr int PARTS = 4;
-  cudaStream_t part_stream[PARTS] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[PARTS] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int PARTS = 8;   // upper bound; MICGPU_PARTS picks fewer (default 4)
+  cudaStream_t part_stream[PARTS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[PARTS] = {};
   // optional per-kernel timing (CUDA events on the launch stream)
   bool profiling = false;
   std::vector<cudaEvent_t> ev;
@@ -272,7 +273,8 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
     }
     loff += n;
   }
-  const int parts = (d->profiling || nu < 256) ? 1 : micgpu_decoder::PARTS;   // per-kernel timing needs one stream
+  static const int parts_cfg = [] { const char* e = getenv("MICGPU_PARTS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > micgpu_decoder::PARTS ? micgpu_decoder::PARTS : v); }();
+  const int parts = (d->profiling || nu < 256) ? 1 : parts_cfg;   // per-kernel timing needs one stream
   if (parts == 1) {
     prof_mark(d, "k_rle_expand", st);
     launch_rle_expand(du, 0, nu, (const uint16_t*)d->d_states.p, (const uint16_t*)d->d_tabS.p, (uint16_t*)d->d_D.p,
@@ -287,7 +289,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   } else {
     if (!d->ev_fork) {
       CUDA_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
-      for (int p = 0; p < parts; p++) {
+      for (int p = 0; p < micgpu_decoder::PARTS; p++) {
         CUDA_TRY(cudaStreamCreateWithFlags(&d->part_stream[p], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&d->ev_join[p], cudaEventDisableTiming));
       }

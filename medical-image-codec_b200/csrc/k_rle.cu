@@ -158,9 +158,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       const int ph = spatial ? (int)((pix + align0 + 8u - (unsigned)skip) & 7u) : 0;
       uint16_t* se = s_e_raw + ph;
       // ---------------- B: header walk + expansion (warp 0) -----------------
-      // The walk is the serial part: ~200 cycles per run.  Run-heavy streams (temporal residuals: a run every ~5
-      // elements, 1.25 M runs per tomo frame) are bound by it -- 86 % of the kernel's samples are the other warps waiting
-      // at the barrier below (profiles/README.md); expanding short runs inside the walk did not change that.
+      // The walk is the serial part.  Run-heavy streams (temporal residuals: a run every ~5 elements, 1.25 M runs per
+      // tomo frame) are bound by it -- 70-86 % of the kernel's samples are the other warps waiting at the barrier below.
       if (warp == 0) {
         int ip = ws.ipos;
         const int wb = ws.wbase, we = ws.wend;
@@ -174,7 +173,53 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           if (budget == 0) done = 1;
         }
         int nr = 0;
+        bool slow_once = false;
         while (o < budget && nr < MAXR) {
+          // Fast block: 32 symbols in registers, one per lane; the header chain inside them is followed with one
+          // shuffle per run (c is warp-uniform after the shuffle, so every branch below is uniform).  The scalar
+          // iteration further down costs ~450 cycles per run (two dependent shared-memory loads, three stores, a dozen
+          // conditions); run-heavy streams -- temporal residuals have a run every ~5 symbols -- spent 86 % of this
+          // kernel waiting for it (profiles/README.md).  Everything irregular (carry-in, window or stream end, a zero
+          // count) is left to the scalar iteration.
+          if (c_rem == 0 && !slow_once && ip + 33 <= we && ip + 33 <= nsym && nr + 16 <= MAXR) {
+            const unsigned cl = s_in[ip - wb + lane];
+            int p = 0;
+            bool stop = false;
+            while (p < 31 && !stop) {
+              const unsigned c = __shfl_sync(0xffffffffu, cl, p);
+              const unsigned v = __shfl_sync(0xffffffffu, cl, p + 1);
+              if (c == 0) { slow_once = true; break; }          // malformed: the scalar path reports it
+              const int room = budget - o;
+              if (c <= mid) {
+                const int take = min((int)c, room);
+                if (take <= 32) {                                // short run: expanded right here, not listed
+                  if (lane < take) se[o + lane] = (uint16_t)v;
+                } else {
+                  if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = -(int)(v + 1u); }
+                  nr++;
+                }
+                o += take; p += 2;
+                if (take < (int)c) { c_rem = c - (unsigned)take; kind = 0; value = v; stop = true; }
+              } else {
+                const int len = (int)(c - mid);
+                const int first = ip + p + 1;                    // stream index of the payload
+                const int take = min(min(len, room), we - first);   // we - first >= 1 inside the block
+                if (take <= 32) {
+                  if (lane < take) se[o + lane] = s_in[first - wb + lane];
+                } else {
+                  if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = first - wb; }
+                  nr++;
+                }
+                o += take;
+                if (take < len) { c_rem = (unsigned)(len - take); kind = 1; p += 1 + take; stop = true; }
+                else p += 1 + len;
+              }
+              if (o >= budget) stop = true;
+            }
+            ip += p;
+            if (!slow_once) continue;
+          }
+          slow_once = false;
           if (c_rem == 0) {
             if (ip >= nsym) { done = 1; break; }
             if (ip >= we) break;
@@ -207,7 +252,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           o += take;
           c_rem -= (unsigned)take;
         }
-        if (!restage && o == 0 && nr == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
+        if (!restage && o == 0 && !done && !(we < nsym && we - ip < IN_N / 2)) { err = 1; done = 1; }  // no progress possible
         if (lane == 0) {
           ws.ipos = ip; ws.c_rem = c_rem; ws.kind = kind; ws.value = value;
           ws.nout = o; ws.nruns = nr; ws.done = done; ws.err = err;

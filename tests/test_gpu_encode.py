@@ -251,3 +251,16 @@ def test_uncodable_stream_fails_like_the_reference(mic, oracle):
     y, x = np.mgrid[0:64, 0:64]
     good = np.stack([(1000 + 3 * x + 5 * y + rng.integers(0, 8, (64, 64))).astype(np.uint16) for _ in range(2)])
     assert mic.CompressMultiFrame(good, 64, 64, 4095, True) == oracle.mic2_compress(good.ravel(), 64, 64, 4095, True)
+
+
+def test_pics_batch_encode_threaded_contexts(mic, oracle, synth):
+    """A batch of >= 16 images and >= 64 MB goes through several encoder contexts on worker threads; every image must
+    still be byte-identical to the reference encoder, in order."""
+    w, h = 2048, 1024
+    base = [synth.xr_image(70 + i, w, h).ravel() for i in range(2)]
+    imgs = [base[i % 2] for i in range(17)]
+    blobs = mic.CompressParallelStripsBatch(imgs, w, h, [int(i.max()) for i in imgs], 8, 8)
+    want = [oracle.pics_compress(b, w, h, int(b.max()), 8, 8) for b in base]
+    assert len(blobs) == 17
+    for i, b in enumerate(blobs):
+        assert b == want[i % 2], f"image {i}"

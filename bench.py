@@ -296,6 +296,7 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     ms_dev = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
+    launches = dec.last_launches      # kernels of one timed step (K1, K2, then K3 + K4 for each of the four unit ranges)
 
     # per-kernel breakdown (separate pass, CUDA events between launches on the same stream)
     dec.set_profiling(True)
@@ -306,7 +307,6 @@ def run_ours(args, rank, local_rank, world):
         for name, ms in dec.kernel_times():
             acc[name] = acc.get(name, 0.0) + ms / prof_iters
     dec.set_profiling(False)
-    launches = dec.last_launches
 
     # ---- end-to-end arm: C-ABI host call, pinned host buffers, copies inside the timed region ----
     bp = (C.c_void_p * n)(*[h_comp_ptr + o for o in offs])

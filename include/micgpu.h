@@ -82,6 +82,19 @@ int micgpu_decoder_add_mic2_range(micgpu_decoder *d, const uint8_t *mic2, size_t
                                   int first_frame, int frame_count, int *width, int *height, int *frames, int *temporal);
 /* d_frames[f][i] += d_carry[i] (mod 2^16) for nframes frames of frame_px pixels, both in device memory. */
 int micgpu_temporal_add_carry(void *d_frames, const void *d_carry, uint64_t frame_px, int nframes, void *cuda_stream);
+/* The same step fused with the exchange: d_peer_last[q] (q < npeers <= 16) is the last frame of earlier range q, readable
+ * from this GPU -- local memory, or the memory of a peer GPU opened with micgpu_ipc_open; the kernel reads them over
+ * NVLink, forms the carry and finishes the local frames in one pass.  The caller makes sure the peers have finished
+ * writing those frames (a host barrier after their decode) and keeps them alive until this stream has run. */
+int micgpu_temporal_add_carry_peers(void *d_frames, const void *const *d_peer_last, int npeers, uint64_t frame_px, int nframes,
+                                    void *cuda_stream);
+/* Plain device buffers (cudaMalloc: whole allocations, which is what CUDA IPC can export) and their IPC handles
+ * (64 opaque bytes) for the exchange above between one-process-per-GPU ranks of one node. */
+void *micgpu_device_alloc(size_t bytes);
+void micgpu_device_free(void *p);
+int micgpu_ipc_export(const void *d_ptr, void *handle64);
+int micgpu_ipc_open(const void *handle64, void **d_ptr);
+int micgpu_ipc_close(void *d_ptr);
 /* Size scratch for the plan.  Must be called after the last add_*. */
 int micgpu_decoder_commit(micgpu_decoder *d);
 int micgpu_decoder_unit_count(const micgpu_decoder *d);

@@ -37,5 +37,11 @@ from .api import (  # noqa: F401
     DecompressSingleFrame,
     MicGpuError,
     temporal_add_carry,
+    temporal_add_carry_peers,
+    device_alloc,
+    device_free,
+    ipc_export,
+    ipc_open,
+    ipc_close,
     lib,
 )

@@ -58,6 +58,14 @@ lib.micgpu_decoder_add_pics.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_
 lib.micgpu_decoder_add_mic2.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, _ip, _ip, _ip, _ip]
 lib.micgpu_decoder_add_mic2_range.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _ip, _ip, _ip, _ip]
 lib.micgpu_temporal_add_carry.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+lib.micgpu_temporal_add_carry_peers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint64, C.c_int, C.c_void_p]
+lib.micgpu_device_alloc.argtypes = [C.c_size_t]
+lib.micgpu_device_alloc.restype = C.c_void_p
+lib.micgpu_device_free.argtypes = [C.c_void_p]
+lib.micgpu_device_free.restype = None
+lib.micgpu_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+lib.micgpu_ipc_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+lib.micgpu_ipc_close.argtypes = [C.c_void_p]
 lib.micgpu_decoder_commit.argtypes = [C.c_void_p]
 lib.micgpu_decoder_unit_count.argtypes = [C.c_void_p]
 lib.micgpu_decoder_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -112,6 +120,40 @@ lib.mic_decompress_parallel_scalar.argtypes = [C.c_void_p, C.c_size_t, C.c_void_
 def temporal_add_carry(d_frames_ptr: int, d_carry_ptr: int, frame_px: int, nframes: int, stream_ptr: int = 0):
     """frames[f] += carry (mod 2^16) on device pointers: the exchange step of a sharded temporal MIC2 stack."""
     _check(lib.micgpu_temporal_add_carry(d_frames_ptr, d_carry_ptr, frame_px, nframes, stream_ptr))
+
+
+def temporal_add_carry_peers(d_frames_ptr: int, peer_last_ptrs, frame_px: int, nframes: int, stream_ptr: int = 0):
+    """Fused exchange: frames[f] += sum of the peers' last frames (device pointers, possibly on peer GPUs)."""
+    n = len(peer_last_ptrs)
+    arr = (C.c_void_p * max(n, 1))(*peer_last_ptrs)
+    _check(lib.micgpu_temporal_add_carry_peers(d_frames_ptr, arr, n, frame_px, nframes, stream_ptr))
+
+
+def device_alloc(nbytes: int) -> int:
+    p = lib.micgpu_device_alloc(nbytes)
+    if not p:
+        raise MicGpuError(E_ALLOC, last_error())
+    return p
+
+
+def device_free(ptr: int):
+    lib.micgpu_device_free(ptr)
+
+
+def ipc_export(d_ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    _check(lib.micgpu_ipc_export(d_ptr, buf))
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    _check(lib.micgpu_ipc_open(C.create_string_buffer(handle, 64), C.byref(p)))
+    return p.value
+
+
+def ipc_close(d_ptr: int):
+    _check(lib.micgpu_ipc_close(d_ptr))
 
 
 def last_error() -> str:

@@ -49,6 +49,50 @@ k_temporal_add_carry(uint16_t* __restrict__ frames, const uint16_t* __restrict__
   }
 }
 
+// The exchange fused with its consumer: the carry of this range is the sum of the last frames of the ranges before it, and
+// those frames sit in the memory of the peer GPUs.  One kernel reads them over NVLink (peer pointers opened through CUDA
+// IPC, coalesced 16 B loads), forms the carry and finishes every local frame -- no staging copy, no separate collective.
+__global__ void __launch_bounds__(256)
+k_temporal_add_carry_peers(uint16_t* __restrict__ frames, PeerFrames peers, unsigned long long fpx, int nframes) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 8ull;
+  for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 8ull; i0 < fpx; i0 += stride) {
+    if (i0 + 8 <= fpx && peers.aligned) {
+      uint32_t c[4] = {0, 0, 0, 0};     // two u16 lanes per word, added lane-wise mod 2^16
+      for (int q = 0; q < peers.n; q++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(peers.last[q] + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) c[j] = ((c[j] + (w[j] & 0xFFFFu)) & 0xFFFFu) | ((c[j] & 0xFFFF0000u) + (w[j] & 0xFFFF0000u));
+      }
+      for (int f = 0; f < nframes; f++) {
+        uint4* p = reinterpret_cast<uint4*>(frames + (unsigned long long)f * fpx + i0);
+        uint4 v = *p;
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = ((w[j] + (c[j] & 0xFFFFu)) & 0xFFFFu) | ((w[j] & 0xFFFF0000u) + (c[j] & 0xFFFF0000u));
+        *p = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      for (unsigned long long i = i0; i < fpx && i < i0 + 8; i++) {
+        unsigned c = 0;
+        for (int q = 0; q < peers.n; q++) c += peers.last[q][i];
+        for (int f = 0; f < nframes; f++) {
+          const unsigned long long at = (unsigned long long)f * fpx + i;
+          frames[at] = (uint16_t)(frames[at] + c);
+        }
+      }
+    }
+  }
+}
+
+void launch_temporal_add_carry_peers(uint16_t* d_frames, const PeerFrames& peers, unsigned long long fpx, int nframes, int sm_count,
+                                     cudaStream_t st) {
+  if (nframes <= 0 || fpx == 0 || peers.n <= 0) return;
+  unsigned long long blocks = (fpx / 8 + 255) / 256 + 1;
+  if (blocks > (unsigned long long)sm_count * 8) blocks = (unsigned long long)sm_count * 8;
+  k_temporal_add_carry_peers<<<(unsigned)blocks, 256, 0, st>>>(d_frames, peers, fpx, nframes);
+}
+
 void launch_temporal_add_carry(uint16_t* d_frames, const uint16_t* d_carry, unsigned long long fpx, int nframes, int sm_count,
                                cudaStream_t st) {
   if (nframes <= 0 || fpx == 0) return;

@@ -37,6 +37,14 @@ int delta_wavefront_threads(int max_width, int max_height);
 // In-place frame-axis running sum for temporal MIC2 (frames contiguous, fpx pixels each).
 void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int first_is_residual, int sm_count,
                                 cudaStream_t st);
+// Last frames of the ranges before this one, readable from this GPU (local or peer memory), for the fused carry kernel.
+struct PeerFrames {
+  const uint16_t* last[16];
+  int n;
+  int aligned;     // every pointer, the frame buffer and frame_px allow 16 B accesses
+};
+void launch_temporal_add_carry_peers(uint16_t* d_frames, const PeerFrames& peers, unsigned long long fpx, int nframes, int sm_count,
+                                     cudaStream_t st);
 // frames[f] += carry (mod 2^16) for a shard of a temporal stack decoded relative to a zero carry
 void launch_temporal_add_carry(uint16_t* d_frames, const uint16_t* d_carry, unsigned long long fpx, int nframes, int sm_count,
                                cudaStream_t st);

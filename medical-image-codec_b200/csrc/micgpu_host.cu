@@ -591,6 +591,63 @@ int micgpu_temporal_add_carry(void* d_frames, const void* d_carry, uint64_t fram
   return 0;
 }
 
+int micgpu_temporal_add_carry_peers(void* d_frames, const void* const* d_peer_last, int npeers, uint64_t frame_px, int nframes,
+                                    void* cuda_stream) {
+  if (!d_frames || (npeers > 0 && !d_peer_last)) return fail(MICGPU_E_HEADER, "null argument");
+  if (npeers < 0 || npeers > 16) return fail(MICGPU_E_HEADER, "at most 16 earlier ranges (got %d)", npeers);
+  if (npeers == 0) return 0;
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PeerFrames pf;
+  pf.n = npeers;
+  pf.aligned = (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0) && (frame_px % 8 == 0);
+  for (int q = 0; q < npeers; q++) {
+    if (!d_peer_last[q]) return fail(MICGPU_E_HEADER, "null peer frame %d", q);
+    pf.last[q] = (const uint16_t*)d_peer_last[q];
+    if (reinterpret_cast<uintptr_t>(d_peer_last[q]) % 16) pf.aligned = 0;
+  }
+  launch_temporal_add_carry_peers((uint16_t*)d_frames, pf, frame_px, nframes, sms, (cudaStream_t)cuda_stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+void* micgpu_device_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail(MICGPU_E_ALLOC, "cudaMalloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void micgpu_device_free(void* p) {
+  if (p) cudaFree(p);
+}
+
+int micgpu_ipc_export(const void* d_ptr, void* handle64) {
+  if (!d_ptr || !handle64) return fail(MICGPU_E_HEADER, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int micgpu_ipc_open(const void* handle64, void** d_ptr) {
+  if (!handle64 || !d_ptr) return fail(MICGPU_E_HEADER, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int micgpu_ipc_close(void* d_ptr) {
+  if (!d_ptr) return 0;
+  CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+}
+
 int micgpu_decoder_commit(micgpu_decoder* d) {
   if (!d) return fail(MICGPU_E_HEADER, "null decoder");
   std::lock_guard<std::mutex> lk(d->mu);

@@ -264,3 +264,35 @@ def test_mic2_temporal_sharded_ranges(mic, oracle, synth, cuts):
         torch.cuda.synchronize()
         got = d_out.cpu().numpy().view(np.uint16)[: (hi - lo) * fpx]
         assert np.array_equal(got, st[lo:hi].ravel()), f"range {lo}:{hi}"
+
+
+def test_temporal_carry_fused_over_peer_pointers(mic, oracle, synth):
+    """The fused form of the exchange: one kernel reads the last frames of the earlier ranges (here: other buffers on this
+    GPU, on a multi-GPU node: peer memory opened through CUDA IPC) and finishes the local frames.  Also checks that a
+    library-allocated buffer exports an IPC handle."""
+    import torch
+
+    w, h, nf = 96, 80, 7        # frame_px % 8 == 0: vector path; the second stack exercises the scalar path
+    for (ww, hh) in ((w, h), (97, 41)):
+        st = synth.tomo_stack(5, nf, ww, hh)
+        fpx = ww * hh
+        full = st.reshape(nf, fpx).astype(np.uint16)
+        cuts = (0, 2, 3, 7)
+        # relative sums of every range, as micgpu_decoder_add_mic2_range + run_device leave them
+        rel = [full[lo:hi].copy() if lo == 0 else (full[lo:hi] - full[lo - 1]).astype(np.uint16) for lo, hi in zip(cuts[:-1], cuts[1:])]
+        lasts = []
+        for r in rel:
+            p = mic.device_alloc(fpx * 2)
+            t = torch.from_numpy(r[-1].astype(np.int16)).cuda()
+            lasts.append((p, t))      # p: a library allocation (IPC-exportable); t: the frame itself
+        stream = torch.cuda.current_stream().cuda_stream
+        for k in range(1, len(rel)):
+            d = torch.from_numpy(rel[k].astype(np.int16)).cuda().contiguous()
+            mic.temporal_add_carry_peers(d.data_ptr(), [lasts[q][1].data_ptr() for q in range(k)], fpx, rel[k].shape[0], stream)
+            torch.cuda.synchronize()
+            lo, hi = cuts[k], cuts[k + 1]
+            assert np.array_equal(d.cpu().numpy().view(np.uint16), full[lo:hi]), (ww, hh, k)
+        handle = mic.ipc_export(lasts[0][0])
+        assert len(handle) == 64 and any(handle)
+        for p, _ in lasts:
+            mic.device_free(p)

@@ -53,7 +53,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
              uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue, int ubase) {
   __shared__ __align__(16) uint16_t s_in[IN_N];
   __shared__ __align__(16) uint16_t s_e_raw[OUT_CH + 16];
-  __shared__ __align__(16) uint16_t s_p[OUT_CH];
+  // the compaction buffer of the exact (slow) path shares s_in: that path is rare and forces the window to be restaged
+  uint16_t* const s_p = s_in;
   __shared__ int s_ui;
   __shared__ uint32_t s_non[NWIN], s_mark[NWIN];
   __shared__ int s_wprev[NWIN], s_pixbase[NWIN + 1];
@@ -118,12 +119,14 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     unsigned long long pix = 0;        // pixels (spatial) or elements (RLE) emitted so far
     unsigned carry_m = 0;              // last element of the previous chunk was a marker
     bool first = true;
+    bool window_clobbered = false;
     __syncthreads();
 
     while (true) {
       // ---------------- A: (re)stage the symbol window ----------------------
       const int ipos = ws.ipos, wend0 = ws.wend;
-      const bool restage = first || (wend0 < nsym && wend0 - ipos < IN_N / 2);
+      const bool restage = first || window_clobbered || (wend0 < nsym && wend0 - ipos < IN_N / 2);
+      window_clobbered = false;
       __syncthreads();
       if (restage) {
         // window = [a0, a0 + nb): starts on a 16 B boundary of the state stream (sym_off is a multiple of 16 elements)
@@ -514,6 +517,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           }
         }
       }
+      window_clobbered = true;   // s_p == s_in
       if (nout > 0) carry_m = (s_mark[(nout - 1) >> 5] >> ((nout - 1) & 31)) & 1u;
       pix += (unsigned)npix_chunk;
       if (done || pix >= npx) break;

@@ -1,0 +1,377 @@
+// k_ans_serial.cu -- K2s: tANS decode of 1-, 2- and 4-state streams with ONE THREAD PER UNIT.
+//
+// Replaces decompress (fsedecompressu16.go:267-377), decompress2State (fse2state.go:203-308) and
+// decompress4State (fse4state.go:195-353) for the streams the Go API emits by default:
+// CompressParallelStrips, CompressSingleFrame (MIC2 frames, MIC3 tile planes) and compressResidualFrame all
+// try the two-state coder first and fall back to the single-state one (multiframecompress.go:15-35,145-162).
+//
+// Why not lanes = states as in k_ans.cu: a round of the lane-parallel kernel costs ~170 cycles whatever N is
+// (table lookup -> nbBits -> cross-lane prefix through shared memory -> window select -> next state), so a 2-state
+// stream advances 2 symbols per 170 cycles.  With the N states of a unit in the registers of one thread the
+// cross-lane exchange disappears: the bit position chains through N integer subtractions, the N table lookups of a
+// round are issued back to back, and the fields of a round (<= 32 bits for N <= 2, <= 64 for N = 4) come out of a
+// two- or three-register window with one select and one funnel shift each.  The chain per round is one
+// shared-memory load plus ~8 dependent ALU instructions (~70 cycles for N <= 2).  Throughput is (resident units) /
+// (round latency), and residency is bounded by shared memory (the decode tables), exactly as for k_ans.cu.
+//
+// Everything else follows k_ans.cu: tables in shared memory as 4-byte cells (newState | nbBits << 16) or 2-byte
+// cells (direct: nbBits | (newState >> nbBits) << 4; or nextState, with a bit array for bit 16 when tableLog is
+// 16), chosen per CTA; the bitstream of a unit in a 128 B shared-memory ring of four 32 B quarters refilled with
+// cp.async; output = the state stream (table index of every symbol), K3 maps it to symbols through tabS.
+// Bit coordinates as in k_ans.cu:26-29 (bitreader.go:26-62): a field of n bits read when P bits remain unread is
+// bits [P-n, P) of the stream viewed as one little-endian integer.
+#include <type_traits>
+
+#include "mic_device.cuh"
+
+namespace micgpu {
+
+namespace {
+
+constexpr int SRING_STRIDE = 36;   // words per unit: 32 ring words + mirror of words 0..3
+constexpr int SERIAL_THREADS = 128;
+
+// Branch-free ring maintenance of one thread's unit (see ring_refill_async in k_ans.cu for the coverage proof; the
+// cadence is the same: at most 256 bits are consumed between two calls).  When the top unread bit has left quarter
+// qtop, the slot of that quarter receives quarter qtop - 4: two 16 B cp.async, plus the mirror copy for ring slot 0.
+__device__ __forceinline__ void serial_refill(int P, int& cross, uint32_t& ra, uint32_t& qo, int& hidx, const uint8_t*& srcp,
+                                              uint32_t ring_sa) {
+  asm volatile(
+      "{\n\t.reg .pred p, pl, q, pp;\n\t"
+      "setp.le.s32 p, %5, %0;\n\t"
+      "setp.ge.and.s32 pl, %3, 0, p;\n\t"
+      "setp.eq.and.u32 q, %2, 0, pl;\n\t"
+      "@pl cp.async.ca.shared.global [%1], [%4], 16;\n\t"
+      "@pl cp.async.ca.shared.global [%1+16], [%4+16], 16;\n\t"
+      "@q cp.async.ca.shared.global [%1+128], [%4], 16;\n\t"
+      "cp.async.commit_group;\n\t"
+      "cp.async.wait_group 2;\n\t"
+      "setp.ge.and.s32 pp, %3, 8, p;\n\t"
+      "@pp prefetch.global.L2 [%4+-256];\n\t"
+      "@p add.s32 %0, %0, -256;\n\t"
+      "@p add.s32 %3, %3, -1;\n\t"
+      "@p add.s64 %4, %4, -32;\n\t"
+      "@p add.s32 %2, %2, -32;\n\t"
+      "@p and.b32 %2, %2, 96;\n\t"
+      "add.s32 %1, %6, %2;\n\t"
+      "}\n"
+      : "+r"(cross), "+r"(ra), "+r"(qo), "+r"(hidx), "+l"(srcp)
+      : "r"(P), "r"(ring_sa)
+      : "memory");
+}
+
+// FMT: 0 = 4-byte cells, 1 = 2-byte nextState cells (+ bit 16 in a bit array when L16), 2 = 2-byte direct cells
+template <int FMT, bool L16>
+struct Cells {
+  const uint8_t* tab;
+  const uint32_t* flags;
+  uint32_t L, S;
+  __device__ __forceinline__ void get(uint32_t st, uint32_t& nb, uint32_t& ns) const {
+    if (FMT == 0) {
+      const uint32_t e = reinterpret_cast<const uint32_t*>(tab)[st];
+      nb = e >> 16; ns = e & 0xFFFFu;
+    } else if (FMT == 1) {
+      uint32_t nx = reinterpret_cast<const uint16_t*>(tab)[st];
+      if (L16) nx |= ((flags[st >> 5] >> (st & 31u)) & 1u) << 16;
+      nb = L - (31u - __clz(nx));   // nextState >= 1 (K1)
+      ns = (nx << nb) - S;
+    } else {
+      const uint32_t e = reinterpret_cast<const uint16_t*>(tab)[st];
+      nb = e & 15u; ns = (e >> 4) << nb;
+    }
+  }
+};
+
+template <int N, int FMT, bool L16>
+__device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restrict__ comp, uint16_t* __restrict__ states_out,
+                                            const uint8_t* mytab, const uint32_t* myflags, uint32_t* ring) {
+  const Cells<FMT, L16> cells{mytab, myflags, U->table_log, 1u << U->table_log};
+  const int L = (int)U->table_log;
+  const uint8_t* bs = comp + U->comp_off + U->bits_off;
+  const uint32_t blen = U->bits_len;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(bs);
+  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(addr & ~(uintptr_t)31);
+  const int shift = (int)(addr & 31) * 8;            // first data bit in ring coordinates
+  const uint32_t lastb = bs[blen - 1];               // non-zero (checked by K1)
+  int P = shift + 8 * (int)(blen - 1) + (31 - __clz(lastb | 1u));   // unread bits are [shift, P); < 2^31 (frames < 256 MB)
+  const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint8_t* ringb = reinterpret_cast<const uint8_t*>(ring);
+  const int qtop = (P - 1) >> 8;
+  int cross = qtop << 8;                             // P <= cross  <=>  the top unread bit left quarter qtop
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int q = qtop - j;
+    if (q >= 0) {
+      const uint32_t dst = ring_sa + (uint32_t)((q & 3) << 5);
+      const uint8_t* src = wbase + (size_t)q * 32;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 16) : "memory");
+      if ((q & 3) == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 128u), "l"(src) : "memory");
+    }
+  }
+  int hidx = qtop - 4;
+  const uint8_t* srcp = wbase + (ptrdiff_t)hidx * 32;
+  uint32_t qo = (uint32_t)((hidx & 3) << 5), ra = ring_sa + qo;
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+
+  // bits [lo, lo+nb) straight from the ring (start-up and tails; the hot loops use a register window)
+  auto extract = [&](int lo, uint32_t nb) -> uint32_t {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + (((uint32_t)lo >> 3) & 0x7Cu));
+    return __funnelshift_r(w[0], w[1], (uint32_t)lo & 31u) & ((1u << nb) - 1u);
+  };
+  auto refill = [&]() { serial_refill(P, cross, ra, qo, hidx, srcp, ring_sa); };
+
+  int err = 0;
+  uint32_t st[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) st[k] = 0;
+  // ---- initial states: A first, tableLog bits each (fsedecompressu16.go:387-391, fse2state.go:216-222) ----
+  if (P - shift < N * L) {
+    err = 1;
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; k++) st[k] = extract(P - (k + 1) * L, (uint32_t)L);
+    P -= N * L;
+  }
+  refill();
+  uint16_t* out = states_out + U->sym_off;
+  uint32_t nsym = 0;
+
+  // Window of NW registers loaded once per group of symbols that consume at most 32 * (NW - 1) bits: the top word
+  // holds bit P-1, so P sits at Pb in (32 (NW-1), 32 NW] and every field of the group lies inside the window.
+  constexpr int NW = N == 4 ? 3 : 2;
+  uint32_t W0 = 0, W1 = 0, W2 = 0, Pb = 0;
+  auto load_window = [&]() {
+    const uint32_t wl = (((uint32_t)(P - 1)) >> 5) - (uint32_t)(NW - 1);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + ((wl & 31u) << 2));
+    W0 = w[0]; W1 = w[1];
+    if (NW == 3) W2 = w[2];
+    Pb = (uint32_t)P - (wl << 5);
+  };
+  auto field = [&](uint32_t lo, uint32_t nb) -> uint32_t {
+    uint32_t a, b;
+    if (NW == 2) {
+      a = (lo & 32u) ? W1 : W0; b = W1;
+    } else {
+      a = (lo & 64u) ? W2 : ((lo & 32u) ? W1 : W0);
+      b = (lo & 32u) ? W2 : W1;
+    }
+    return __funnelshift_r(a, b, lo) & ((1u << nb) - 1u);
+  };
+
+  if (N == 1) {
+    // 1-state: no symbol count; the stream ends when the bits do (fsedecompressu16.go:351-376)
+    const uint32_t cap = U->sym_cap;
+    uint32_t s0 = st[0];
+    // 16 symbols (<= 256 bits) per ring check, two per window; cannot reach the end of the bits inside the group
+    while (!err && P - shift > 256 && nsym + 16 <= cap) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        load_window();
+        uint32_t nb, ns;
+        cells.get(s0, nb, ns);
+        const uint32_t e0 = s0;
+        uint32_t lo = Pb - nb;
+        s0 = ns + field(lo, nb);
+        cells.get(s0, nb, ns);
+        const uint32_t e1 = s0;
+        lo -= nb;
+        s0 = ns + field(lo, nb);
+        *reinterpret_cast<uint32_t*>(out + nsym) = e0 | (e1 << 16);
+        nsym += 2;
+        P -= (int)(Pb - lo);
+      }
+      refill();
+    }
+    while (!err) {
+      uint32_t nb, ns;
+      cells.get(s0, nb, ns);
+      if (P == shift && nb > 0) {        // decoderU16.finished()
+        if (s0 != 0) {
+          if (nsym >= cap) { err = 2; break; }
+          out[nsym++] = (uint16_t)s0;    // final()
+        }
+        break;
+      }
+      if (nsym >= cap) { err = 2; break; }
+      out[nsym++] = (uint16_t)s0;
+      if ((uint32_t)(P - shift) < nb) { err = 1; break; }   // partial over-read -> io.ErrUnexpectedEOF
+      s0 = ns + extract(P - (int)nb, nb);
+      P -= (int)nb;
+      refill();
+    }
+  } else {
+    const uint32_t count = U->count;
+    if (count > U->sym_cap) err = 2;
+    const uint32_t full = err ? 0u : count / N;
+    // one round = N symbols in stream order A, B, ...: emit the current states, then move each one
+    auto round_win = [&](uint16_t* op) {
+      load_window();
+      uint32_t nb[N], ns[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) cells.get(st[k], nb[k], ns[k]);
+      if (N == 2) {
+        *reinterpret_cast<uint32_t*>(op) = st[0] | (st[1] << 16);
+      } else {
+        *reinterpret_cast<uint2*>(op) = make_uint2(st[0] | (st[1] << 16), st[2] | (st[3] << 16));
+      }
+      uint32_t lo = Pb;
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        lo -= nb[k];
+        st[k] = ns[k] + field(lo, nb[k]);
+      }
+      P -= (int)(Pb - lo);
+    };
+    constexpr uint32_t RPC = 16 / N;    // rounds per ring check: RPC * N * 16 = 256 bits
+    uint32_t r = 0;
+    uint16_t* op = out;
+    for (; r + RPC <= full; r += RPC) {
+#pragma unroll
+      for (uint32_t j = 0; j < RPC; j++) round_win(op + j * N);
+      op += RPC * N;
+      refill();
+      if (P < shift) break;             // over-read (corrupt stream): reads stayed inside the ring, writes inside sym_cap
+    }
+    if (P >= shift) {
+      for (; r < full; r++) {
+        round_win(op);
+        op += N;
+        refill();
+      }
+      const uint32_t tail = err ? 0u : count - full * N;
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        if ((uint32_t)k < tail) {
+          uint32_t nb, ns;
+          cells.get(st[k], nb, ns);
+          op[k] = (uint16_t)st[k];
+          P -= (int)nb;
+        }
+      }
+    }
+    if (P < shift && !err) err = 1;
+    nsym = count;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // no copy may land in the ring after the next unit took it over
+  U->nsym = nsym;
+  if (err) U->status = err == 1 ? MIC_E_BITSTREAM : MIC_E_SIZE;
+}
+
+}  // namespace
+
+// mode: 0 = 4-byte cells, 1 = 2-byte cells.  Slots are dealt round-robin over the warps (slot = lane * nwarps + warp) so
+// that every scheduler of the SM gets its share of the units.
+template <int N>
+__global__ void __launch_bounds__(SERIAL_THREADS)
+k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
+                    const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots, int mode) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int slot = lane * nwarps + warp;
+  const bool l16 = mode == 1 && max_log == 16;
+  const size_t tbytes = (size_t)(1u << max_log) * (mode == 0 ? 4 : 2) + (l16 ? (1u << 16) / 8 : 0);
+  uint32_t* rings = reinterpret_cast<uint32_t*>(smem + (size_t)slots * tbytes);
+
+  for (int base = blockIdx.x * slots; base < nlist; base += gridDim.x * slots) {
+    __syncthreads();   // the previous pass is done with the tables
+    // ---- stage the tables of this pass, all threads per table --------------------------------------------
+    const int npass = min(slots, nlist - base);
+    bool wide_any = false;
+    for (int s = 0; s < npass; s++) {
+      const MicUnit* V = &units[list[base + s]];
+      if (V->status != MIC_OK) continue;
+      const uint32_t L = V->table_log, S = 1u << L;
+      const uint4* A4 = reinterpret_cast<const uint4*>(tabA + V->tab_off);
+      uint8_t* T = smem + (size_t)s * tbytes;
+      if (mode == 0) {
+        uint4* T4 = reinterpret_cast<uint4*>(T);
+        for (uint32_t i = tid; i < S / 4; i += blockDim.x) T4[i] = __ldg(A4 + i);
+      } else {
+        // direct cells (k_ans.cu:469-472): valid while newState >> nbBits < 4096 and tableLog <= 15
+        uint2* T2 = reinterpret_cast<uint2*>(T);
+        uint32_t wide = L > 15 ? 4096u : 0u;
+        for (uint32_t i = tid; i < S / 4; i += blockDim.x) {
+          const uint4 e = __ldg(A4 + i);
+          const uint32_t d0 = (e.x & 0xFFFF) >> (e.x >> 16), d1 = (e.y & 0xFFFF) >> (e.y >> 16);
+          const uint32_t d2 = (e.z & 0xFFFF) >> (e.z >> 16), d3 = (e.w & 0xFFFF) >> (e.w >> 16);
+          wide |= d0 | d1 | d2 | d3;
+          T2[i] = make_uint2(((d0 << 4) | (e.x >> 16)) | (((d1 << 4) | (e.y >> 16)) << 16),
+                             ((d2 << 4) | (e.z >> 16)) | (((d3 << 4) | (e.w >> 16)) << 16));
+        }
+        wide_any |= wide >= 4096u;
+      }
+    }
+    // one cell format per CTA: direct cells if every table of the pass allows them, else nextState cells for all
+    const bool d16 = mode == 1 && !__syncthreads_or(wide_any ? 1 : 0);
+    if (mode == 1 && !d16) {
+      for (int s = 0; s < npass; s++) {
+        const MicUnit* V = &units[list[base + s]];
+        if (V->status != MIC_OK) continue;
+        const uint32_t L = V->table_log, S = 1u << L;
+        const uint4* A4 = reinterpret_cast<const uint4*>(tabA + V->tab_off);
+        uint8_t* T = smem + (size_t)s * tbytes;
+        uint2* T2 = reinterpret_cast<uint2*>(T);
+        uint32_t* F = reinterpret_cast<uint32_t*>(T + ((size_t)2 << max_log));
+        if (l16) {
+          for (uint32_t j = tid; j < (1u << 16) / 32; j += blockDim.x) F[j] = 0;
+          __syncthreads();
+        }
+        for (uint32_t i = tid; i < S / 4; i += blockDim.x) {
+          const uint4 e = __ldg(A4 + i);
+          // nextState = (newState + S) >> nbBits  (inverse of fsedecompressu16.go:250-251)
+          const uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
+          const uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
+          T2[i] = make_uint2((n0 & 0xFFFF) | (n1 << 16), (n2 & 0xFFFF) | (n3 << 16));
+          if (l16) {
+            const uint32_t hi = (n0 >> 16) | ((n1 >> 16) << 1) | ((n2 >> 16) << 2) | ((n3 >> 16) << 3);
+            if (hi) atomicOr(&F[i >> 3], hi << ((i & 7u) * 4));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- one thread per unit ----------------------------------------------------------------------------
+    if (slot < npass) {
+      MicUnit* U = &units[list[base + slot]];
+      if (U->status == MIC_OK) {
+        const uint8_t* mytab = smem + (size_t)slot * tbytes;
+        const uint32_t* myflags = reinterpret_cast<const uint32_t*>(mytab + ((size_t)2 << max_log));
+        uint32_t* ring = rings + slot * SRING_STRIDE;
+        if (mode == 0) decode_unit<N, 0, false>(U, comp, states_out, mytab, myflags, ring);
+        else if (d16) decode_unit<N, 2, false>(U, comp, states_out, mytab, myflags, ring);
+        else if (l16) decode_unit<N, 1, true>(U, comp, states_out, mytab, myflags, ring);
+        else decode_unit<N, 1, false>(U, comp, states_out, mytab, myflags, ring);
+      }
+    }
+  }
+}
+
+size_t ans_serial_smem_bytes(int max_log, int mode, int slots) {
+  size_t t = (size_t)(1u << max_log) * (mode == 0 ? 4 : 2);
+  if (mode == 1 && max_log == 16) t += (1u << 16) / 8;
+  return (size_t)slots * (t + SRING_STRIDE * 4);
+}
+
+int ans_serial_threads(int slots) {
+  // up to four warps so that each scheduler of the SM drives its own share of the units
+  const int warps = slots >= 4 ? 4 : (slots < 1 ? 1 : slots);
+  return 32 * warps;
+}
+
+void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, int nlist, int nstates, const uint8_t* d_comp,
+                              const uint32_t* d_tabA, uint16_t* d_states, int max_log, int mode, int slots, int grid,
+                              cudaStream_t st) {
+  if (nlist <= 0) return;
+  const size_t smem = ans_serial_smem_bytes(max_log, mode, slots);
+  const int threads = ans_serial_threads(slots);
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, threads, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, mode);
+  };
+  if (nstates == 1) go(k_ans_decode_serial<1>);
+  else if (nstates == 2) go(k_ans_decode_serial<2>);
+  else go(k_ans_decode_serial<4>);
+}
+
+}  // namespace micgpu

@@ -105,7 +105,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     unsigned long long outlen = 0;  // RLE kind: expected expanded length
     if (!spatial) {
       outlen = ((unsigned long long)Sy[st[1]] << 16) + Sy[st[2]];
-      if (outlen > npx) {
+      if (outlen > npx || (U->exact_len && outlen != npx)) {
         if (tid == 0) U->status = MIC_E_SIZE;
         continue;
       }

@@ -21,6 +21,13 @@ void launch_ans_decode(MicUnit* d_units, const int* d_list, int nlist, int nstat
                        int grid, cudaStream_t st);
 size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta);
 
+// Thread-per-unit decode of 1-, 2- and 4-state streams (k_ans_serial.cu).  mode: 0 = 4-byte cells, 1 = 2-byte cells;
+// slots = units per CTA (<= 128).
+void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, int nlist, int nstates, const uint8_t* d_comp,
+                              const uint32_t* d_tabA, uint16_t* d_states, int max_log, int mode, int slots, int grid,
+                              cudaStream_t st);
+size_t ans_serial_smem_bytes(int max_log, int mode, int slots);
+
 // RLE expand (+ escape split for spatial units).  Spatial units produce the
 // residual plane D (pitch wp) and the literal bit mask M; RLE units write
 // their expanded stream straight to d_out.

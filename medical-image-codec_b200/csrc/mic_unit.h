@@ -43,6 +43,8 @@ struct MicUnit {
   unsigned int sym_cap;         // capacity (elements) reserved at sym_off
   unsigned int align0;          // (output element address of pixel (0,0)) mod 8, set per run; row y of D and M
                                 // is stored at padded column a_y + x with a_y = (align0 + y*width) mod 8
+  unsigned int exact_len;       // RLE kind: 1 = the expanded length must equal `width` (a MIC2 residual frame is exactly
+                                // one frame, multiframecompress.go:165-175); 0 = `width` is only a capacity
   // ---- device-filled ----------------------------------------------------
   unsigned int bits_off;        // byte offset of the bitstream inside the frame
   unsigned int bits_len;        // bitstream length in bytes

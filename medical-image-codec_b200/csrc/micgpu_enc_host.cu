@@ -317,7 +317,8 @@ static int pics_compress_range(micgpu_encoder* e, int i0, int i1, const uint16_t
                                const uint16_t* max_values, int num_strips, int nstates, uint8_t* const* outs, const size_t* caps,
                                size_t* out_lens, int* status, std::string* msg) {
   std::lock_guard<std::mutex> lk(e->mu);
-  auto done = [&](int rc) { if (rc && msg) *msg = err_slot(); return rc; };
+  // an error return first waits for whatever this context still has in flight (copies into the caller's buffers)
+  auto done = [&](int rc) { if (rc) { cudaStreamSynchronize(e->stream); if (msg) *msg = err_slot(); } return rc; };
   const int n = i1 - i0;
   // strip geometry (parallelstrips.go:62-72)
   int ns = std::min(num_strips, height);

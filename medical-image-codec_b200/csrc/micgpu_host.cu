@@ -32,7 +32,14 @@ int nstates_index(unsigned n) { return n == 1 ? 0 : n == 2 ? 1 : n == 4 ? 2 : 3;
 
 struct AnsPlan {
   int nstates = 0, max_log = 0, mode = 0, slots = 0, grid = 0;
+  bool serial = false;   // thread-per-unit kernel (k_ans_serial.cu)
 };
+
+// Streams with at most this many states go through the thread-per-unit kernel (MICGPU_K2_SERIAL_MAXN: 0 = never, 1, 2, 4).
+int serial_max_n() {
+  static const int v = [] { const char* e = getenv("MICGPU_K2_SERIAL_MAXN"); return e ? atoi(e) : 2; }();
+  return v;
+}
 
 struct TemporalGroup {
   unsigned long long out_off, fpx;
@@ -51,6 +58,7 @@ struct micgpu_decoder {
   std::vector<int> lists[4];
   std::vector<int> spatial;
   std::vector<TemporalGroup> temporal;
+  std::vector<std::pair<unsigned long long, unsigned long long>> zero_ranges;   // output elements no unit covers (offset, count)
   AnsPlan ans[4];
   unsigned long long sym_total = 0, tab_total = 0, d_total = 0, m_total = 0, out_need = 0;
   int max_log_all = 5, max_w = 1, max_h = 1;
@@ -127,7 +135,7 @@ int plan_commit(micgpu_decoder* d) {
     const unsigned long long px = (unsigned long long)u.width * u.height;
     // symbol capacity: exact for N-state streams; for 1-state the stream is bounded by the
     // RLE worst case (every pixel escaped, plus run headers)
-    unsigned long long cap = u.nstates > 1 ? u.count : 2 * px + px / 64 + 4096;
+    unsigned long long cap = u.nstates > 1 ? u.count : 3 * px + 4096;
     if (cap > 0xFFFFFFF0ull) { u.status = MIC_E_UNSUPPORTED; cap = 0; }
     if (u.nstates > 1 && cap > 3 * px + 4096) { u.status = MIC_E_SIZE; cap = 0; }   // count cannot exceed the RLE worst case
     u.sym_cap = (unsigned)cap;
@@ -176,6 +184,26 @@ int plan_commit(micgpu_decoder* d) {
       while (s < 64 && ans_decode_smem_bytes(ml, mode, s + 1) <= budget) s++;
       return s;
     };
+    a.serial = false;
+    if (a.nstates <= serial_max_n()) {
+      auto fit_s = [&](int mode) {
+        int s = 0;
+        while (s < 128 && ans_serial_smem_bytes(ml, mode, s + 1) <= budget) s++;
+        return s;
+      };
+      const int want = std::min(need_per_sm, 128);
+      const int smode = fit_s(0) >= want ? 0 : 1;   // 2-byte cells hold twice the units per SM
+      const int f = fit_s(smode);
+      if (f >= 1) {
+        a.serial = true;
+        a.mode = smode;
+        a.slots = std::max(1, std::min(f, want));
+        const size_t per_cta = ans_serial_smem_bytes(ml, smode, a.slots) + 1024;
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>((228 * 1024) / per_cta, 16));
+        a.grid = std::min((n + a.slots - 1) / a.slots, d->sm_count * ctas_per_sm);
+        continue;
+      }
+    }
     int mode = 0;
     // 2-byte cells hold tableLog <= 15; the packed kernel (N > 1) adds a bit array for tableLog 16
     if (fit(0) < std::min(need_per_sm, slots_max)) mode = (ml <= 15 || (ml == 16 && a.nstates > 1)) && fit(1) > fit(0) ? 1 : 0;
@@ -252,6 +280,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   memcpy(d->h_units, d->units.data(), nu * sizeof(MicUnit));
   CUDA_TRY(cudaMemcpyAsync(d->d_units.p, d->h_units, nu * sizeof(MicUnit), cudaMemcpyHostToDevice, st));
   if (d->m_total) CUDA_TRY(cudaMemsetAsync(d->d_M.p, 0, d->m_total * sizeof(uint32_t), st));
+  for (const auto& z : d->zero_ranges) CUDA_TRY(cudaMemsetAsync((uint16_t*)d_out + z.first, 0, z.second * sizeof(uint16_t), st));
   MicUnit* du = (MicUnit*)d->d_units.p;
   const uint8_t* comp = (const uint8_t*)d_comp;
   d->ev_used = 0;
@@ -265,10 +294,17 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
     const int n = (int)d->lists[g].size();
     if (n) {
       const AnsPlan& a = d->ans[g];
-      static const char* NAMES[4] = {"k_ans_decode<1>", "k_ans_decode<2>", "k_ans_decode<4>", "k_ans_decode<8>"};
-      prof_mark(d, NAMES[g], st);
-      launch_ans_decode(du, dl + loff, n, a.nstates, comp, (const uint32_t*)d->d_tabA.p, (uint16_t*)d->d_states.p, a.max_log,
-                        a.mode, a.slots, a.grid, st);
+      // names as launched: the thread-per-unit kernel, the packed kernel (N > 1 with tables in shared memory), else one unit per warp
+      static const char* SERIAL[4] = {"k_ans_decode_serial<1>", "k_ans_decode_serial<2>", "k_ans_decode_serial<4>", "k_ans_decode_serial<8>"};
+      static const char* PACKED[4] = {"k_ans_decode<1>", "k_ans_decode_packed<2>", "k_ans_decode_packed<4>", "k_ans_decode_packed<8>"};
+      static const char* ONE[4] = {"k_ans_decode<1>", "k_ans_decode<2>", "k_ans_decode<4>", "k_ans_decode<8>"};
+      prof_mark(d, a.serial ? SERIAL[g] : (a.mode != 2 ? PACKED[g] : ONE[g]), st);
+      if (a.serial)
+        launch_ans_decode_serial(du, dl + loff, n, a.nstates, comp, (const uint32_t*)d->d_tabA.p, (uint16_t*)d->d_states.p, a.max_log,
+                                 a.mode, a.slots, a.grid, st);
+      else
+        launch_ans_decode(du, dl + loff, n, a.nstates, comp, (const uint32_t*)d->d_tabA.p, (uint16_t*)d->d_states.p, a.max_log,
+                          a.mode, a.slots, a.grid, st);
       d->launches++;
     }
     loff += n;
@@ -386,6 +422,12 @@ int add_pics_locked(micgpu_decoder* d, const uint8_t* pics, size_t len, uint64_t
     add_unit_locked(d, pics + start, sl, comp_off + start, MIC_KIND_SPATIAL, (uint32_t)ph.w, (uint32_t)sh,
                     out_off + (uint64_t)y0 * ph.w);
   }
+  // A strip table that stops short of the image leaves the remaining rows as make() left them: zero
+  // (parallelstrips.go:288).  The output buffer here is recycled scratch, so those rows are cleared explicitly.
+  const unsigned long long covered = std::min<unsigned long long>((unsigned long long)ph.nstrips * ph.strip_h, (unsigned long long)ph.h);
+  if (covered < (unsigned long long)ph.h)
+    d->zero_ranges.push_back({out_off + covered * ph.w, ((unsigned long long)ph.h - covered) * ph.w});
+  d->out_need = std::max<unsigned long long>(d->out_need, out_off + (unsigned long long)ph.w * ph.h);
   if (w) *w = ph.w;
   if (h) *h = ph.h;
   return 0;
@@ -413,16 +455,18 @@ int add_mic2_locked(micgpu_decoder* d, const uint8_t* p, size_t len, uint64_t co
   int rc = parse_mic2(p, len, mh);
   if (rc) return rc;
   const unsigned long long fpx = (unsigned long long)mh.w * mh.h;
-  const int nf = last_frame < 0 ? mh.n : std::min(mh.n, last_frame + 1);
+  const int nf = last_frame < 0 ? mh.n : (int)std::min<long long>(mh.n, (long long)last_frame + 1);
   if (first_frame < 0 || first_frame > nf) return fail(MICGPU_E_HEADER, "MIC2: frame range starts at %d of %d", first_frame, nf);
+  if ((unsigned long long)mh.w * mh.h > 0xFFFFFFFFull) return fail(MICGPU_E_UNSUPPORTED, "MIC2: frames of %dx%d pixels", mh.w, mh.h);
   out_off -= (uint64_t)first_frame * fpx;   // frame i lands at out_off + (i - first_frame) * fpx
   for (int i = first_frame; i < nf; i++) {
     const size_t o = rd32(p + 20 + (size_t)i * 8), l = rd32(p + 24 + (size_t)i * 8);
-    if (mh.data_off + o + l > len) return fail(MICGPU_E_HEADER, "MIC2: frame %d data extends beyond file", i);
+    if (o > len - mh.data_off || l > len - mh.data_off - o) return fail(MICGPU_E_HEADER, "MIC2: frame %d data extends beyond file", i);
     const bool residual = mh.temporal && i > 0;
     // residual frames expand to exactly w*h ZigZag words (multiframecompress.go:165-175)
-    add_unit_locked(d, p + mh.data_off + o, l, comp_off + mh.data_off + o, residual ? MIC_KIND_RLE : MIC_KIND_SPATIAL,
-                    residual ? (uint32_t)fpx : (uint32_t)mh.w, residual ? 1u : (uint32_t)mh.h, out_off + (uint64_t)i * fpx);
+    const int ui = add_unit_locked(d, p + mh.data_off + o, l, comp_off + mh.data_off + o, residual ? MIC_KIND_RLE : MIC_KIND_SPATIAL,
+                                   residual ? (uint32_t)fpx : (uint32_t)mh.w, residual ? 1u : (uint32_t)mh.h, out_off + (uint64_t)i * fpx);
+    if (residual) d->units[ui].exact_len = 1;   // a shorter residual frame would leave stale scratch in the running sum
   }
   const int count = nf - first_frame;
   if (mh.temporal && (count > 1 || (count == 1 && first_frame > 0)))
@@ -531,6 +575,7 @@ int micgpu_decoder_begin(micgpu_decoder* d) {
   std::lock_guard<std::mutex> lk(d->mu);
   d->units.clear();
   d->temporal.clear();
+  d->zero_ranges.clear();
   d->out_need = 0;
   d->committed = false;
   return 0;
@@ -571,9 +616,13 @@ int micgpu_decoder_add_mic2_range(micgpu_decoder* d, const uint8_t* mic2, size_t
   if (first_frame < 0 || frame_count < 0) return fail(MICGPU_E_HEADER, "MIC2: negative frame range");
   std::lock_guard<std::mutex> lk(d->mu);
   Mic2Header mh;
-  int rc = add_mic2_locked(d, mic2, len, comp_off, out_off, first_frame + frame_count - 1, mh, first_frame);
+  int rc = parse_mic2(mic2, len, mh);
   if (rc) return rc;
-  if (first_frame + frame_count > mh.n) return fail(MICGPU_E_HEADER, "MIC2: frame range %d+%d exceeds %d frames", first_frame, frame_count, mh.n);
+  // validated in 64 bits before any unit is added, so a failed call leaves the plan as it was
+  if ((long long)first_frame + frame_count > mh.n) return fail(MICGPU_E_HEADER, "MIC2: frame range %d+%d exceeds %d frames", first_frame, frame_count, mh.n);
+  const size_t units_before = d->units.size(), temporal_before = d->temporal.size();
+  rc = add_mic2_locked(d, mic2, len, comp_off, out_off, first_frame + frame_count - 1, mh, first_frame);
+  if (rc) { d->units.resize(units_before); d->temporal.resize(temporal_before); return rc; }
   if (width) *width = mh.w;
   if (height) *height = mh.h;
   if (frames) *frames = mh.n;
@@ -717,6 +766,10 @@ struct PicsPending {
   bool active = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // MICGPU_TRACE: start, H2D done, kernels done, D2H done
   double t_enq0 = 0, t_enq1 = 0;
+  ~PicsPending() {
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
 };
 
 bool trace_on() {
@@ -739,6 +792,7 @@ int pics_enqueue(micgpu_decoder* d, int i0, int i1, const uint8_t* const* blobs,
   P.t_enq0 = trace_on() ? host_ms() : 0;
   d->units.clear();
   d->temporal.clear();
+  d->zero_ranges.clear();
   d->out_need = 0;
   // layout: blobs back to back (64-byte aligned) in one device buffer; outputs back to back
   std::vector<uint64_t> coff(n), ooff(n + 1);
@@ -752,10 +806,12 @@ int pics_enqueue(micgpu_decoder* d, int i0, int i1, const uint8_t* const* blobs,
     ooff[k] = otot;
     P.first_unit[k] = (int)d->units.size();
     int w = 0, h = 0;
+    const size_t zr_before = d->zero_ranges.size();
+    const unsigned long long need_before = d->out_need;
     P.hdr_rc[k] = add_pics_locked(d, blobs[i], lens[i], ctot, otot, &w, &h);
     if (!P.hdr_rc[k] && (size_t)w * h > caps[i]) P.hdr_rc[k] = fail(MICGPU_E_SIZE, "image %d: output buffer too small", i);
     if (!P.hdr_rc[k]) otot += (uint64_t)w * h;
-    else d->units.resize(P.first_unit[k]);
+    else { d->units.resize(P.first_unit[k]); d->zero_ranges.resize(zr_before); d->out_need = need_before; }
     ctot += (lens[i] + 63) & ~(size_t)63;
   }
   ooff[n] = otot;
@@ -842,8 +898,8 @@ int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_
     if (!d) return MICGPU_E_CUDA;
     std::lock_guard<std::mutex> lk(d->mu);
     PicsPending P;
-    if ((rc = pics_enqueue(d, 0, n, blobs, lens, outs, caps, P))) return rc;
-    if ((rc = pics_finish(d, P, status, &first))) return rc;
+    if ((rc = pics_enqueue(d, 0, n, blobs, lens, outs, caps, P))) { cudaStreamSynchronize(d->stream); return rc; }
+    if ((rc = pics_finish(d, P, status, &first))) { cudaStreamSynchronize(d->stream); return rc; }
     return first;
   }
   // Pipelined: ~16 chunks over PIPE_DEPTH decoder contexts (each with its own stream and scratch).  The ANS stage of a
@@ -858,17 +914,26 @@ int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_
     if (!(D[k] = pipe_decoder(dev, k))) return MICGPU_E_CUDA;
   std::unique_lock<std::mutex> locks[PIPE_DEPTH];
   for (int k = 0; k < PIPE_DEPTH; k++) locks[k] = std::unique_lock<std::mutex>(D[k]->mu);
+  // An error in one chunk must not leave kernels and device->host copies of the other contexts running into the
+  // caller's buffers after the call has returned (their locks and the PicsPending array die with this frame).
+  auto drain = [&]() {
+    for (int k = 0; k < PIPE_DEPTH; k++) {
+      cudaSetDevice(D[k]->device);
+      cudaStreamSynchronize(D[k]->stream);
+      P[k].active = false;
+    }
+  };
   int c = 0, size = std::max(2, chunk / 4);
   for (int i0 = 0; i0 < n; c++) {
     const int k = c % PIPE_DEPTH;
     const int i1 = std::min(n, i0 + size);
-    if ((rc = pics_finish(D[k], P[k], status, &first))) return rc;
-    if ((rc = pics_enqueue(D[k], i0, i1, blobs, lens, outs, caps, P[k]))) return rc;
+    if ((rc = pics_finish(D[k], P[k], status, &first))) { drain(); return rc; }
+    if ((rc = pics_enqueue(D[k], i0, i1, blobs, lens, outs, caps, P[k]))) { drain(); return rc; }
     i0 = i1;
     size = std::min(chunk, size * 2);
   }
   for (int k = 0; k < PIPE_DEPTH; k++)
-    if ((rc = pics_finish(D[k], P[k], status, &first))) return rc;
+    if ((rc = pics_finish(D[k], P[k], status, &first))) { drain(); return rc; }
   return first;
 }
 
@@ -889,6 +954,7 @@ int micgpu_decompress_single_frame(const uint8_t* frame, size_t len, uint16_t* p
   std::lock_guard<std::mutex> lk(d->mu);
   d->units.clear();
   d->temporal.clear();
+  d->zero_ranges.clear();
   d->out_need = 0;
   add_unit_locked(d, frame, len, 0, MIC_KIND_SPATIAL, (uint32_t)width, (uint32_t)height, 0);
   int rc = plan_commit(d);
@@ -904,6 +970,7 @@ static int mic2_decode(const uint8_t* mic2, size_t len, int last_frame, bool onl
   std::lock_guard<std::mutex> lk(d->mu);
   d->units.clear();
   d->temporal.clear();
+  d->zero_ranges.clear();
   d->out_need = 0;
   Mic2Header mh;
   int rc = parse_mic2(mic2, len, mh);
@@ -918,7 +985,7 @@ static int mic2_decode(const uint8_t* mic2, size_t len, int last_frame, bool onl
   if (only_last && !mh.temporal) {
     // independent mode: decode just the requested frame (multiframecompress.go:277-288)
     const size_t o = rd32(mic2 + 20 + (size_t)last_frame * 8), l = rd32(mic2 + 24 + (size_t)last_frame * 8);
-    if (mh.data_off + o + l > len) return fail(MICGPU_E_HEADER, "MIC2: frame %d data extends beyond file", last_frame);
+    if (o > len - mh.data_off || l > len - mh.data_off - o) return fail(MICGPU_E_HEADER, "MIC2: frame %d data extends beyond file", last_frame);
     add_unit_locked(d, mic2 + mh.data_off + o, l, mh.data_off + o, MIC_KIND_SPATIAL, (uint32_t)mh.w, (uint32_t)mh.h, 0);
     nout = 1;
   } else {
@@ -979,6 +1046,18 @@ int parse_mic3(const uint8_t* p, size_t len, Mic3Header& h) {
   if (h.total_tiles > (len - h.table_off) / 16) return fail(MICGPU_E_HEADER, "MIC3: truncated tile offset table");
   h.data_off = h.table_off + (size_t)h.total_tiles * 16;
   if (h.tile_w <= 0 || h.tile_h <= 0 || h.width <= 0 || h.height <= 0) return fail(MICGPU_E_HEADER, "MIC3: invalid dimensions");
+  if (h.tile_w > 32768 || h.tile_h > 32768) return fail(MICGPU_E_UNSUPPORTED, "MIC3: tile size %dx%d", h.tile_w, h.tile_h);
+  if (h.nlv > MICGPU_WSI_MAX_LEVELS) return fail(MICGPU_E_UNSUPPORTED, "MIC3: %d pyramid levels (at most %d)", h.nlv, MICGPU_WSI_MAX_LEVELS);
+  // Level descriptors are file data: every field a later index computation relies on is checked here (the Go reader
+  // would panic on an out-of-range slice; a GPU kernel would write out of bounds).
+  for (int l = 0; l < h.nlv; l++) {
+    const uint8_t* q = p + h.lv_off + (size_t)l * 20;
+    const uint32_t w = rd32(q), hh = rd32(q + 4), tx = rd32(q + 8), ty = rd32(q + 12), first = rd32(q + 16);
+    if (w == 0 || hh == 0 || w > 0x7FFFFFFFu || hh > 0x7FFFFFFFu) return fail(MICGPU_E_HEADER, "MIC3: level %d has invalid dimensions", l);
+    const uint64_t etx = ((uint64_t)w + h.tile_w - 1) / h.tile_w, ety = ((uint64_t)hh + h.tile_h - 1) / h.tile_h;
+    if (tx != etx || ty != ety) return fail(MICGPU_E_HEADER, "MIC3: level %d tile grid %ux%u does not match %ux%u pixels", l, tx, ty, w, hh);
+    if ((uint64_t)first + etx * ety > h.total_tiles) return fail(MICGPU_E_HEADER, "MIC3: level %d tiles exceed the tile table", l);
+  }
   return 0;
 }
 Mic3Level mic3_level(const uint8_t* p, const Mic3Header& h, int l) {
@@ -989,7 +1068,8 @@ Mic3Level mic3_level(const uint8_t* p, const Mic3Header& h, int l) {
 int mic3_tile_blob(const uint8_t* p, size_t len, const Mic3Header& h, long long idx, const uint8_t** blob, size_t* bl) {
   if (idx < 0 || (uint64_t)idx >= h.total_tiles) return fail(MICGPU_E_HEADER, "MIC3: tile index %lld out of range", idx);
   const uint64_t o = rd64(p + h.table_off + (size_t)idx * 16), n = rd64(p + h.table_off + (size_t)idx * 16 + 8);
-  if (h.data_off + o + n > len || n > len) return fail(MICGPU_E_HEADER, "MIC3: tile %lld data extends beyond file", idx);
+  const uint64_t room = (uint64_t)len - h.data_off;   // data_off <= len (parse_mic3); no sum of file fields can wrap
+  if (o > room || n > room - o) return fail(MICGPU_E_HEADER, "MIC3: tile %lld data extends beyond file", idx);
   *blob = p + h.data_off + o;
   *bl = (size_t)n;
   return 0;
@@ -1008,6 +1088,7 @@ struct TileReq {
 int wsi_run_locked(micgpu_decoder* d, std::vector<TileReq>& tiles, size_t out_bytes) {
   d->units.clear();
   d->temporal.clear();
+  d->zero_ranges.clear();
   d->out_need = 0;
   std::vector<PlaneFillJob> fills;
   std::vector<TileBlitJob> blits;
@@ -1056,8 +1137,16 @@ int wsi_run_locked(micgpu_decoder* d, std::vector<TileReq>& tiles, size_t out_by
     }
     if (T.status) continue;
     const unsigned mode = rgb ? (T.ct ? 0u : 1u) : (T.bps <= 8 ? 2u : 3u);
-    for (const Blit& b : T.blits)
+    const unsigned bppx = rgb ? 3u : (T.bps <= 8 ? 1u : 2u);
+    for (const Blit& b : T.blits) {
+      // a rectangle must lie inside the tile and inside the byte output (k_tile_blit does not clip)
+      if ((uint64_t)b.sx + b.w > (uint64_t)T.tile_w || (uint64_t)b.sy + b.h > (uint64_t)T.tile_h || b.w == 0 || b.h == 0 ||
+          (uint64_t)b.w * bppx > b.dst_pitch || b.dst_off + (uint64_t)(b.h - 1) * b.dst_pitch + (uint64_t)b.w * bppx > out_bytes) {
+        T.status = fail(MICGPU_E_SIZE, "MIC3: blit rectangle outside the tile or the output");
+        break;
+      }
       blits.push_back(TileBlitJob{plane0, b.dst_off, (unsigned)T.tile_w, (unsigned)T.tile_h, b.sx, b.sy, b.w, b.h, b.dst_pitch, mode});
+    }
   }
   int rc = plan_commit(d);
   if (rc) return rc;
@@ -1130,7 +1219,9 @@ int micgpu_wsi_decompress_tiles(const uint8_t* mic3, size_t len, int n, const in
     if (txs[i] < 0 || txs[i] >= lv.tx || tys[i] < 0 || tys[i] >= lv.ty) { T.status = fail(MICGPU_E_HEADER, "MIC3: tile (%d,%d) out of range for level %d", txs[i], tys[i], levels[i]); continue; }
     if ((T.status = mic3_tile_blob(mic3, len, h, (long long)lv.first + (long long)tys[i] * lv.tx + txs[i], &T.blob, &T.len))) continue;
     // edge tiles are cropped to the level extent (wsicompress.go:200-216)
-    const int aw = std::min(h.tile_w, lv.w - txs[i] * h.tile_w), ah = std::min(h.tile_h, lv.h - tys[i] * h.tile_h);
+    const int aw = (int)std::min<long long>(h.tile_w, (long long)lv.w - (long long)txs[i] * h.tile_w);
+    const int ah = (int)std::min<long long>(h.tile_h, (long long)lv.h - (long long)tys[i] * h.tile_h);
+    if (aw <= 0 || ah <= 0) { T.status = fail(MICGPU_E_HEADER, "MIC3: tile (%d,%d) lies outside level %d", txs[i], tys[i], levels[i]); continue; }
     if (widths) widths[i] = aw;
     if (heights) heights[i] = ah;
     osz[i] = (size_t)aw * ah * bpp;
@@ -1167,8 +1258,8 @@ int micgpu_wsi_decompress_region(const uint8_t* mic3, size_t len, int level, int
   if (level < 0 || level >= hd.nlv) return fail(MICGPU_E_HEADER, "MIC3: level %d out of range [0, %d)", level, hd.nlv);
   const Mic3Level lv = mic3_level(mic3, hd, level);
   if (x < 0 || y < 0) return fail(MICGPU_E_HEADER, "MIC3: negative region origin");
-  if (x + w > lv.w) w = lv.w - x;
-  if (y + h > lv.h) h = lv.h - y;
+  if ((long long)x + w > lv.w) w = (int)std::max<long long>(0, (long long)lv.w - x);
+  if ((long long)y + h > lv.h) h = (int)std::max<long long>(0, (long long)lv.h - y);
   if (w <= 0 || h <= 0) return fail(MICGPU_E_HEADER, "MIC3: empty region");
   const int bpp = bytes_per_pixel(hd.channels, hd.bps);
   if ((size_t)w * h * bpp > cap) return fail(MICGPU_E_SIZE, "region output buffer too small");
@@ -1265,6 +1356,7 @@ int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t* const* blobs, const
   std::lock_guard<std::mutex> lk(d->mu);
   d->units.clear();
   d->temporal.clear();
+  d->zero_ranges.clear();
   d->out_need = 0;
   struct Img { unsigned rows, cols; int levels, unit, st; uint64_t coff, px_off; };
   std::vector<Img> im(n);

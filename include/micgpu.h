@@ -48,7 +48,15 @@ const char *micgpu_last_error(void);
 /* Pinned host memory helpers (optional; pageable buffers work, slower). */
 void *micgpu_host_alloc(size_t bytes);
 void micgpu_host_free(void *p);
-/* Release the per-device default contexts used by the one-shot calls. */
+/* Devices the one-call batch entry points spread their units over: the list replaces the worker
+ * pools of the reference (goroutines in parallelstrips.go:292-321, `Workers` in wsicompress.go:112-115, pthreads in
+ * ojph/mic_parallel.c:131-189).  devices == NULL or n <= 0 selects every visible device.  Returns the number of devices
+ * in use (> 0) or an error.  Without this call everything runs on the calling thread's current device.  Affects
+ * micgpu_pics_decompress_batch, micgpu_mic2_decompress and micgpu_wsi_decompress_tile_range: each device gets a
+ * contiguous unit range balanced by compressed bytes, its own host thread, stream and scratch; nothing is exchanged
+ * between devices except the carry frames of a temporal MIC2 stack (peer reads). */
+int micgpu_init(const int *devices, int n);
+/* Release the per-device default contexts used by the one-shot calls (and forget the device list). */
 void micgpu_shutdown(void);
 
 /* ---- batch decoder: plan once from HOST copies of the streams, run many ---- */
@@ -153,6 +161,29 @@ int micgpu_wsi_decompress_tiles(const uint8_t *mic3, size_t len, int n, const in
 /* DecompressWSIRegion (wsicompress.go:220-296) */
 int micgpu_wsi_decompress_region(const uint8_t *mic3, size_t len, int level, int x, int y, int w, int h, uint8_t *out, size_t cap,
                                  int *out_w, int *out_h);
+/* ---- tile ranges: plan once, run many (viewer / batch conversion path) ------------------------------------------
+ * Tiles [first_tile, first_tile + n_tiles) of the container's tile table (level l starts at first_tile[l], row-major:
+ * wsiformat.go:145-155), each decoded as a FULL tile_w x tile_h block of pixels, tile_bytes apart (edge tiles keep the
+ * zero padding the encoder added, wsicompress.go:529-556; crop with the level extent from micgpu_wsi_read_header).
+ * The plan parses the container once (every compressed plane = one unit; constant planes cost nothing; raw planes are
+ * copies); a run needs the bytes [span_off, span_off + span_len) of the container in device memory and writes
+ * out_bytes of pixels -- no host work per tile. */
+typedef struct micgpu_wsi_plan micgpu_wsi_plan;
+micgpu_wsi_plan *micgpu_wsi_plan_tiles(int device, const uint8_t *mic3, size_t len, uint64_t first_tile, uint64_t n_tiles);
+void micgpu_wsi_plan_destroy(micgpu_wsi_plan *p);
+int micgpu_wsi_plan_info(const micgpu_wsi_plan *p, uint64_t *span_off, uint64_t *span_len, uint64_t *tile_bytes, uint64_t *out_bytes,
+                         int *n_units);
+/* d_span: device copy of mic3[span_off .. span_off+span_len) (+256 readable bytes); d_out: out_bytes. Asynchronous. */
+int micgpu_wsi_plan_run_device(micgpu_wsi_plan *p, const void *d_span, void *d_out, void *cuda_stream);
+/* Waits for the last run; tile_status[i] (optional, n entries) = 0 or the error of tile first_tile + i. */
+int micgpu_wsi_plan_status(micgpu_wsi_plan *p, int *tile_status, int n, void *cuda_stream);
+int micgpu_wsi_plan_launches(const micgpu_wsi_plan *p);
+/* on >= 0: switch per-kernel CUDA-event timing of the plan on/off; on < 0: fetch names (';'-separated) and durations
+ * of the last run, as micgpu_decoder_kernel_times does. */
+int micgpu_wsi_plan_kernel_times(micgpu_wsi_plan *p, int on, char *names, size_t names_cap, float *ms, int cap);
+/* Host buffers in and out: one H2D copy of the span, the kernels, one D2H copy per device (micgpu_init). */
+int micgpu_wsi_decompress_tile_range(const uint8_t *mic3, size_t len, uint64_t first_tile, uint64_t n_tiles, uint8_t *out, size_t cap,
+                                     int *status);
 /* DecompressRGB (rgbcompress.go:31-33) */
 int micgpu_rgb_decompress(const uint8_t *blob, size_t len, int width, int height, uint8_t *rgb_out);
 

@@ -30,6 +30,9 @@ from .api import (  # noqa: F401
     DecompressWSIRegion,
     DecompressWSITile,
     DecompressWSITiles,
+    DecompressWSITileRange,
+    WsiPlan,
+    Init,
     ReadWSIHeader,
     WaveletV2DecompressBatch,
     WaveletV2RLEFSEDecompressU16,

@@ -79,6 +79,18 @@ lib.micgpu_pics_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.P
 lib.micgpu_decompress_single_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
 lib.micgpu_mic2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip, _ip, _ip]
 lib.micgpu_mic2_decompress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_init.argtypes = [_ip, C.c_int]
+lib.micgpu_wsi_plan_tiles.restype = C.c_void_p
+lib.micgpu_wsi_plan_tiles.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64]
+lib.micgpu_wsi_plan_destroy.argtypes = [C.c_void_p]
+lib.micgpu_wsi_plan_destroy.restype = None
+_u64p = C.POINTER(C.c_uint64)
+lib.micgpu_wsi_plan_info.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p, _ip]
+lib.micgpu_wsi_plan_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.micgpu_wsi_plan_status.argtypes = [C.c_void_p, _ip, C.c_int, C.c_void_p]
+lib.micgpu_wsi_plan_launches.argtypes = [C.c_void_p]
+lib.micgpu_wsi_plan_kernel_times.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
+lib.micgpu_wsi_decompress_tile_range.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, _ip]
 
 
 class WsiInfo(C.Structure):
@@ -295,6 +307,78 @@ def DecompressWSIRegion(data, level: int, x: int, y: int, w: int, h: int):
     ow, oh = C.c_int(), C.c_int()
     _check(lib.micgpu_wsi_decompress_region(a.ctypes.data, a.size, level, x, y, w, h, out.ctypes.data, out.size, C.byref(ow), C.byref(oh)))
     return out[: ow.value * oh.value * _wsi_bpp(hdr)], ow.value, oh.value
+
+
+def Init(devices=None) -> int:
+    """micgpu_init: spread the one-call batch entry points over these devices (None = all visible)."""
+    if devices is None:
+        rc = lib.micgpu_init(None, 0)
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        rc = lib.micgpu_init(arr, len(devices))
+    if rc <= 0:
+        raise MicGpuError(rc, last_error())
+    return rc
+
+
+def DecompressWSITileRange(data, first_tile: int, n_tiles: int):
+    """Tiles [first, first+n) of the tile table as full (uncropped) tiles -> uint8 array (n_tiles, tile_bytes)."""
+    a = _bytes_view(data)
+    hdr = ReadWSIHeader(a)
+    tile_bytes = hdr["TileWidth"] * hdr["TileHeight"] * _wsi_bpp(hdr)
+    out = np.empty(max(n_tiles, 1) * tile_bytes, np.uint8)
+    st = (C.c_int * max(n_tiles, 1))()
+    _check(lib.micgpu_wsi_decompress_tile_range(a.ctypes.data, a.size, C.c_uint64(first_tile), C.c_uint64(n_tiles), out.ctypes.data, out.size, st))
+    return out[: n_tiles * tile_bytes].reshape(n_tiles, tile_bytes)
+
+
+class WsiPlan:
+    """micgpu_wsi_plan_*: plan a tile range once, run it from device-resident bytes (pointers are raw device addresses)."""
+
+    def __init__(self, data, first_tile: int, n_tiles: int, device: int = 0):
+        a = _bytes_view(data)
+        self.p = lib.micgpu_wsi_plan_tiles(device, a.ctypes.data, a.size, C.c_uint64(first_tile), C.c_uint64(n_tiles))
+        if not self.p:
+            raise MicGpuError(-1, last_error())
+        so, sl, tb, ob, nu = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        _check(lib.micgpu_wsi_plan_info(self.p, C.byref(so), C.byref(sl), C.byref(tb), C.byref(ob), C.byref(nu)))
+        self.span_off, self.span_len, self.tile_bytes, self.out_bytes, self.n_units = so.value, sl.value, tb.value, ob.value, nu.value
+        self.n_tiles = n_tiles
+
+    def close(self):
+        if self.p:
+            lib.micgpu_wsi_plan_destroy(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_device(self, d_span_ptr: int, d_out_ptr: int, stream_ptr: int = 0):
+        _check(lib.micgpu_wsi_plan_run_device(self.p, C.c_void_p(d_span_ptr), C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
+
+    def status(self, stream_ptr: int = 0):
+        st = (C.c_int * max(self.n_tiles, 1))()
+        lib.micgpu_wsi_plan_status(self.p, st, self.n_tiles, C.c_void_p(stream_ptr))
+        return list(st)[: self.n_tiles]
+
+    @property
+    def last_launches(self) -> int:
+        return lib.micgpu_wsi_plan_launches(self.p)
+
+    def set_profiling(self, on: bool):
+        _check(lib.micgpu_wsi_plan_kernel_times(self.p, 1 if on else 0, None, 0, None, 0))
+
+    def kernel_times(self):
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n = lib.micgpu_wsi_plan_kernel_times(self.p, -1, names, 4096, ms, 64)
+        if n < 0:
+            raise MicGpuError(n, last_error())
+        nm = names.value.decode().split(";") if n else []
+        return [(nm[i], ms[i]) for i in range(n)]
 
 
 def DecompressRGB(data, width: int, height: int) -> np.ndarray:

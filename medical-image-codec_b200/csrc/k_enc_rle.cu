@@ -172,7 +172,7 @@ k_enc_rle_segments(MicEncUnit* __restrict__ units, int nunits, const uint16_t* _
       {
         // long[i0-1]
         const long long i = (long long)i0 - 1;
-        if (i >= 0) {
+        if (i >= 0 && i0 < n) {   // threads past the end of the stream have nothing to flag (and must not read V[i0-3])
           // needs V[i0-3]: reload
           const unsigned a = i >= 2 ? V[i - 2] : 0x20000u, b = w[0], c = w[1], d2 = w[2], e = w[3];
           prev_long = (a == b && b == c) || (b == c && c == d2) || (c == d2 && d2 == e);

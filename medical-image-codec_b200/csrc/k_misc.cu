@@ -127,38 +127,112 @@ k_plane_fill(const PlaneFillJob* __restrict__ jobs, int njobs, const uint8_t* __
 // ---- MIC3 tile finish: planes -> pixels, YCoCg-R inverse, crop / region blit -----------------------
 // Replaces YCoCgRInverse (ycocgr.go:28-35, asm_generic.go:40-53, ycocgRInverseSSSE3/NEON), the planar->RGB
 // interleave (wsicompress.go:466-473), uint16ToBytes (:592-603), cropTile (:558-572) and the row copies of
-// DecompressWSIRegion (:282-291).  One job = one rectangle of one tile.
+// DecompressWSIRegion (:282-291).  One job = one rectangle of one tile; constant planes (modes 0/1) are carried in the
+// job instead of being materialised.
+//   * vector path (whole 16-pixel groups: full-width rectangles of tiles whose width is a multiple of 16, 16 B aligned
+//     planes and destination -- every tile of the batch path, every interior tile of a region): a thread loads 2 x 16 B
+//     per plane, converts 16 pixels and stores 3 x 16 B (RGB) / 1-2 x 16 B (grey);
+//   * scalar path for everything else: rows over blockIdx.x, pixels over threads (no per-pixel division).
+__device__ __forceinline__ void ycocg_inv(int y, int co_zz, int cg_zz, int& r, int& g, int& b) {
+  const int co = (int)(short)((co_zz >> 1) ^ -(co_zz & 1)), cg = (int)(short)((cg_zz >> 1) ^ -(cg_zz & 1));
+  const int t = y - (cg >> 1);
+  g = cg + t;
+  b = t - (co >> 1);
+  r = co + b;
+}
+
 __global__ void __launch_bounds__(256)
 k_tile_blit(const TileBlitJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ planes, uint8_t* __restrict__ out) {
   for (int j = blockIdx.y; j < njobs; j += gridDim.y) {
     const TileBlitJob J = jobs[j];
-    const unsigned long long npx = (unsigned long long)J.copy_w * J.copy_h;
-    const unsigned long long plane_px = (unsigned long long)J.tile_w * J.tile_h;
-    const uint16_t* p0 = planes + J.plane_off;
+    const unsigned bpp = J.mode <= 1 ? 3u : (J.mode == 2 ? 1u : 2u);
+    const unsigned nplanes = J.mode <= 1 ? 3u : 1u;
     uint8_t* dst = out + J.dst_off;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-      const unsigned ry = (unsigned)(i / J.copy_w), rx = (unsigned)(i - (unsigned long long)ry * J.copy_w);
-      const unsigned long long s = (unsigned long long)(J.src_y + ry) * J.tile_w + (J.src_x + rx);
-      uint8_t* d = dst + (unsigned long long)ry * J.dst_pitch;
-      if (J.mode == 0 || J.mode == 1) {
-        const int a = p0[s], b = p0[plane_px + s], c = p0[2 * plane_px + s];
-        int r, g, bl;
-        if (J.mode == 0) {                  // YCoCg-R inverse
-          const int co = (int)(short)((b >> 1) ^ -(b & 1)), cg = (int)(short)((c >> 1) ^ -(c & 1));
-          const int t = a - (cg >> 1);
-          g = cg + t;
-          bl = t - (co >> 1);
-          r = co + bl;
-        } else {                            // planar R,G,B
-          r = a; g = b; bl = c;
+    const uint16_t* pl[3];
+#pragma unroll
+    for (unsigned k = 0; k < 3; k++) pl[k] = planes + J.plane_off[k < nplanes ? k : 0];
+    bool vec = J.src_x == 0 && J.copy_w == J.tile_w && (J.tile_w & 15u) == 0 && J.dst_pitch == J.tile_w * bpp &&
+               ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+    for (unsigned k = 0; k < nplanes; k++)
+      if (!((J.cmask >> k) & 1u)) vec = vec && ((reinterpret_cast<uintptr_t>(pl[k]) & 15u) == 0);
+    if (vec) {
+      // the rectangle is rows [src_y, src_y + copy_h) of the tile, contiguous on both sides
+      const unsigned long long first = (unsigned long long)J.src_y * J.tile_w;
+      const unsigned ngroups = (unsigned)(((unsigned long long)J.copy_w * J.copy_h) >> 4);
+      for (unsigned gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < ngroups; gidx += gridDim.x * blockDim.x) {
+        uint32_t v[3][8];   // 16 samples per plane, two per word
+#pragma unroll
+        for (unsigned k = 0; k < 3; k++) {
+          if (k < nplanes) {
+            if ((J.cmask >> k) & 1u) {
+              const uint32_t c2 = (uint32_t)J.cval[k] * 0x00010001u;
+#pragma unroll
+              for (int q = 0; q < 8; q++) v[k][q] = c2;
+            } else {
+              const uint4* src = reinterpret_cast<const uint4*>(pl[k] + first) + 2ull * gidx;
+              const uint4 a = __ldg(src), b = __ldg(src + 1);
+              v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+              v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
+            }
+          }
         }
-        d[3 * rx] = (uint8_t)r; d[3 * rx + 1] = (uint8_t)g; d[3 * rx + 2] = (uint8_t)bl;
-      } else if (J.mode == 2) {             // grey 8-bit
-        d[rx] = (uint8_t)p0[s];
-      } else {                              // grey 16-bit little endian
-        const unsigned v = p0[s];
-        d[2 * rx] = (uint8_t)v; d[2 * rx + 1] = (uint8_t)(v >> 8);
+        if (J.mode <= 1) {
+          uint8_t px[48];
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            const int a = (v[0][q >> 1] >> (16 * (q & 1))) & 0xFFFF, b = (v[1][q >> 1] >> (16 * (q & 1))) & 0xFFFF,
+                      c = (v[2][q >> 1] >> (16 * (q & 1))) & 0xFFFF;
+            int r, g, bl;
+            if (J.mode == 0) ycocg_inv(a, b, c, r, g, bl);
+            else { r = a; g = b; bl = c; }
+            px[3 * q] = (uint8_t)r; px[3 * q + 1] = (uint8_t)g; px[3 * q + 2] = (uint8_t)bl;
+          }
+          uint4* o = reinterpret_cast<uint4*>(dst) + 3ull * gidx;
+#pragma unroll
+          for (int w = 0; w < 3; w++) {
+            uint32_t x[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int bidx = 16 * w + 4 * i;
+              x[i] = (uint32_t)px[bidx] | ((uint32_t)px[bidx + 1] << 8) | ((uint32_t)px[bidx + 2] << 16) | ((uint32_t)px[bidx + 3] << 24);
+            }
+            o[w] = make_uint4(x[0], x[1], x[2], x[3]);
+          }
+        } else if (J.mode == 2) {
+          uint32_t x[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            x[i] = (v[0][2 * i] & 0xFFu) | (((v[0][2 * i] >> 16) & 0xFFu) << 8) | ((v[0][2 * i + 1] & 0xFFu) << 16) | (((v[0][2 * i + 1] >> 16) & 0xFFu) << 24);
+          reinterpret_cast<uint4*>(dst)[gidx] = make_uint4(x[0], x[1], x[2], x[3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(dst) + 2ull * gidx;
+          o[0] = make_uint4(v[0][0], v[0][1], v[0][2], v[0][3]);
+          o[1] = make_uint4(v[0][4], v[0][5], v[0][6], v[0][7]);
+        }
+      }
+      continue;
+    }
+    for (unsigned ry = blockIdx.x; ry < J.copy_h; ry += gridDim.x) {
+      const unsigned long long srow = (unsigned long long)(J.src_y + ry) * J.tile_w + J.src_x;
+      uint8_t* d = dst + (unsigned long long)ry * J.dst_pitch;
+      for (unsigned rx = threadIdx.x; rx < J.copy_w; rx += blockDim.x) {
+        const unsigned long long s = srow + rx;
+        int a = 0, b = 0, c = 0;
+        a = (J.cmask & 1u) ? J.cval[0] : pl[0][s];
+        if (nplanes == 3) {
+          b = (J.cmask & 2u) ? J.cval[1] : pl[1][s];
+          c = (J.cmask & 4u) ? J.cval[2] : pl[2][s];
+        }
+        if (J.mode <= 1) {
+          int r, g, bl;
+          if (J.mode == 0) ycocg_inv(a, b, c, r, g, bl);
+          else { r = a; g = b; bl = c; }
+          d[3 * rx] = (uint8_t)r; d[3 * rx + 1] = (uint8_t)g; d[3 * rx + 2] = (uint8_t)bl;
+        } else if (J.mode == 2) {
+          d[rx] = (uint8_t)a;
+        } else {
+          d[2 * rx] = (uint8_t)a; d[2 * rx + 1] = (uint8_t)(a >> 8);
+        }
       }
     }
   }
@@ -172,7 +246,8 @@ void launch_plane_fill(const PlaneFillJob* d_jobs, int njobs, const uint8_t* d_c
 
 void launch_tile_blit(const TileBlitJob* d_jobs, int njobs, const uint16_t* d_planes, uint8_t* d_out, cudaStream_t st) {
   if (njobs <= 0) return;
-  dim3 grid(8, njobs < 65535 ? njobs : 65535);
+  // a 256x256 tile is 4096 groups of 16 pixels: 4 CTAs of 256 threads take four groups per thread
+  dim3 grid(njobs >= 1024 ? 4 : 16, njobs < 65535 ? njobs : 65535);
   k_tile_blit<<<grid, 256, 0, st>>>(d_jobs, njobs, d_planes, d_out);
 }
 

@@ -12,6 +12,14 @@ namespace micgpu {
 void launch_build_tables(MicUnit* d_units, int nunits, const uint8_t* d_comp, uint32_t* d_tabA, uint16_t* d_tabS,
                          uint8_t* d_scratch, unsigned long long scratch_stride, int max_log, int grid, cudaStream_t st);
 
+// Split table build (k_table.cu): K1a one warp per unit parses the ncount header, K1b one CTA per unit builds the
+// decode table in shared memory; d_norm / d_sym hold the present-symbol lists at each unit's tab_off.  Units the
+// split path cannot take are built by the one-kernel path on fallback_grid CTAs (0 = none can occur).
+void launch_parse_ncount(MicUnit* d_units, int nunits, const uint8_t* d_comp, int32_t* d_norm, uint16_t* d_sym, cudaStream_t st);
+void launch_build_dtable(MicUnit* d_units, int nunits, const uint8_t* d_comp, uint32_t* d_tabA, uint16_t* d_tabS,
+                         const int32_t* d_norm, const uint16_t* d_sym, unsigned int* d_queue, uint8_t* d_scratch,
+                         unsigned long long scratch_stride, int max_log, int fallback_grid, int sm_count, cudaStream_t st);
+
 // ANS decode of the units listed in d_list (all with the same state count).
 // Output: the *state* stream (table indices, u16) at units[i].sym_off; symbols
 // are recovered later through tabS.  smem_mode: 0 = u32 entries in shared
@@ -65,12 +73,14 @@ struct PlaneFillJob {
   unsigned int value;
 };
 struct TileBlitJob {
-  unsigned long long plane_off;   // first plane of the tile (planes are tile_w*tile_h apart)
-  unsigned long long dst_off;     // byte offset of the destination rectangle
+  unsigned long long plane_off[3];   // element offset of each plane (unused for a constant plane)
+  unsigned long long dst_off;        // byte offset of the destination rectangle
   unsigned int tile_w, tile_h;
   unsigned int src_x, src_y, copy_w, copy_h;
-  unsigned int dst_pitch;         // bytes per destination row
-  unsigned int mode;              // 0 YCoCg-R -> RGB8, 1 planar RGB -> RGB8, 2 grey8, 3 grey16
+  unsigned int dst_pitch;            // bytes per destination row
+  unsigned int mode;                 // 0 YCoCg-R -> RGB8, 1 planar RGB -> RGB8, 2 grey8, 3 grey16
+  unsigned int cmask;                // bit k: plane k is constant (plane modes 0/1, wsicompress.go:487-500): no plane is materialised
+  unsigned short cval[4];            // its value
 };
 void launch_plane_fill(const PlaneFillJob* d_jobs, int njobs, const uint8_t* d_comp, uint16_t* d_planes, cudaStream_t st);
 void launch_tile_blit(const TileBlitJob* d_jobs, int njobs, const uint16_t* d_planes, uint8_t* d_out, cudaStream_t st);

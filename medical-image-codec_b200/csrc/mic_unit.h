@@ -48,6 +48,7 @@ struct MicUnit {
   // ---- device-filled ----------------------------------------------------
   unsigned int bits_off;        // byte offset of the bitstream inside the frame
   unsigned int bits_len;        // bitstream length in bytes
+  unsigned int npres;           // K1a -> K1b: symbols with a non-zero normalised count (0xFFFFFFFF: one-kernel fallback)
   unsigned int nsym;            // symbols actually decoded
   unsigned int thr;             // deltaThreshold (deltarlecompressu16.go:72-74)
   unsigned int delim;           // delimiterForOverflow

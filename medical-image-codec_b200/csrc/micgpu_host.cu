@@ -15,6 +15,7 @@
 #include <chrono>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_common.h"
@@ -67,6 +68,8 @@ struct micgpu_decoder {
   bool committed = false;
   int launches = 0;
   DevBuf d_units, d_list, d_tabA, d_tabS, d_states, d_D, d_M, d_k1, d_comp, d_out, d_queue;
+  DevBuf d_norm, d_psym;    // split table build: present-symbol lists (normalised count, symbol value) at each unit's tab_off
+  bool k1_split = true, k1_fallback = false;
   DevBuf d_jobs, d_bytes;   // MIC3: fill / blit job tables, byte-typed pixel output
   DevBuf d_wA, d_wB, d_wflags;   // WaveletV2: int32 ping-pong planes, escape flags
   MicUnit* h_units = nullptr;   // pinned staging copy
@@ -86,7 +89,7 @@ struct micgpu_decoder {
   ~micgpu_decoder() {
     cudaSetDevice(device);
     d_units.release(); d_list.release(); d_tabA.release(); d_tabS.release(); d_states.release();
-    d_D.release(); d_M.release(); d_k1.release(); d_queue.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
+    d_D.release(); d_M.release(); d_k1.release(); d_norm.release(); d_psym.release(); d_queue.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
     for (int p = 0; p < PARTS; p++) {
@@ -236,7 +239,18 @@ int plan_commit(micgpu_decoder* d) {
   if ((rc = d->d_states.ensure((d->sym_total + 64) * sizeof(uint16_t)))) return rc;
   if ((rc = d->d_D.ensure((d->d_total + 64) * sizeof(uint16_t)))) return rc;
   if ((rc = d->d_M.ensure((d->m_total + 64) * sizeof(uint32_t)))) return rc;
-  if ((rc = d->d_k1.ensure((size_t)d->k1_grid * d->k1_stride))) return rc;
+  // Split table build (K1a parse + K1b build) unless MICGPU_K1_SPLIT=0; the one-kernel path stays for the units it
+  // cannot take: rANS streams, tableLog > 13, more than 2048 present symbols (only possible from tableLog 12 up).
+  static const bool split_cfg = [] { const char* e = getenv("MICGPU_K1_SPLIT"); return !(e && e[0] == '0'); }();
+  d->k1_split = split_cfg;
+  bool any_rans = false;
+  for (const MicUnit& u : d->units) any_rans |= u.rans != 0;
+  d->k1_fallback = !d->k1_split || any_rans || d->max_log_all >= 12;
+  if (d->k1_fallback && (rc = d->d_k1.ensure((size_t)d->k1_grid * d->k1_stride))) return rc;
+  if (d->k1_split) {
+    if ((rc = d->d_norm.ensure((d->tab_total + 64) * sizeof(int32_t)))) return rc;
+    if ((rc = d->d_psym.ensure((d->tab_total + 64) * sizeof(uint16_t)))) return rc;
+  }
   if ((rc = d->d_queue.ensure(256))) return rc;
   if (nu > d->h_units_cap) {
     if (d->h_units) cudaFreeHost(d->h_units);
@@ -284,10 +298,20 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   MicUnit* du = (MicUnit*)d->d_units.p;
   const uint8_t* comp = (const uint8_t*)d_comp;
   d->ev_used = 0;
-  prof_mark(d, "k_build_tables", st);
-  launch_build_tables(du, nu, comp, (uint32_t*)d->d_tabA.p, (uint16_t*)d->d_tabS.p, (uint8_t*)d->d_k1.p, d->k1_stride,
-                      d->max_log_all, d->k1_grid, st);
-  d->launches++;
+  if (d->k1_split) {
+    prof_mark(d, "k_parse_ncount", st);
+    launch_parse_ncount(du, nu, comp, (int32_t*)d->d_norm.p, (uint16_t*)d->d_psym.p, st);
+    prof_mark(d, "k_build_dtable", st);
+    launch_build_dtable(du, nu, comp, (uint32_t*)d->d_tabA.p, (uint16_t*)d->d_tabS.p, (const int32_t*)d->d_norm.p, (const uint16_t*)d->d_psym.p,
+                        (unsigned int*)d->d_queue.p + 32, (uint8_t*)d->d_k1.p, d->k1_stride, d->max_log_all,
+                        d->k1_fallback ? d->k1_grid : 0, d->sm_count, st);
+    d->launches += d->k1_fallback ? 3 : 2;
+  } else {
+    prof_mark(d, "k_build_tables", st);
+    launch_build_tables(du, nu, comp, (uint32_t*)d->d_tabA.p, (uint16_t*)d->d_tabS.p, (uint8_t*)d->d_k1.p, d->k1_stride,
+                        d->max_log_all, d->k1_grid, st);
+    d->launches++;
+  }
   const int* dl = (const int*)d->d_list.p;
   size_t loff = 0;
   for (int g = 0; g < 4; g++) {
@@ -481,6 +505,14 @@ constexpr int PIPE_DEPTH = 6;
 std::mutex g_pipe_mu;
 micgpu_decoder* g_pipe[64][PIPE_DEPTH] = {};
 
+// Devices the one-call batch entry points spread their units over (micgpu_init); empty = the current device only.
+std::mutex g_dev_mu;
+std::vector<int> g_devices;
+std::vector<int> configured_devices() {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  return g_devices;
+}
+
 micgpu_decoder* default_decoder(int dev) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (dev < 0 || dev >= 64) return nullptr;
@@ -525,7 +557,31 @@ void micgpu_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+int micgpu_init(const int* devices, int n) {
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) return fail(MICGPU_E_CUDA, "no CUDA device available (libmicgpu has no CPU fallback)");
+  std::vector<int> v;
+  if (!devices || n <= 0) {
+    for (int i = 0; i < have; i++) v.push_back(i);     // all visible devices
+  } else {
+    for (int i = 0; i < n; i++) {
+      if (devices[i] < 0 || devices[i] >= have) return fail(MICGPU_E_CUDA, "device %d out of range [0,%d)", devices[i], have);
+      for (int q : v)
+        if (q == devices[i]) return fail(MICGPU_E_HEADER, "device %d listed twice", q);
+      v.push_back(devices[i]);
+    }
+  }
+  if (v.size() > 64) return fail(MICGPU_E_UNSUPPORTED, "at most 64 devices");
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  g_devices = v;
+  return (int)v.size();
+}
+
 void micgpu_shutdown(void) {
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    g_devices.clear();
+  }
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& d : g_default) {
     delete d;
@@ -1078,27 +1134,31 @@ int mic3_tile_blob(const uint8_t* p, size_t len, const Mic3Header& h, long long 
 struct Blit { unsigned sx, sy, w, h; unsigned long long dst_off; unsigned dst_pitch; };
 struct TileReq {
   const uint8_t* blob; size_t len;       // host copy of the tile blob
+  uint64_t comp_off = 0;                 // where the blob sits in the device compressed buffer
   int tile_w, tile_h, channels, bps, ct;
   std::vector<Blit> blits;               // rectangles of the decoded tile to place in the byte output
   int status = 0;
 };
 
-// decompressTileBlob for a batch of tiles (wsicompress.go:424-484) + the blits that follow it.
-// Output bytes land in d->d_bytes; the caller copies them back.
-int wsi_run_locked(micgpu_decoder* d, std::vector<TileReq>& tiles, size_t out_bytes) {
+// Everything a batch of tiles needs besides the decoder's unit plan: raw-plane copies, the blit table, what to report.
+struct WsiWork {
+  std::vector<PlaneFillJob> fills;             // plane mode 3 (raw little-endian samples)
+  std::vector<TileBlitJob> blits;
+  std::vector<std::pair<int, int>> unit_tile;  // unit -> tile
+  uint64_t ptot = 0;                           // plane elements (u16) to reserve
+};
+
+// decompressTileBlob for a batch of tiles (wsicompress.go:424-484): every compressed plane becomes one unit of the
+// decoder plan, raw planes a copy job, constant planes (modes 0 and 1) a field of the tile's blit jobs.
+// T.comp_off must be set; nothing touches the device here.
+void wsi_build(micgpu_decoder* d, std::vector<TileReq>& tiles, size_t out_bytes, WsiWork& W) {
   d->units.clear();
   d->temporal.clear();
   d->zero_ranges.clear();
   d->out_need = 0;
-  std::vector<PlaneFillJob> fills;
-  std::vector<TileBlitJob> blits;
-  std::vector<std::pair<int, int>> unit_tile;   // unit -> tile
-  uint64_t ctot = 0, ptot = 0;
-  std::vector<uint64_t> coff(tiles.size());
   for (size_t t = 0; t < tiles.size(); t++) {
     TileReq& T = tiles[t];
-    coff[t] = ctot;
-    ctot += (T.len + 63) & ~(size_t)63;
+    if (T.status) continue;
     const bool rgb = T.channels == 3 && T.bps == 8;
     if (!rgb && T.channels != 1) { T.status = fail(MICGPU_E_UNSUPPORTED, "MIC3: %d channels at %d bits is not supported", T.channels, T.bps); continue; }
     const uint64_t px = (uint64_t)T.tile_w * T.tile_h;
@@ -1107,68 +1167,112 @@ int wsi_run_locked(micgpu_decoder* d, std::vector<TileReq>& tiles, size_t out_by
     if (rgb) {
       if (T.len < 12) { T.status = fail(MICGPU_E_HEADER, "MIC3: RGB tile blob too small"); continue; }
       const size_t l0 = rd32(T.blob), l1 = rd32(T.blob + 4), l2 = rd32(T.blob + 8);
-      if (12 + l0 + l1 + l2 > T.len) { T.status = fail(MICGPU_E_HEADER, "MIC3: RGB tile blob truncated"); continue; }
+      if (l0 > T.len - 12 || l1 > T.len - 12 - l0 || l2 > T.len - 12 - l0 - l1) { T.status = fail(MICGPU_E_HEADER, "MIC3: RGB tile blob truncated"); continue; }
       pl[0] = T.blob + 12; ln[0] = l0; pl[1] = pl[0] + l0; ln[1] = l1; pl[2] = pl[1] + l1; ln[2] = l2;
     } else {
       pl[0] = T.blob; ln[0] = T.len;
     }
-    const uint64_t plane0 = ptot;
-    ptot += px * nplanes;
+    const size_t units_before = d->units.size(), fills_before = W.fills.size(), ut_before = W.unit_tile.size(), blits_before = W.blits.size();
+    const uint64_t ptot_before = W.ptot;
+    TileBlitJob proto;
+    memset(&proto, 0, sizeof proto);
     for (int k = 0; k < nplanes && !T.status; k++) {
-      const uint64_t poff = plane0 + px * k;
-      const uint64_t boff = coff[t] + (uint64_t)(pl[k] - T.blob);
+      const uint64_t boff = T.comp_off + (uint64_t)(pl[k] - T.blob);
       if (ln[k] == 0) { T.status = fail(MICGPU_E_HEADER, "empty plane data"); break; }
       switch (pl[k][0]) {   // decompressWSIPlane (wsicompress.go:487-524)
-        case 0: fills.push_back(PlaneFillJob{poff, 0, px, 0, 0}); break;
+        case 0: proto.cmask |= 1u << k; proto.cval[k] = 0; break;
         case 1:
           if (ln[k] < 3) { T.status = fail(MICGPU_E_HEADER, "constant plane data truncated"); break; }
-          fills.push_back(PlaneFillJob{poff, 0, px, 0, (unsigned)(pl[k][1] | (pl[k][2] << 8))});
+          proto.cmask |= 1u << k; proto.cval[k] = (unsigned short)(pl[k][1] | (pl[k][2] << 8));
           break;
         case 2:
-          add_unit_locked(d, pl[k] + 1, ln[k] - 1, boff + 1, MIC_KIND_SPATIAL, (uint32_t)T.tile_w, (uint32_t)T.tile_h, poff);
-          unit_tile.push_back({(int)d->units.size() - 1, (int)t});
+          proto.plane_off[k] = W.ptot;
+          add_unit_locked(d, pl[k] + 1, ln[k] - 1, boff + 1, MIC_KIND_SPATIAL, (uint32_t)T.tile_w, (uint32_t)T.tile_h, W.ptot);
+          W.unit_tile.push_back({(int)d->units.size() - 1, (int)t});
+          W.ptot += (px + 7) & ~7ull;     // planes start on 16 B boundaries (vector blit)
           break;
         case 3:
           if (ln[k] < 1 + px * 2) { T.status = fail(MICGPU_E_HEADER, "raw plane data truncated"); break; }
-          fills.push_back(PlaneFillJob{poff, boff + 1, px, 1, 0});
+          proto.plane_off[k] = W.ptot;
+          W.fills.push_back(PlaneFillJob{W.ptot, boff + 1, px, 1, 0});
+          W.ptot += (px + 7) & ~7ull;
           break;
         default: T.status = fail(MICGPU_E_HEADER, "unknown plane mode %d", pl[k][0]);
       }
     }
-    if (T.status) continue;
-    const unsigned mode = rgb ? (T.ct ? 0u : 1u) : (T.bps <= 8 ? 2u : 3u);
     const unsigned bppx = rgb ? 3u : (T.bps <= 8 ? 1u : 2u);
-    for (const Blit& b : T.blits) {
-      // a rectangle must lie inside the tile and inside the byte output (k_tile_blit does not clip)
-      if ((uint64_t)b.sx + b.w > (uint64_t)T.tile_w || (uint64_t)b.sy + b.h > (uint64_t)T.tile_h || b.w == 0 || b.h == 0 ||
-          (uint64_t)b.w * bppx > b.dst_pitch || b.dst_off + (uint64_t)(b.h - 1) * b.dst_pitch + (uint64_t)b.w * bppx > out_bytes) {
-        T.status = fail(MICGPU_E_SIZE, "MIC3: blit rectangle outside the tile or the output");
-        break;
+    if (!T.status) {
+      proto.tile_w = (unsigned)T.tile_w; proto.tile_h = (unsigned)T.tile_h;
+      proto.mode = rgb ? (T.ct ? 0u : 1u) : (T.bps <= 8 ? 2u : 3u);
+      for (const Blit& b : T.blits) {
+        // a rectangle must lie inside the tile and inside the byte output (k_tile_blit does not clip)
+        if ((uint64_t)b.sx + b.w > (uint64_t)T.tile_w || (uint64_t)b.sy + b.h > (uint64_t)T.tile_h || b.w == 0 || b.h == 0 ||
+            (uint64_t)b.w * bppx > b.dst_pitch || b.dst_off + (uint64_t)(b.h - 1) * b.dst_pitch + (uint64_t)b.w * bppx > out_bytes) {
+          T.status = fail(MICGPU_E_SIZE, "MIC3: blit rectangle outside the tile or the output");
+          break;
+        }
+        TileBlitJob J = proto;
+        J.dst_off = b.dst_off; J.src_x = b.sx; J.src_y = b.sy; J.copy_w = b.w; J.copy_h = b.h; J.dst_pitch = b.dst_pitch;
+        W.blits.push_back(J);
       }
-      blits.push_back(TileBlitJob{plane0, b.dst_off, (unsigned)T.tile_w, (unsigned)T.tile_h, b.sx, b.sy, b.w, b.h, b.dst_pitch, mode});
+    }
+    if (T.status) {   // a tile that failed planning leaves nothing behind
+      d->units.resize(units_before);
+      W.fills.resize(fills_before);
+      W.unit_tile.resize(ut_before);
+      W.blits.resize(blits_before);
+      W.ptot = ptot_before;
     }
   }
+}
+
+// Upload the job tables (once per plan) behind the decoder's own buffers.
+int wsi_upload_jobs(micgpu_decoder* d, const WsiWork& W, cudaStream_t st) {
+  int rc;
+  const size_t fbytes = W.fills.size() * sizeof(PlaneFillJob), bbytes = W.blits.size() * sizeof(TileBlitJob);
+  if ((rc = d->d_jobs.ensure(((fbytes + 15) & ~(size_t)15) + bbytes + 64))) return rc;
+  if (fbytes) CUDA_TRY(cudaMemcpyAsync(d->d_jobs.p, W.fills.data(), fbytes, cudaMemcpyHostToDevice, st));
+  if (bbytes) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_jobs.p + ((fbytes + 15) & ~(size_t)15), W.blits.data(), bbytes, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// K1..K4 over the planned units, raw-plane copies, then the blits into d_bytes_out.
+int wsi_launch(micgpu_decoder* d, const WsiWork& W, const void* d_comp, size_t comp_bytes, void* d_planes, void* d_bytes_out, cudaStream_t st) {
+  int rc;
+  if ((rc = run_device_locked(d, d_comp, comp_bytes, d_planes, (size_t)W.ptot, st))) return rc;
+  const size_t fbytes = W.fills.size() * sizeof(PlaneFillJob);
+  launch_plane_fill((const PlaneFillJob*)d->d_jobs.p, (int)W.fills.size(), (const uint8_t*)d_comp, (uint16_t*)d_planes, st);
+  launch_tile_blit((const TileBlitJob*)((uint8_t*)d->d_jobs.p + ((fbytes + 15) & ~(size_t)15)), (int)W.blits.size(), (const uint16_t*)d_planes,
+                   (uint8_t*)d_bytes_out, st);
+  d->launches += (W.fills.empty() ? 0 : 1) + (W.blits.empty() ? 0 : 1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// One-shot path of the tile / region / RGB calls: blobs are staged one by one (they may be scattered in the container),
+// output bytes land in d->d_bytes; the caller copies them back.
+int wsi_run_locked(micgpu_decoder* d, std::vector<TileReq>& tiles, size_t out_bytes) {
+  uint64_t ctot = 0;
+  for (TileReq& T : tiles) {
+    T.comp_off = ctot;
+    ctot += (T.len + 63) & ~(size_t)63;
+  }
+  WsiWork W;
+  wsi_build(d, tiles, out_bytes, W);
   int rc = plan_commit(d);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(d->device));
   if ((rc = d->d_comp.ensure(ctot + 256))) return rc;
-  if ((rc = d->d_out.ensure(std::max<uint64_t>(ptot, 1) * sizeof(uint16_t)))) return rc;
+  if ((rc = d->d_out.ensure(std::max<uint64_t>(W.ptot, 1) * sizeof(uint16_t)))) return rc;
   if ((rc = d->d_bytes.ensure(std::max<size_t>(out_bytes, 1)))) return rc;
-  const size_t fbytes = fills.size() * sizeof(PlaneFillJob), bbytes = blits.size() * sizeof(TileBlitJob);
-  if ((rc = d->d_jobs.ensure(fbytes + bbytes + 64))) return rc;
   cudaStream_t st = d->stream;
   for (size_t t = 0; t < tiles.size(); t++)
-    if (!tiles[t].status) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_comp.p + coff[t], tiles[t].blob, tiles[t].len, cudaMemcpyHostToDevice, st));
-  if (fbytes) CUDA_TRY(cudaMemcpyAsync(d->d_jobs.p, fills.data(), fbytes, cudaMemcpyHostToDevice, st));
-  if (bbytes) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_jobs.p + fbytes, blits.data(), bbytes, cudaMemcpyHostToDevice, st));
-  if ((rc = run_device_locked(d, d->d_comp.p, ctot, d->d_out.p, ptot, st))) return rc;
-  launch_plane_fill((const PlaneFillJob*)d->d_jobs.p, (int)fills.size(), (const uint8_t*)d->d_comp.p, (uint16_t*)d->d_out.p, st);
-  launch_tile_blit((const TileBlitJob*)((uint8_t*)d->d_jobs.p + fbytes), (int)blits.size(), (const uint16_t*)d->d_out.p, (uint8_t*)d->d_bytes.p, st);
-  d->launches += (fills.empty() ? 0 : 1) + (blits.empty() ? 0 : 1);
-  CUDA_TRY(cudaGetLastError());
+    if (!tiles[t].status) CUDA_TRY(cudaMemcpyAsync((uint8_t*)d->d_comp.p + tiles[t].comp_off, tiles[t].blob, tiles[t].len, cudaMemcpyHostToDevice, st));
+  if ((rc = wsi_upload_jobs(d, W, st))) return rc;
+  if ((rc = wsi_launch(d, W, d->d_comp.p, ctot, d->d_out.p, d->d_bytes.p, st))) return rc;
   std::vector<int> ust(d->units.size());
   unit_status_locked(d, ust.data(), (int)ust.size(), st);
-  for (auto& ut : unit_tile)
+  for (auto& ut : W.unit_tile)
     if (ust[ut.first] && !tiles[ut.second].status) tiles[ut.second].status = ust[ut.first];
   return 0;
 }
@@ -1314,6 +1418,218 @@ int micgpu_rgb_decompress(const uint8_t* blob, size_t len, int width, int height
 }  // extern "C"
 
 extern "C" {
+}  // extern "C"
+
+// ---- MIC3 tile ranges: plan once, run many (batch / serving path) ---------------------------------------------------
+struct micgpu_wsi_plan {
+  micgpu_decoder* dec = nullptr;    // owns the unit plan, the scratch and the job tables
+  bool own_dec = false;
+  WsiWork W;
+  uint64_t first = 0, n = 0;
+  uint64_t span_off = 0, span_len = 0;     // bytes of the container that hold the range's tile blobs
+  uint64_t tile_bytes = 0, out_bytes = 0;
+  std::vector<int> host_status;            // per tile: what planning found
+};
+
+namespace {
+
+// C++ twin of shard.partition_by_bytes: contiguous ranges of `n` items balanced by their byte sizes.
+void partition_by_bytes(const uint64_t* sizes, uint64_t n, int parts, std::vector<uint64_t>& cuts) {
+  cuts.assign(parts + 1, n);
+  cuts[0] = 0;
+  unsigned long long total = 0;
+  for (uint64_t i = 0; i < n; i++) total += sizes[i];
+  unsigned long long acc = 0;
+  int p = 1;
+  for (uint64_t i = 0; i < n && p < parts; i++) {
+    acc += sizes[i];
+    while (p < parts && acc * parts >= total * (unsigned long long)p) cuts[p++] = i + 1;
+  }
+  for (int q = 1; q <= parts; q++) cuts[q] = std::max(cuts[q], cuts[q - 1]);
+}
+
+int wsi_plan_build(micgpu_wsi_plan* P, const uint8_t* mic3, size_t len, uint64_t first, uint64_t n) {
+  Mic3Header h;
+  int rc = parse_mic3(mic3, len, h);
+  if (rc) return rc;
+  if (first > h.total_tiles || n > h.total_tiles - first) return fail(MICGPU_E_HEADER, "MIC3: tile range %llu+%llu exceeds %llu tiles", (unsigned long long)first, (unsigned long long)n, (unsigned long long)h.total_tiles);
+  if (n > 0x7FFFFFFFull / 4) return fail(MICGPU_E_UNSUPPORTED, "MIC3: %llu tiles in one plan", (unsigned long long)n);
+  const int bpp = h.bps == 16 ? h.channels * 2 : h.channels;
+  P->first = first; P->n = n;
+  P->tile_bytes = (uint64_t)h.tile_w * h.tile_h * bpp;
+  P->out_bytes = P->tile_bytes * n;
+  P->host_status.assign(n, 0);
+  std::vector<TileReq> tiles(n);
+  uint64_t lo = ~0ull, hi = 0;
+  for (uint64_t t = 0; t < n; t++) {
+    TileReq& T = tiles[t];
+    T.tile_w = h.tile_w; T.tile_h = h.tile_h; T.channels = h.channels; T.bps = h.bps; T.ct = h.ct;
+    T.blob = mic3; T.len = 0;
+    if ((T.status = mic3_tile_blob(mic3, len, h, (long long)(first + t), &T.blob, &T.len))) continue;
+    const uint64_t o = (uint64_t)(T.blob - mic3);
+    lo = std::min(lo, o);
+    hi = std::max(hi, o + T.len);
+    T.blits.push_back(Blit{0, 0, (unsigned)h.tile_w, (unsigned)h.tile_h, t * P->tile_bytes, (unsigned)(h.tile_w * bpp)});
+  }
+  if (hi <= lo) { lo = 0; hi = 0; }
+  P->span_off = lo; P->span_len = hi - lo;
+  for (TileReq& T : tiles)
+    if (!T.status) T.comp_off = (uint64_t)(T.blob - mic3) - lo;
+  micgpu_decoder* d = P->dec;
+  P->W = WsiWork();
+  wsi_build(d, tiles, (size_t)P->out_bytes, P->W);
+  for (uint64_t t = 0; t < n; t++) P->host_status[t] = tiles[t].status;
+  if ((rc = plan_commit(d))) return rc;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if ((rc = d->d_out.ensure(std::max<uint64_t>(P->W.ptot, 1) * sizeof(uint16_t)))) return rc;
+  if ((rc = wsi_upload_jobs(d, P->W, d->stream))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int wsi_plan_fold_status(micgpu_wsi_plan* P, int* tile_status, int n, cudaStream_t st) {
+  micgpu_decoder* d = P->dec;
+  std::vector<int> ust(d->units.size());
+  unit_status_locked(d, ust.data(), (int)ust.size(), st);
+  std::vector<int> ts(P->host_status);
+  for (auto& ut : P->W.unit_tile)
+    if (ust[ut.first] && !ts[ut.second]) ts[ut.second] = ust[ut.first];
+  int first = 0;
+  for (size_t t = 0; t < ts.size(); t++) {
+    if (tile_status && (int)t < n) tile_status[t] = ts[t];
+    if (!first && ts[t]) first = ts[t];
+  }
+  return first;
+}
+
+}  // namespace
+
+extern "C" {
+
+micgpu_wsi_plan* micgpu_wsi_plan_tiles(int device, const uint8_t* mic3, size_t len, uint64_t first_tile, uint64_t n_tiles) {
+  if (!mic3) { fail(MICGPU_E_HEADER, "null argument"); return nullptr; }
+  micgpu_decoder* d = micgpu_decoder_create(device);
+  if (!d) return nullptr;
+  micgpu_wsi_plan* P = new micgpu_wsi_plan();
+  P->dec = d;
+  P->own_dec = true;
+  std::lock_guard<std::mutex> lk(d->mu);
+  if (wsi_plan_build(P, mic3, len, first_tile, n_tiles)) {
+    delete d;
+    delete P;
+    return nullptr;
+  }
+  return P;
+}
+
+void micgpu_wsi_plan_destroy(micgpu_wsi_plan* p) {
+  if (!p) return;
+  if (p->own_dec) delete p->dec;
+  delete p;
+}
+
+int micgpu_wsi_plan_info(const micgpu_wsi_plan* p, uint64_t* span_off, uint64_t* span_len, uint64_t* tile_bytes, uint64_t* out_bytes,
+                         int* n_units) {
+  if (!p) return fail(MICGPU_E_HEADER, "null plan");
+  if (span_off) *span_off = p->span_off;
+  if (span_len) *span_len = p->span_len;
+  if (tile_bytes) *tile_bytes = p->tile_bytes;
+  if (out_bytes) *out_bytes = p->out_bytes;
+  if (n_units) *n_units = (int)p->dec->units.size();
+  return 0;
+}
+
+int micgpu_wsi_plan_run_device(micgpu_wsi_plan* p, const void* d_span, void* d_out, void* cuda_stream) {
+  if (!p || (!d_span && p->span_len) || (!d_out && p->out_bytes)) return fail(MICGPU_E_HEADER, "null argument");
+  micgpu_decoder* d = p->dec;
+  std::lock_guard<std::mutex> lk(d->mu);
+  CUDA_TRY(cudaSetDevice(d->device));
+  return wsi_launch(d, p->W, d_span, (size_t)p->span_len, d->d_out.p, d_out, (cudaStream_t)cuda_stream);
+}
+
+int micgpu_wsi_plan_status(micgpu_wsi_plan* p, int* tile_status, int n, void* cuda_stream) {
+  if (!p) return fail(MICGPU_E_HEADER, "null plan");
+  std::lock_guard<std::mutex> lk(p->dec->mu);
+  return wsi_plan_fold_status(p, tile_status, n, (cudaStream_t)cuda_stream);
+}
+
+int micgpu_wsi_plan_launches(const micgpu_wsi_plan* p) { return p ? p->dec->launches : 0; }
+
+int micgpu_wsi_plan_kernel_times(micgpu_wsi_plan* p, int on, char* names, size_t names_cap, float* ms, int cap) {
+  if (!p) return fail(MICGPU_E_HEADER, "null plan");
+  if (on >= 0) return micgpu_decoder_set_profiling(p->dec, on);
+  return micgpu_decoder_kernel_times(p->dec, names, names_cap, ms, cap);
+}
+
+}  // extern "C"
+
+namespace {
+
+// One device's share of a tile-range call: plan, one H2D copy of the span, kernels, one D2H copy.
+int wsi_range_on_device(int dev, const uint8_t* mic3, size_t len, uint64_t first, uint64_t n, uint8_t* out, int* status, std::string* msg) {
+  auto done = [&](int rc) { if (rc && msg) *msg = err_slot(); return rc; };
+  if (n == 0) return 0;
+  if (cudaSetDevice(dev) != cudaSuccess) return done(fail(MICGPU_E_CUDA, "cudaSetDevice(%d) failed", dev));
+  micgpu_decoder* d = pipe_decoder(dev, PIPE_DEPTH - 1);   // a context of its own: the plan keeps its scratch between calls
+  if (!d) return done(MICGPU_E_CUDA);
+  std::lock_guard<std::mutex> lk(d->mu);
+  micgpu_wsi_plan P;
+  P.dec = d;
+  int rc = wsi_plan_build(&P, mic3, len, first, n);
+  if (rc) return done(rc);
+  if ((rc = d->d_comp.ensure(P.span_len + 256))) return done(rc);
+  if ((rc = d->d_bytes.ensure(std::max<uint64_t>(P.out_bytes, 1)))) return done(rc);
+  cudaStream_t st = d->stream;
+  if (P.span_len && cudaMemcpyAsync(d->d_comp.p, mic3 + P.span_off, P.span_len, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return done(fail(MICGPU_E_CUDA, "H2D copy of the tile span failed"));
+  if ((rc = wsi_launch(d, P.W, d->d_comp.p, (size_t)P.span_len, d->d_out.p, d->d_bytes.p, st))) { cudaStreamSynchronize(st); return done(rc); }
+  if (cudaMemcpyAsync(out, d->d_bytes.p, P.out_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+    cudaStreamSynchronize(st);
+    return done(fail(MICGPU_E_CUDA, "D2H copy of the tiles failed"));
+  }
+  rc = wsi_plan_fold_status(&P, status, (int)n, st);   // synchronises the stream
+  return done(rc);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Tiles [first_tile, first_tile + n_tiles) of the container's tile table, each as a full tile_w x tile_h block
+// (tile_bytes apart, edge tiles keep the zero padding the encoder added, wsicompress.go:529-556).  With several
+// devices configured (micgpu_init) the range is cut by compressed bytes from the u64 offset table
+// (wsiformat.go:145-155) and every device decodes its share on its own host thread.
+int micgpu_wsi_decompress_tile_range(const uint8_t* mic3, size_t len, uint64_t first_tile, uint64_t n_tiles, uint8_t* out, size_t cap,
+                                     int* status) {
+  if (!mic3 || (!out && n_tiles)) return fail(MICGPU_E_HEADER, "null argument");
+  Mic3Header h;
+  int rc = parse_mic3(mic3, len, h);
+  if (rc) return rc;
+  if (first_tile > h.total_tiles || n_tiles > h.total_tiles - first_tile) return fail(MICGPU_E_HEADER, "MIC3: tile range exceeds the tile table");
+  const uint64_t tile_bytes = (uint64_t)h.tile_w * h.tile_h * (h.bps == 16 ? h.channels * 2 : h.channels);
+  if (n_tiles && tile_bytes > cap / n_tiles) return fail(MICGPU_E_SIZE, "output buffer too small for %llu tiles", (unsigned long long)n_tiles);
+  std::vector<int> devs = configured_devices();
+  if (devs.size() <= 1 || n_tiles < 2 * devs.size()) {
+    std::string msg;
+    return wsi_range_on_device(devs.empty() ? current_device() : devs[0], mic3, len, first_tile, n_tiles, out, status, nullptr);
+  }
+  std::vector<uint64_t> sizes(n_tiles), cuts;
+  for (uint64_t t = 0; t < n_tiles; t++) sizes[t] = rd64(mic3 + h.table_off + (size_t)(first_tile + t) * 16 + 8) + 1024;
+  partition_by_bytes(sizes.data(), n_tiles, (int)devs.size(), cuts);
+  std::vector<int> rcs(devs.size(), 0);
+  std::vector<std::string> msgs(devs.size());
+  std::vector<std::thread> th;
+  for (size_t k = 0; k < devs.size(); k++)
+    th.emplace_back([&, k] {
+      rcs[k] = wsi_range_on_device(devs[k], mic3, len, first_tile + cuts[k], cuts[k + 1] - cuts[k], out + cuts[k] * tile_bytes,
+                                   status ? status + cuts[k] : nullptr, &msgs[k]);
+    });
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < devs.size(); k++)
+    if (rcs[k]) { err_slot() = msgs[k]; return rcs[k]; }
+  return 0;
+}
+
 }  // extern "C"
 
 // ---- WaveletV2 ---------------------------------------------------------------------

@@ -59,8 +59,11 @@ def test_ragged_sizes(mic, oracle, w, h, coder):
 
 def test_pics_more_strips_than_rows(mic, oracle, synth):
     # TestParallelStripsSingleRowImage (parallelstrips_test.go:118-144): numStrips > height clamps to one-row strips
-    w, rows = 256, 2
-    img = synth.xr_image(2, w, 64).ravel()[: w * rows]
+    import os
+    from conftest import GOLDEN
+
+    w, rows = 256, 2    # the first two rows of the reference's MR image, as in the Go test
+    img = np.fromfile(os.path.join(GOLDEN, "MR_256_256_image.bin"), dtype="<u2")[: w * rows].copy()
     for nstates in (2, 8):
         blob = oracle.pics_compress(img, w, rows, int(img.max()), 256, nstates)
         assert int.from_bytes(blob[12:16], "little") == 2 and int.from_bytes(blob[16:20], "little") == 1

@@ -23,13 +23,15 @@ def test_fuzz_corrupt_units_in_mixed_batches(mic, oracle, synth):
     """>= 200 seeded damages (bit flips, truncation, inflated symbol count, broken ncount header) on mixed 2/4/8-state
     batches: the call returns, the damaged image never passes silently when the damage is detectable by construction,
     and every neighbour decodes exactly."""
-    shapes = [(97, 33), (300, 60), (64, 64), (211, 47), (500, 17), (128, 40), (257, 29), (40, 150), (33, 31), (256, 2)]
+    shapes = [(97, 33), (300, 60), (64, 64), (211, 47), (500, 17), (128, 40), (257, 29), (40, 150), (333, 31), (256, 12)]
     imgs, blobs, dims = [], [], []
     for i in range(20):
         w, h = shapes[i % len(shapes)]
         im = synth.xr_image(900 + i, w, h).ravel()
         imgs.append(im); dims.append((w, h))
-        blobs.append(oracle.pics_compress(im, w, h, int(im.max()), (1, 2, 4, 3)[i % 4], (2, 4, 8)[i % 3]))
+        # strips of a few rows are too short for the 4-/8-state coders at 12 bits: fewer strips for the flat shapes
+        strips = (1, 2, 4, 3)[i % 4] if h >= 40 else 1
+        blobs.append(oracle.pics_compress(im, w, h, int(im.max()), strips, (2, 4, 8)[i % 3]))
     rc, st, outs = _batch(mic, blobs, dims)
     assert rc == 0 and all(np.array_equal(o, im) for o, im in zip(outs, imgs))
     kinds = ("flip", "truncate", "count", "ncount")
@@ -94,7 +96,7 @@ def test_mic2_residual_of_wrong_length_is_rejected(mic, oracle, synth):
     """A temporal residual frame must expand to exactly width*height words (multiframecompress.go:165-175 + TemporalDeltaDecode);
     a shorter one used to succeed and leave stale scratch in the running sum."""
     w, h, nf = 64, 48, 4
-    st = synth.tomo_stack(9, nf, w, h)
+    st = synth.tomo_stack(9, nf, h, w)     # (frames, rows, cols)
     blob = bytearray(oracle.mic2_compress(st.ravel(), w, h, 1023, True))
     res = oracle.temporal_encode(st[2].ravel(), st[1].ravel())
     short = oracle.compress_residual_frame(res[: w * h - 100], int(res.max()))
@@ -116,7 +118,7 @@ def test_mic2_residual_of_wrong_length_is_rejected(mic, oracle, synth):
     with pytest.raises(mic.MicGpuError):
         mic.DecompressMultiFrame(bytes(out))
     frames_ok, _ = mic.DecompressMultiFrame(bytes(blob))
-    assert np.array_equal(frames_ok, st)
+    assert np.array_equal(frames_ok.reshape(st.shape), st)
 
 
 def _wsi_blob(oracle, synth):

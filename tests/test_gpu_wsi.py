@@ -78,3 +78,83 @@ def test_greyscale_slide(mic, oracle, synth, bps):
                 assert (gw, gh) == (rw, rh) and np.array_equal(got, ref)
     full, fw, fh = mic.DecompressWSIRegion(blob, 0, 0, 0, W, H)
     assert np.array_equal(full.tobytes(), px)
+
+
+def _full_tiles_from_oracle(oracle, blob, hdr):
+    """Every tile of the table as a full (zero-padded) tile, from the oracle's cropped tiles."""
+    tw, th = hdr["TileWidth"], hdr["TileHeight"]
+    bpp = hdr["Channels"] * (2 if hdr["BitsPerSample"] == 16 else 1)
+    out = []
+    for l, (w, h, ntx, nty, first) in enumerate(hdr["Levels"]):
+        for ty in range(nty):
+            for tx in range(ntx):
+                ref, rw, rh = oracle.wsi_decompress_tile(blob, l, tx, ty)
+                full = np.zeros((th, tw * bpp), np.uint8)
+                full[:rh, : rw * bpp] = np.asarray(ref, np.uint8).reshape(rh, rw * bpp)
+                out.append(full.ravel())
+    return out
+
+
+def test_tile_range_batch(mic, oracle, slide):
+    """The batch / serving path: tile-index ranges of the table decode to full tiles, in one call and through a plan
+    that runs from device-resident bytes (micgpu_wsi_plan_*).  Edge tiles carry the encoder's zero padding."""
+    import torch
+
+    rgb, blob = slide
+    hdr = mic.ReadWSIHeader(blob)
+    ref = _full_tiles_from_oracle(oracle, blob, hdr)
+    n = hdr["TotalTiles"]
+    assert n == len(ref)
+    got = mic.DecompressWSITileRange(blob, 0, n)
+    for i in range(n):
+        assert np.array_equal(got[i], ref[i]), i
+    # sub-ranges, including one that starts inside level 0 and ends in level 1, and an empty one
+    for first, cnt in [(2, 5), (7, n - 7), (n - 1, 1), (3, 0)]:
+        part = mic.DecompressWSITileRange(blob, first, cnt)
+        assert part.shape[0] == cnt
+        for i in range(cnt):
+            assert np.array_equal(part[i], ref[first + i]), (first, i)
+    with pytest.raises(mic.MicGpuError):
+        mic.DecompressWSITileRange(blob, n - 1, 2)
+    # plan once, run twice from device memory
+    a = np.frombuffer(blob, np.uint8)
+    plan = mic.WsiPlan(blob, 1, n - 2)
+    assert plan.tile_bytes == 256 * 256 * 3 and plan.out_bytes == (n - 2) * plan.tile_bytes and plan.n_units > 0
+    d_span = torch.zeros(plan.span_len + 256, dtype=torch.uint8, device="cuda")
+    d_span[: plan.span_len] = torch.from_numpy(a[plan.span_off: plan.span_off + plan.span_len].copy()).cuda()
+    d_out = torch.zeros(plan.out_bytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        d_out.fill_(0x5A)
+        plan.run_device(d_span.data_ptr(), d_out.data_ptr(), stream)
+        assert not any(plan.status(stream))
+        out = d_out.cpu().numpy().reshape(n - 2, plan.tile_bytes)
+        for i in range(n - 2):
+            assert np.array_equal(out[i], ref[1 + i]), i
+    assert plan.last_launches >= 4
+    plan.close()
+
+
+def test_tile_range_reports_the_damaged_tile(mic, oracle, slide):
+    rgb, blob = slide
+    hdr = mic.ReadWSIHeader(blob)
+    n = hdr["TotalTiles"]
+    nlv = len(hdr["Levels"])
+    table_off = 48 + 20 * nlv
+    data_off = table_off + 16 * n
+    b = bytearray(blob)
+    o = int.from_bytes(blob[table_off + 16 * 4: table_off + 16 * 4 + 8], "little")
+    b[data_off + o + 1] ^= 0xFF                 # plane length of tile 4 no longer fits its blob
+    b[data_off + o + 3] |= 0x40
+    a = np.frombuffer(bytes(b), np.uint8)
+    tile_bytes = 256 * 256 * 3
+    out = np.zeros(n * tile_bytes, np.uint8)
+    import ctypes as C
+
+    st = (C.c_int * n)()
+    rc = mic.lib.micgpu_wsi_decompress_tile_range(a.ctypes.data, a.size, C.c_uint64(0), C.c_uint64(n), out.ctypes.data, out.size, st)
+    assert rc != 0 and st[4] != 0
+    good = mic.DecompressWSITileRange(blob, 0, n)
+    for i in range(n):
+        if i != 4:
+            assert st[i] == 0 and np.array_equal(out[i * tile_bytes:(i + 1) * tile_bytes], good[i]), i

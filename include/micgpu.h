@@ -56,6 +56,10 @@ void micgpu_host_free(void *p);
  * contiguous unit range balanced by compressed bytes, its own host thread, stream and scratch; nothing is exchanged
  * between devices except the carry frames of a temporal MIC2 stack (peer reads). */
 int micgpu_init(const int *devices, int n);
+/* The partition those calls use, exported for callers that shard by process instead (one rank per GPU): `parts`
+ * contiguous ranges of n units balanced by sizes[] (compressed bytes from the container's own offset table:
+ * parallelstrips.go:115-122, multiframe.go:72-78, wsiformat.go:145-155); cuts[] receives parts + 1 boundaries. */
+int micgpu_partition_by_bytes(const uint64_t *sizes, uint64_t n, int parts, uint64_t *cuts);
 /* Release the per-device default contexts used by the one-shot calls (and forget the device list). */
 void micgpu_shutdown(void);
 

@@ -68,6 +68,7 @@ struct micgpu_decoder {
   bool committed = false;
   int launches = 0;
   DevBuf d_units, d_list, d_tabA, d_tabS, d_states, d_D, d_M, d_k1, d_comp, d_out, d_queue;
+  DevBuf d_park, d_peer;    // multi-device temporal MIC2: this range's relative last frame; staged copies of the peers' frames
   DevBuf d_norm, d_psym;    // split table build: present-symbol lists (normalised count, symbol value) at each unit's tab_off
   bool k1_split = true, k1_fallback = false;
   DevBuf d_jobs, d_bytes;   // MIC3: fill / blit job tables, byte-typed pixel output
@@ -89,7 +90,7 @@ struct micgpu_decoder {
   ~micgpu_decoder() {
     cudaSetDevice(device);
     d_units.release(); d_list.release(); d_tabA.release(); d_tabS.release(); d_states.release();
-    d_D.release(); d_M.release(); d_k1.release(); d_norm.release(); d_psym.release(); d_queue.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
+    d_D.release(); d_M.release(); d_k1.release(); d_norm.release(); d_psym.release(); d_park.release(); d_peer.release(); d_queue.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
     for (int p = 0; p < PARTS; p++) {
@@ -511,6 +512,28 @@ std::vector<int> g_devices;
 std::vector<int> configured_devices() {
   std::lock_guard<std::mutex> lk(g_dev_mu);
   return g_devices;
+}
+
+// C++ twin of shard.partition_by_bytes: `parts` contiguous ranges of n units with near-equal byte sums;
+// every unit owned exactly once, trailing ranges may be empty when there are fewer units than parts.
+void partition_by_bytes(const uint64_t* sizes, uint64_t n, int parts, std::vector<uint64_t>& cuts) {
+  cuts.assign((size_t)parts + 1, n);
+  unsigned __int128 total = 0;
+  for (uint64_t i = 0; i < n; i++) total += sizes[i];
+  uint64_t lo = 0;
+  unsigned __int128 acc = 0;
+  for (int r = 0; r < parts; r++) {
+    cuts[r] = lo;
+    uint64_t hi = lo;
+    // target = total * (r + 1) / parts, compared without the division
+    while (hi < n && ((acc + sizes[hi]) * (unsigned)parts <= total * (unsigned)(r + 1) || (hi == lo && n - hi > (uint64_t)(parts - 1 - r)))) {
+      acc += sizes[hi];
+      hi++;
+    }
+    if (r == parts - 1) hi = n;
+    lo = hi;
+  }
+  cuts[parts] = n;
 }
 
 micgpu_decoder* default_decoder(int dev) {
@@ -944,10 +967,15 @@ micgpu_decoder* pipe_decoder(int dev, int k) {
 
 extern "C" {
 
-int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
-                                 const size_t* caps, int* status) {
+}  // extern "C"
+
+namespace {
+
+// One device's share of a PICS batch (all of it without micgpu_init).
+int pics_batch_on_device(int dev, int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
+                         const size_t* caps, int* status) {
   if (n <= 0) return 0;
-  const int dev = current_device();
+  if (cudaSetDevice(dev) != cudaSuccess) return fail(MICGPU_E_CUDA, "cudaSetDevice(%d) failed", dev);
   int first = 0, rc;
   if (n < 16) {
     micgpu_decoder* d = default_decoder(dev);
@@ -991,6 +1019,37 @@ int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_
   for (int k = 0; k < PIPE_DEPTH; k++)
     if ((rc = pics_finish(D[k], P[k], status, &first))) { drain(); return rc; }
   return first;
+}
+
+}  // namespace
+
+extern "C" {
+
+int micgpu_pics_decompress_batch(int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
+                                 const size_t* caps, int* status) {
+  if (n <= 0) return 0;
+  if (!blobs || !lens || !outs || !caps) return fail(MICGPU_E_HEADER, "null argument");
+  const std::vector<int> devs = configured_devices();
+  if (devs.size() <= 1 || n < 2 * (int)devs.size())
+    return pics_batch_on_device(devs.empty() ? current_device() : devs[0], n, blobs, lens, outs, caps, status);
+  // several devices: contiguous image ranges balanced by compressed bytes, one host thread per device (the goroutine
+  // pool of parallelstrips.go:292-321 becomes one batched launch sequence per device); nothing is exchanged
+  std::vector<uint64_t> sizes(n), cuts;
+  for (int i = 0; i < n; i++) sizes[i] = lens[i];
+  partition_by_bytes(sizes.data(), (uint64_t)n, (int)devs.size(), cuts);
+  std::vector<int> rcs(devs.size(), 0);
+  std::vector<std::string> msgs(devs.size());
+  std::vector<std::thread> th;
+  for (size_t k = 0; k < devs.size(); k++)
+    th.emplace_back([&, k] {
+      const int i0 = (int)cuts[k], i1 = (int)cuts[k + 1];
+      rcs[k] = pics_batch_on_device(devs[k], i1 - i0, blobs + i0, lens + i0, outs + i0, caps + i0, status ? status + i0 : nullptr);
+      if (rcs[k]) msgs[k] = err_slot();
+    });
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < devs.size(); k++)
+    if (rcs[k]) { err_slot() = msgs[k]; return rcs[k]; }   // first failing image in batch order (parallelstrips.go:324-328)
+  return 0;
 }
 
 int micgpu_pics_decompress(const uint8_t* pics, size_t len, uint16_t* pixels_out, size_t cap_px, int* width, int* height) {
@@ -1063,8 +1122,134 @@ static int mic2_decode(const uint8_t* mic2, size_t len, int last_frame, bool onl
   return unit_status_locked(d, nullptr, 0, d->stream);
 }
 
+// DecompressMultiFrame over the configured devices: frame ranges balanced by compressed bytes (multiframe.go:72-78), one
+// host thread per device.  Independent mode needs nothing else.  Temporal mode (multiframecompress.go:236-258): every
+// range decodes to running sums relative to a zero carry, parks its last frame, and after a host barrier ONE kernel per
+// device reads the parked frames of the earlier devices straight out of their memory (peer access over NVLink; a
+// staged peer copy where the topology has none), forms the carry and finishes its frames -- the single exchange step of
+// the whole path.
+static int mic2_decode_multi(const std::vector<int>& devs, const uint8_t* mic2, size_t len, const Mic2Header& mh0, uint16_t* out) {
+  const int nd = (int)devs.size();
+  const size_t fpx = (size_t)mh0.w * mh0.h;
+  std::vector<uint64_t> sizes(mh0.n), cuts;
+  for (int i = 0; i < mh0.n; i++) sizes[i] = rd32(mic2 + 24 + (size_t)i * 8);
+  partition_by_bytes(sizes.data(), (uint64_t)mh0.n, nd, cuts);
+  std::vector<micgpu_decoder*> D(nd);
+  for (int k = 0; k < nd; k++)
+    if (!(D[k] = default_decoder(devs[k]))) return MICGPU_E_CUDA;
+  std::vector<std::unique_lock<std::mutex>> locks;
+  for (int k = 0; k < nd; k++) locks.emplace_back(D[k]->mu);   // device-list order: no two calls can deadlock
+  std::vector<int> rcs(nd, 0);
+  std::vector<std::string> msgs(nd);
+  auto phase = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++)
+      th.emplace_back([&, k] {
+        rcs[k] = fn(k);
+        if (rcs[k]) msgs[k] = err_slot();
+      });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < nd; k++)
+      if (rcs[k]) { err_slot() = msgs[k]; return rcs[k]; }
+    return 0;
+  };
+  // ---- phase 1: every device decodes its frame range ---------------------------------------------------------
+  int rc = phase([&](int k) -> int {
+    const int f0 = (int)cuts[k], f1 = (int)cuts[k + 1];
+    if (f1 <= f0) return 0;
+    micgpu_decoder* d = D[k];
+    CUDA_TRY(cudaSetDevice(d->device));
+    d->units.clear();
+    d->temporal.clear();
+    d->zero_ranges.clear();
+    d->out_need = 0;
+    // only the bytes of this range travel: [span0, span1) of the container sits at offset 0 of the device buffer
+    const size_t o0 = rd32(mic2 + 20 + (size_t)f0 * 8), o1 = rd32(mic2 + 20 + (size_t)(f1 - 1) * 8), l1 = rd32(mic2 + 24 + (size_t)(f1 - 1) * 8);
+    size_t span0 = mh0.data_off + o0, span1 = mh0.data_off + o1 + l1;
+    for (int i = f0; i < f1; i++) {   // frame tables are written in order, but nothing forces them to be
+      const size_t o = rd32(mic2 + 20 + (size_t)i * 8), l = rd32(mic2 + 24 + (size_t)i * 8);
+      span0 = std::min(span0, mh0.data_off + o);
+      span1 = std::max(span1, mh0.data_off + o + l);
+    }
+    if (span1 > len) return fail(MICGPU_E_HEADER, "MIC2: frame data extends beyond file");
+    Mic2Header mh;
+    int r = add_mic2_locked(d, mic2, len, (uint64_t)0 - (uint64_t)span0, 0, f1 - 1, mh, f0);
+    if (r) return r;
+    if ((r = plan_commit(d))) return r;
+    const size_t nfr = (size_t)(f1 - f0);
+    if ((r = d->d_comp.ensure(span1 - span0 + 256))) return r;
+    if ((r = d->d_out.ensure(nfr * fpx * sizeof(uint16_t)))) return r;
+    CUDA_TRY(cudaMemcpyAsync(d->d_comp.p, mic2 + span0, span1 - span0, cudaMemcpyHostToDevice, d->stream));
+    if ((r = run_device_locked(d, d->d_comp.p, span1 - span0, d->d_out.p, nfr * fpx, d->stream))) return r;
+    if (mh0.temporal) {
+      if ((r = d->d_park.ensure(fpx * sizeof(uint16_t) + 16))) return r;
+      CUDA_TRY(cudaMemcpyAsync(d->d_park.p, (uint16_t*)d->d_out.p + (nfr - 1) * fpx, fpx * sizeof(uint16_t), cudaMemcpyDeviceToDevice, d->stream));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(out + (size_t)f0 * fpx, d->d_out.p, nfr * fpx * sizeof(uint16_t), cudaMemcpyDeviceToHost, d->stream));
+    }
+    return unit_status_locked(d, nullptr, 0, d->stream);   // synchronises the stream
+  });
+  if (rc || !mh0.temporal) return rc;
+  // ---- phase 2 (temporal): carry from the parked frames of the earlier devices, then the copy back ----------------
+  return phase([&](int k) -> int {
+    const int f0 = (int)cuts[k], f1 = (int)cuts[k + 1];
+    if (f1 <= f0) return 0;
+    micgpu_decoder* d = D[k];
+    CUDA_TRY(cudaSetDevice(d->device));
+    const size_t nfr = (size_t)(f1 - f0);
+    PeerFrames pf;
+    pf.n = 0;
+    pf.aligned = (fpx % 8 == 0) ? 1 : 0;
+    int staged = 0;
+    for (int q = 0; q < k; q++) {
+      if (cuts[q + 1] <= cuts[q]) continue;     // an empty range carries nothing
+      if (pf.n >= 16) return fail(MICGPU_E_UNSUPPORTED, "temporal MIC2 over more than 17 devices");
+      const uint16_t* src = (const uint16_t*)D[q]->d_park.p;
+      int can = 0;
+      if (D[q]->device != d->device) {
+        cudaDeviceCanAccessPeer(&can, d->device, D[q]->device);
+        if (can) {
+          const cudaError_t e = cudaDeviceEnablePeerAccess(D[q]->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+          cudaGetLastError();
+        }
+        if (!can) {   // no peer mapping on this topology: the frame is copied over instead of read in place
+          int r = d->d_peer.ensure((size_t)16 * (fpx * sizeof(uint16_t) + 16));
+          if (r) return r;
+          uint16_t* dst = (uint16_t*)((uint8_t*)d->d_peer.p + (size_t)staged * (fpx * sizeof(uint16_t) + 16));
+          CUDA_TRY(cudaMemcpyPeerAsync(dst, d->device, src, D[q]->device, fpx * sizeof(uint16_t), d->stream));
+          src = dst;
+          staged++;
+        }
+      }
+      if (reinterpret_cast<uintptr_t>(src) % 16) pf.aligned = 0;
+      pf.last[pf.n++] = src;
+    }
+    if (reinterpret_cast<uintptr_t>(d->d_out.p) % 16) pf.aligned = 0;
+    if (pf.n) launch_temporal_add_carry_peers((uint16_t*)d->d_out.p, pf, fpx, (int)nfr, d->sm_count, d->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out + (size_t)f0 * fpx, d->d_out.p, nfr * fpx * sizeof(uint16_t), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return 0;
+  });
+}
+
 int micgpu_mic2_decompress(const uint8_t* mic2, size_t len, uint16_t* frames_out, size_t cap_px, int* width, int* height,
                            int* frames, int* temporal) {
+  const std::vector<int> devs = configured_devices();
+  if (devs.size() > 1 && mic2 && frames_out) {
+    Mic2Header mh;
+    int rc = parse_mic2(mic2, len, mh);
+    if (rc) return rc;
+    if (mh.n >= 2 * (int)devs.size() && (unsigned long long)mh.w * mh.h <= 0xFFFFFFFFull) {
+      if (width) *width = mh.w;
+      if (height) *height = mh.h;
+      if (frames) *frames = mh.n;
+      if (temporal) *temporal = mh.temporal;
+      if ((size_t)mh.n * mh.w * mh.h > cap_px) return fail(MICGPU_E_SIZE, "output buffer too small");
+      return mic2_decode_multi(devs, mic2, len, mh, frames_out);
+    }
+  }
   return mic2_decode(mic2, len, -1, false, frames_out, cap_px, width, height, frames, temporal);
 }
 
@@ -1433,21 +1618,6 @@ struct micgpu_wsi_plan {
 
 namespace {
 
-// C++ twin of shard.partition_by_bytes: contiguous ranges of `n` items balanced by their byte sizes.
-void partition_by_bytes(const uint64_t* sizes, uint64_t n, int parts, std::vector<uint64_t>& cuts) {
-  cuts.assign(parts + 1, n);
-  cuts[0] = 0;
-  unsigned long long total = 0;
-  for (uint64_t i = 0; i < n; i++) total += sizes[i];
-  unsigned long long acc = 0;
-  int p = 1;
-  for (uint64_t i = 0; i < n && p < parts; i++) {
-    acc += sizes[i];
-    while (p < parts && acc * parts >= total * (unsigned long long)p) cuts[p++] = i + 1;
-  }
-  for (int q = 1; q <= parts; q++) cuts[q] = std::max(cuts[q], cuts[q - 1]);
-}
-
 int wsi_plan_build(micgpu_wsi_plan* P, const uint8_t* mic3, size_t len, uint64_t first, uint64_t n) {
   Mic3Header h;
   int rc = parse_mic3(mic3, len, h);
@@ -1599,6 +1769,14 @@ extern "C" {
 // (tile_bytes apart, edge tiles keep the zero padding the encoder added, wsicompress.go:529-556).  With several
 // devices configured (micgpu_init) the range is cut by compressed bytes from the u64 offset table
 // (wsiformat.go:145-155) and every device decodes its share on its own host thread.
+int micgpu_partition_by_bytes(const uint64_t* sizes, uint64_t n, int parts, uint64_t* cuts) {
+  if ((!sizes && n) || !cuts || parts <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  std::vector<uint64_t> c;
+  partition_by_bytes(sizes, n, parts, c);
+  for (int i = 0; i <= parts; i++) cuts[i] = c[i];
+  return 0;
+}
+
 int micgpu_wsi_decompress_tile_range(const uint8_t* mic3, size_t len, uint64_t first_tile, uint64_t n_tiles, uint8_t* out, size_t cap,
                                      int* status) {
   if (!mic3 || (!out && n_tiles)) return fail(MICGPU_E_HEADER, "null argument");

@@ -128,7 +128,7 @@ def run(mic, torch, steps: int, warmup: int, side: int = 32768, seed: int = 11, 
 
     orc = Oracle()
     s = SRC_SIDE // TILE
-    checks = [(0, 0), (n_side // 2, n_side // 2), (n_side - 1, n_side - 1), (s + 13, 2 * s + 17), (n_side // 2 + 3, 5), (17, n_side - 9)]
+    checks = [(0, 0), (n_side // 2, n_side // 2), (n_side - 1, n_side - 1), ((s + 13) % n_side, (2 * s + 17) % n_side), (n_side // 2 + 3, 5), (17, n_side - 9)]
     blob_b = blob.tobytes() if blob.size < (1 << 31) else None
     for tx, ty in checks:
         idx = ty * n_side + tx

@@ -10,11 +10,16 @@ Workload (config.workload): BASELINE configs[1] -- PICS-8 parallel strips Delta+
 
 `value`  : decode GB/s of raw pixel bytes, streams resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : the same metric through the C-ABI host call micgpu_pics_decompress_batch (host buffers in
-           and out, H2D/D2H inside the timed region).
+           and out, H2D/D2H inside the timed region), --steps steps.
 `roofline`: dominant kernel's (compressed bytes read + raw bytes written) / its CUDA-event time vs the
-           measured HBM copy bandwidth in MEASURED_PEAKS.json.
+           measured HBM copy bandwidth in MEASURED_PEAKS.json; `traffic` from the ncu capture summarised in
+           profiles/traffic.json (tools/ncu_summary.py), keyed by the kernel as launched.
 `cpu_baseline`: the reference's own C decoder (oracle/_ref, built from /root/reference/ojph/*.c) on the
            host cores of the same box, bounded sample.
+Extra keys at N=1 (not part of the contract metric; the same measurement rules):
+`value_2state` / `e2e_2state` / `roofline_2state`: the same batch as 2-state strips, the stream CompressParallelStrips
+           emits by default (parallelstrips.go:55);
+`mic3`   : BASELINE configs[4], level-0 tile decode of a 32768x32768 procedural slide window (tools/mic3_bench.py).
 
 Input generation (not timed): synthetic images are encoded once by the product's own CUDA encoder
 (micgpu_pics_compress_batch); the CPU oracle only encodes the inputs of the --impl reference / cpu_baseline legs.
@@ -43,6 +48,9 @@ PKG = "medical-image-codec_b200"
 W, H, STRIPS = 2577, 2048, 8
 METRIC = "pics8_decode_GBps"
 UNIT = "GB/s"
+REF_BUILD_NOTE = ("oracle/_ref/libmicref.so = the reference's ojph/mic_{compress,decompress}_c.c + mic_parallel.c compiled by oracle/Makefile with "
+                  "-O3 -march=x86-64-v3 (AVX2; the cgo build uses -march=native, ojph/mic_c.go:12-14, but the .so is built where the "
+                  "sources are and travels to the GPU box, which has no /root/reference)")
 
 
 def log(*a):
@@ -56,6 +64,17 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def load_synth():
+    """The synthetic generators by file path: importing the package would load libmicgpu.so, which the reference arm
+    must not map."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("micgpu_synth", os.path.join(ROOT, PKG, "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_inputs(batch: int, distinct: int, nstates: int, seed0: int, use_gpu: bool = True):
     """-> (list of PICS blobs (bytes), raw image bytes per image, encode stats).  `distinct` images are generated
     and encoded; the batch cycles through them (each copy is a separate buffer on the device).
@@ -63,7 +82,7 @@ def make_inputs(batch: int, distinct: int, nstates: int, seed0: int, use_gpu: bo
     use_gpu=True : inputs come from the product's own CUDA encoder (CompressParallelStrips8State semantics,
                    byte-identical to the reference encoder, tests/test_gpu_encode.py).
     use_gpu=False: the CPU oracle encodes them (the --impl reference arm has no GPU dependency)."""
-    synth = importlib.import_module(PKG + ".synth")
+    synth = load_synth()
     with ThreadPoolExecutor(max_workers=host_threads()) as ex:
         imgs = list(ex.map(lambda i: synth.xr_image(seed0 + i, W, H).ravel(), range(distinct)))
     stats = {}
@@ -143,11 +162,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload_key: str):
+def ncu_traffic(workload_key: str, kernel: str):
+    """dram read+write bytes per launch of `kernel` on `workload_key`, from the ncu capture summarised by
+    tools/ncu_summary.py into profiles/traffic.json (None when no capture of this kernel on this workload is committed)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload_key)
+            return json.load(open(p)).get(workload_key, {}).get(kernel)
         except Exception:
             return None
     return None
@@ -189,9 +210,10 @@ def run_reference(args, rank, world):
         if rc != 0:
             raise RuntimeError(f"reference decoder rc={rc}")
 
+    pool = ThreadPoolExecutor(max_workers=nthreads)    # created once: thread start-up is not part of a step
+
     def step():
-        with ThreadPoolExecutor(max_workers=nthreads) as ex:
-            list(ex.map(work, tasks))
+        list(pool.map(work, tasks))
 
     for _ in range(max(1, min(args.warmup, 2))):
         step()
@@ -199,6 +221,7 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
+    pool.shutdown()
     gbs = sample * raw_per / dt / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -207,7 +230,8 @@ def run_reference(args, rank, world):
         "config": {"workload": f"PICS-8 {nst}-state Delta+RLE+FSE decode, synthetic 2577x2048 12-bit XR, sample of {sample} images "
                                f"({sample * STRIPS} strips) of the batch of {args.batch}", "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": round(gbs, 4), "unit": UNIT, "cores": nthreads, "kind": "reference",
-                         "sample": f"{sample} images x {STRIPS} strips, mic_decompress_{name}_state_simd per strip, {nthreads} host threads"},
+                         "sample": f"{sample} images x {STRIPS} strips, mic_decompress_{name}_state_simd per strip, {nthreads} host threads",
+                         "build": REF_BUILD_NOTE},
         "e2e": {"value": round(gbs, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -215,25 +239,13 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------
-def run_ours(args, rank, local_rank, world):
+def pics_leg(ctx, nst, full):
+    """One PICS-8 decode measurement with `nst`-state strips: device-resident arm, per-kernel pass, e2e arm and (full
+    only) the encode twin.  Returns a dict of raw measurements for this rank."""
     import torch
 
-    import __graft_entry__ as g
-
-    g.build()
-    mic = importlib.import_module(PKG)
+    args, rank, local_rank, mic, dist = ctx["args"], ctx["rank"], ctx["local_rank"], ctx["mic"], ctx["dist"]
     api = mic.api
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (micgpu has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    nst = args.nstates
     t_setup = time.time()
     blobs, raw_per, enc_stats = make_inputs(args.batch, args.distinct, nst, 1 + 1000 * rank, use_gpu=True)
     imgs_max = enc_stats.pop("_max_values")
@@ -253,7 +265,7 @@ def run_ours(args, rank, local_rank, world):
     h_out = np.ctypeslib.as_array(C.cast(h_out_ptr, C.POINTER(C.c_uint16)), shape=(raw_bytes // 2,))
     for b, o in zip(blobs, offs):
         h_comp[o:o + len(b)] = np.frombuffer(b, np.uint8)
-    log(f"[rank {rank}] setup: {n} images, {tot / 1e6:.1f} MB compressed, ratio {raw_bytes / comp_bytes_alg:.3f}, {time.time() - t_setup:.1f}s")
+    log(f"[rank {rank}] {nst}-state setup: {n} images, {tot / 1e6:.1f} MB compressed, ratio {raw_bytes / comp_bytes_alg:.3f}, {time.time() - t_setup:.1f}s")
 
     # ---- device-resident arm -----------------------------------------------------------------
     d_comp = torch.empty(tot + 256, dtype=torch.uint8, device="cuda")
@@ -274,8 +286,7 @@ def run_ours(args, rank, local_rank, world):
     st = dec.unit_status(stream)
     assert not any(st), "unit decode failed"
     # correctness guard inside the bench: image 0 decodes to the generator's pixels
-    synth = importlib.import_module(PKG + ".synth")
-    ref0 = synth.xr_image(1 + 1000 * rank, W, H).ravel()
+    ref0 = load_synth().xr_image(1 + 1000 * rank, W, H).ravel()
     got0 = d_out[: W * H].cpu().numpy().view(np.uint16)
     assert np.array_equal(got0, ref0), "decoded pixels differ from the source image"
 
@@ -296,7 +307,7 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     ms_dev = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
-    launches = dec.last_launches      # kernels of one timed step (K1, K2, then K3 + K4 for each of the four unit ranges)
+    launches = dec.last_launches      # kernels of one timed step
 
     # per-kernel breakdown (separate pass, CUDA events between launches on the same stream)
     dec.set_profiling(True)
@@ -307,6 +318,9 @@ def run_ours(args, rank, local_rank, world):
         for name, ms in dec.kernel_times():
             acc[name] = acc.get(name, 0.0) + ms / prof_iters
     dec.set_profiling(False)
+    dec.close()
+    del d_comp, d_out
+    torch.cuda.empty_cache()
 
     # ---- end-to-end arm: C-ABI host call, pinned host buffers, copies inside the timed region ----
     bp = (C.c_void_p * n)(*[h_comp_ptr + o for o in offs])
@@ -320,11 +334,10 @@ def run_ours(args, rank, local_rank, world):
         if rc != 0:
             raise RuntimeError("micgpu_pics_decompress_batch rc=%d: %s" % (rc, api.last_error()))
 
-    e2e_warm = max(1, min(args.warmup, 2))
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, args.steps)
     ms_e2e = float("nan")
     if not args.quick:
-        for _ in range(e2e_warm):
+        for _ in range(max(1, min(args.warmup, 3))):
             step_e2e()
         assert np.array_equal(h_out[: W * H], ref0), "e2e decoded pixels differ from the source image"
         barrier()
@@ -338,7 +351,7 @@ def run_ours(args, rank, local_rank, world):
     # The decoded batch sitting in the pinned output buffer is encoded back through micgpu_pics_compress_batch into
     # pinned memory and must reproduce the input containers byte for byte.
     enc_info = None
-    if not args.quick:
+    if full and not args.quick:
         mv = (C.c_uint16 * n)(*[int(imgs_max[i % len(imgs_max)]) for i in range(n)])
         ecap = [len(b) + 4096 for b in blobs]
         eoffs, etot = [], 0
@@ -370,6 +383,53 @@ def run_ours(args, rank, local_rank, world):
                         "api": "micgpu_pics_compress_batch (pinned host buffers, this rank only)",
                         "byte_identical_to_inputs": bool(same)}
             api.lib.micgpu_host_free(h_enc_ptr)
+    api.lib.micgpu_host_free(h_comp_ptr)
+    api.lib.micgpu_host_free(h_out_ptr)
+    return {"ms_dev": ms_dev, "ms_e2e": ms_e2e, "e2e_steps": e2e_steps, "launches": launches, "acc": acc, "clocks": clocks,
+            "comp_bytes": comp_bytes_alg, "raw_bytes": raw_bytes, "enc_stats": enc_stats, "enc_info": enc_info}
+
+
+def roofline_of(leg, nst, args, ms_dev):
+    peak, peak_src = measured_peak()
+    acc = leg["acc"]
+    dom = max(acc.items(), key=lambda kv: kv[1]) if acc else ("none", ms_dev)
+    alg_bytes = leg["comp_bytes"] + leg["raw_bytes"]          # per launch of the dominant kernel: this rank's whole batch
+    achieved = alg_bytes / (dom[1] * 1e-3) / 1e9
+    wkey = f"pics8_{nst}state_b{args.batch}"
+    return {
+        "bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": ncu_traffic(wkey, dom[0]),
+        "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(dom[1], 4),
+        "pipeline_achieved": round(alg_bytes / (ms_dev * 1e-3) / 1e9, 2),
+        "pipeline_frac": round(alg_bytes / (ms_dev * 1e-3) / 1e9 / peak, 4),
+        "stages_ms": {k: round(v, 4) for k, v in acc.items()},
+        "stages_note": "per-kernel CUDA-event times of a separate profiling pass that runs the kernels back to back on one "
+                       "stream; the timed step overlaps the K3/K4 launches of four unit ranges on their own streams",
+    }
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+
+    import __graft_entry__ as g
+
+    g.build()
+    mic = importlib.import_module(PKG)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (micgpu has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = {"args": args, "rank": rank, "local_rank": local_rank, "mic": mic, "dist": dist}
+
+    nst = args.nstates
+    leg = pics_leg(ctx, nst, full=True)
+    ms_dev, ms_e2e = leg["ms_dev"], leg["ms_e2e"]
+    raw_bytes, comp_bytes_alg = leg["raw_bytes"], leg["comp_bytes"]
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
     if dist:
@@ -380,22 +440,34 @@ def run_ours(args, rank, local_rank, world):
     value = total_raw / (ms_dev * 1e-3) / 1e9
     e2e_val = total_raw / (ms_e2e * 1e-3) / 1e9
 
+    # ---- extra legs on a single GPU: the API-default 2-state strips and the MIC3 tile workload -------------------------
+    extra = {}
+    if world == 1 and not args.quick and not args.no_extra:
+        if nst != 2:
+            leg2 = pics_leg(ctx, 2, full=False)
+            extra["value_2state"] = round(leg2["raw_bytes"] / (leg2["ms_dev"] * 1e-3) / 1e9, 3)
+            extra["e2e_2state"] = {"value": round(leg2["raw_bytes"] / (leg2["ms_e2e"] * 1e-3) / 1e9, 3), "unit": UNIT,
+                                   "ms_per_step": round(leg2["ms_e2e"], 3), "steps": leg2["e2e_steps"],
+                                   "h2d_bytes_per_step": leg2["comp_bytes"], "d2h_bytes_per_step": leg2["raw_bytes"]}
+            extra["roofline_2state"] = roofline_of(leg2, 2, args, leg2["ms_dev"])
+            extra["config_2state"] = {"workload": "the same batch as 2-state strips: what CompressParallelStrips emits by default (parallelstrips.go:55)",
+                                      "ms_per_step": round(leg2["ms_dev"], 4), "ratio": round(leg2["raw_bytes"] / leg2["comp_bytes"], 3),
+                                      "gpu_launches_per_step": leg2["launches"]}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            mic3_bench = importlib.import_module("mic3_bench")
+            m3 = mic3_bench.run(mic, torch, max(3, min(args.steps, 10)), 3, side=args.mic3_side, log=log)
+            peak, peak_src = measured_peak()
+            if "roofline" in m3:
+                m3["roofline"].update({"peak": peak, "unit": "GB/s", "frac": round(m3["roofline"]["achieved"] / peak, 4),
+                                       "pipeline_frac": round(m3["roofline"]["pipeline_achieved"] / peak, 4), "peak_source": peak_src,
+                                       "traffic": ncu_traffic("mic3_tiles", m3["roofline"]["kernel"])})
+            extra["mic3"] = m3
+        except Exception as e:  # noqa: BLE001 -- the contract line must still be printed
+            extra["mic3"] = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
-        peak, peak_src = measured_peak()
-        dom = max(acc.items(), key=lambda kv: kv[1]) if acc else ("none", ms_dev)
-        alg_bytes = comp_bytes_alg + raw_bytes          # per launch of the dominant kernel: this rank's whole batch
-        achieved = alg_bytes / (dom[1] * 1e-3) / 1e9
-        wkey = f"pics8_{nst}state_b{args.batch}"
-        roof = {
-            "bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": ncu_traffic(wkey),
-            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(dom[1], 4),
-            "pipeline_achieved": round(alg_bytes / (ms_dev * 1e-3) / 1e9, 2),
-            "pipeline_frac": round(alg_bytes / (ms_dev * 1e-3) / 1e9 / peak, 4),
-            "stages_ms": {k: round(v, 4) for k, v in acc.items()},
-            "stages_note": "per-kernel CUDA-event times of a separate profiling pass that runs the kernels back to back on one "
-                           "stream; the timed step overlaps the K3/K4 launches of four unit ranges on their own streams",
-        }
+        roof = roofline_of(leg, nst, args, ms_dev)
         cpu = None if args.quick else cpu_baseline_sample(args, nst)
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -405,14 +477,15 @@ def run_ours(args, rank, local_rank, world):
                                    f"({args.batch * STRIPS} strips; {args.distinct} distinct images cycled, separate buffers)",
                        "ratio": round(raw_bytes / comp_bytes_alg, 3), "l2": "inputs larger than L2 (no flush needed)",
                        "inputs": "encoded before timing by the product's own CUDA encoder (byte-identical to the reference encoder)",
-                       **enc_stats},
-            "clocks": clocks,
+                       **leg["enc_stats"]},
+            "clocks": leg["clocks"],
             "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": comp_bytes_alg, "d2h_bytes_per_step": raw_bytes,
-                    "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps, "api": "micgpu_pics_decompress_batch (pinned host buffers)"},
-            "gpu_launches": launches * args.steps,
+                    "ms_per_step": round(ms_e2e, 3), "steps": leg["e2e_steps"], "api": "micgpu_pics_decompress_batch (pinned host buffers)"},
+            "gpu_launches": leg["launches"] * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "encode_e2e": enc_info,
+            "encode_e2e": leg["enc_info"],
+            **extra,
         }
         emit_json(line)
     if dist:
@@ -449,9 +522,10 @@ def cpu_baseline_sample(args, nst):
         if fn(t[0], t[1], t[2], W, t[3]) != 0:
             raise RuntimeError("reference decoder failed")
 
+    pool = ThreadPoolExecutor(max_workers=nthreads)
+
     def step():
-        with ThreadPoolExecutor(max_workers=nthreads) as ex:
-            list(ex.map(work, tasks))
+        list(pool.map(work, tasks))
 
     step()
     reps, t0 = 0, time.perf_counter()
@@ -459,6 +533,7 @@ def cpu_baseline_sample(args, nst):
         step()
         reps += 1
     dt = (time.perf_counter() - t0) / reps
+    pool.shutdown()
     # single-thread figure on one image for context
     t1 = time.perf_counter()
     for t in tasks[:STRIPS]:
@@ -466,7 +541,7 @@ def cpu_baseline_sample(args, nst):
     st = time.perf_counter() - t1
     return {"value": round(sample * raw_per / dt / 1e9, 4), "unit": UNIT, "cores": nthreads, "kind": "reference",
             "sample": f"{sample} images x {STRIPS} strips x {reps} reps, mic_decompress_{name}_state_simd per strip under {nthreads} host threads",
-            "single_thread_GBps": round(raw_per / st / 1e9, 4)}
+            "single_thread_GBps": round(raw_per / st / 1e9, 4), "build": REF_BUILD_NOTE}
 
 
 _JSON_FD = None
@@ -501,6 +576,8 @@ def main():
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic images generated per rank")
     ap.add_argument("--nstates", type=int, default=8, choices=[2, 4, 8], help="FSE state count of the strips")
     ap.add_argument("--quick", action="store_true", help="profiling aid: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 2-state and MIC3 legs (extra keys of the N=1 line)")
+    ap.add_argument("--mic3-side", type=int, default=32768, help="side of the MIC3 slide window in pixels (multiple of 256)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.distinct = min(args.distinct, args.batch)

@@ -81,7 +81,7 @@ template <int K4_RING>
 __global__ void __launch_bounds__(1024)
 k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist,
                   const uint16_t* __restrict__ D, const uint32_t* __restrict__ M, uint16_t* __restrict__ out,
-                  int brow_pitch) {
+                  int brow_pitch, int redo_only) {
   // dynamic shared memory: row_in | row_out (full rows, padded coordinates) | boundary rings | exchange slots |
   // residual ring | mask ring | mbarriers
   extern __shared__ __align__(16) uint16_t s_brow[];
@@ -90,6 +90,7 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
   const int nwarps = blockDim.x >> 5;
   const MicUnit* U = &units[list[blockIdx.x]];
   if (U->status != MIC_OK) return;
+  if (redo_only && !U->k4_redo) return;   // only the units the row-scan kernel (k_delta_scan.cu) handed back
   const int W = (int)U->width, H = (int)U->height;
   const unsigned wp = U->wp;
   const int thr = (int)U->thr;
@@ -325,7 +326,7 @@ int delta_wavefront_threads(int max_width, int max_height) {
 }
 
 void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,
-                            uint16_t* d_out, int max_width, int max_height, cudaStream_t st) {
+                            uint16_t* d_out, int max_width, int max_height, cudaStream_t st, int redo_only) {
   if (nlist <= 0) return;
   const int threads = delta_wavefront_threads(max_width, max_height);
   const int nwarps = threads / 32;
@@ -333,10 +334,10 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
   const size_t smem = 2 * (size_t)pitch * sizeof(uint16_t) + (size_t)nwarps * k4_warp_bytes();
   if (k4_ring() == 4) {
     cudaFuncSetAttribute(k_delta_wavefront<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_delta_wavefront<4><<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);
+    k_delta_wavefront<4><<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch, redo_only);
   } else {
     cudaFuncSetAttribute(k_delta_wavefront<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_delta_wavefront<8><<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch);
+    k_delta_wavefront<8><<<nlist, threads, smem, st>>>(d_units, d_list, nlist, d_D, d_M, d_out, pitch, redo_only);
   }
 }
 

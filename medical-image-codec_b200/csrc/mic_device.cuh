@@ -46,7 +46,12 @@ void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* 
 
 // Inverse avg(top,left) predictor as an anti-diagonal wavefront; one CTA per spatial unit.
 void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,
-                            uint16_t* d_out, int max_width, int max_height, cudaStream_t st);
+                            uint16_t* d_out, int max_width, int max_height, cudaStream_t st, int redo_only = 0);
+// The same predictor one row per step with lanes = 8-pixel column blocks and a warp scan over block functions
+// (k_delta_scan.cu).  Units whose pixels wrap uint16 are flagged (MicUnit::k4_redo) for the wavefront kernel.
+// Returns false (nothing launched) when the widest unit needs more than 32 warps.
+bool launch_delta_rowscan(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,
+                          uint16_t* d_out, int max_width, cudaStream_t st);
 int delta_wavefront_threads(int max_width, int max_height);
 
 // In-place frame-axis running sum for temporal MIC2 (frames contiguous, fpx pixels each).

@@ -52,5 +52,6 @@ struct MicUnit {
   unsigned int nsym;            // symbols actually decoded
   unsigned int thr;             // deltaThreshold (deltarlecompressu16.go:72-74)
   unsigned int delim;           // delimiterForOverflow
+  unsigned int k4_redo;         // row-scan predictor kernel saw a uint16 wrap: the wavefront kernel redoes the unit
   int status;                   // MicStatus
 };

@@ -281,6 +281,20 @@ void prof_mark(micgpu_decoder* d, const char* name, cudaStream_t st) {
   cudaEventRecord(d->ev[d->ev_used++], st);
 }
 
+// K4 over a slice of the spatial list: the row-scan kernel, then the wavefront kernel for the units it handed back
+// (uint16 wrap: none on encoder-made streams) -- or the wavefront kernel alone with MICGPU_K4=wave / for units wider than
+// one CTA can chain.  Returns the number of launches.
+int launch_k4(micgpu_decoder* d, MicUnit* du, const int* list, int n, void* d_out, cudaStream_t st) {
+  static const bool wave_only = [] { const char* e = getenv("MICGPU_K4"); return e && e[0] == 'w'; }();
+  if (n <= 0) return 0;
+  if (!wave_only && launch_delta_rowscan(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, st)) {
+    launch_delta_wavefront(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, d->max_h, st, 1);
+    return 2;
+  }
+  launch_delta_wavefront(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, d->max_h, st, 0);
+  return 1;
+}
+
 int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, void* d_out, size_t out_elems, cudaStream_t st) {
   if (!d->committed) return fail(MICGPU_E_HEADER, "decoder plan not committed");
   if (out_elems < d->out_need) return fail(MICGPU_E_SIZE, "output buffer holds %zu elements, plan needs %llu", out_elems, d->out_need);
@@ -342,10 +356,8 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
                       (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(nu, d->sm_count * 8), (unsigned int*)d->d_queue.p, st);
     d->launches++;
     if (!d->spatial.empty()) {
-      prof_mark(d, "k_delta_wavefront", st);
-      launch_delta_wavefront(du, dl + loff, (int)d->spatial.size(), (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p,
-                             (uint16_t*)d_out, d->max_w, d->max_h, st);
-      d->launches++;
+      prof_mark(d, "k_delta_rowscan", st);
+      d->launches += launch_k4(d, du, dl + loff, (int)d->spatial.size(), d_out, st);
     }
   } else {
     if (!d->ev_fork) {
@@ -368,9 +380,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
       const int s0 = (int)(std::lower_bound(d->spatial.begin(), d->spatial.end(), u0) - d->spatial.begin());
       const int s1 = (int)(std::lower_bound(d->spatial.begin(), d->spatial.end(), u1) - d->spatial.begin());
       if (s1 > s0) {
-        launch_delta_wavefront(du, dl + loff + s0, s1 - s0, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p,
-                               (uint16_t*)d_out, d->max_w, d->max_h, ps);
-        d->launches++;
+        d->launches += launch_k4(d, du, dl + loff + s0, s1 - s0, d_out, ps);
       }
       CUDA_TRY(cudaEventRecord(d->ev_join[p], ps));
       CUDA_TRY(cudaStreamWaitEvent(st, d->ev_join[p], 0));

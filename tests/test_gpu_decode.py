@@ -312,3 +312,33 @@ def test_temporal_carry_fused_over_peer_pointers(mic, oracle, synth):
         assert len(handle) == 64 and any(handle)
         for p, _ in lasts:
             mic.device_free(p)
+
+
+@pytest.mark.parametrize("w,h", [(300, 40), (256, 64), (2577, 9)])
+def test_predictor_uint16_wrap_follows_the_reference(mic, oracle, w, h):
+    """uint16(pred + diff) wraps in the reference (deltarlecompressu16.go:123).  No encoder emits such a stream, but a
+    decoder has to follow it: symbols are tampered after Delta+RLE so that pixels overflow / underflow, then FSE-coded.
+    The row-scan predictor kernel detects the wrap and hands the unit to the pixel-by-pixel wavefront kernel."""
+    rng = np.random.default_rng(w + h)
+    img = (65000 + rng.integers(0, 400, w * h)).astype(np.uint16)
+    img[::7] = rng.integers(0, 300, img[::7].size).astype(np.uint16)      # near both ends of the range
+    sym = oracle.delta_rle_compress(img, w, h, 65535).copy()
+    depth = 16
+    thr = (1 << (depth - 1)) - 1
+    # push plain diff symbols (not headers / delimiters / literals) towards +thr or 0 so that pred + diff leaves [0, 65535]
+    ref_px = oracle.delta_rle_decompress(sym, w, h)
+    assert np.array_equal(ref_px, img)
+    cand = np.flatnonzero((sym > thr - 2000) & (sym < thr + 2000))
+    cand = cand[(cand > 8)]
+    pick = cand[:: max(1, cand.size // 40)]
+    sym[pick[0::2]] = 2 * thr - 3
+    sym[pick[1::2]] = 5
+    try:
+        want = oracle.delta_rle_decompress(sym, w, h)
+    except Exception:
+        pytest.skip("tampered symbol stream no longer parses as RLE")
+    for coder in (2, 8):
+        blob = oracle.fse_compress(sym, coder)
+        got = mic.DecompressSingleFrame(blob, w, h)
+        assert np.array_equal(got, want), coder
+    assert not np.array_equal(want, img)

@@ -260,30 +260,32 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
 
 }  // namespace
 
-// mode: 0 = 4-byte cells, 1 = 2-byte cells.  Slots are dealt round-robin over the warps (slot = lane * nwarps + warp) so
-// that every scheduler of the SM gets its share of the units.
+// mode: 0 = 4-byte cells, 1 = 2-byte cells.  The host cuts the unit list into SEGMENTS (first index, count) whose tables
+// and rings fit one CTA together; slot_off[i] is the byte offset of list entry i inside its segment's shared memory
+// (table, then -- tableLog 16 in 2-byte cells -- the bit array, then the ring).  Tables of different sizes share a
+// CTA, so a batch of 4 KB and 8 KB tables (MIC3 luma / chroma planes) fills shared memory instead of paying the
+// largest table for every unit.  Slots are dealt round-robin over the warps (slot = lane * nwarps + warp) so that
+// every scheduler of the SM gets its share of the units.
 template <int N>
 __global__ void __launch_bounds__(SERIAL_THREADS)
-k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint8_t* __restrict__ comp,
-                    const uint32_t* __restrict__ tabA, uint16_t* __restrict__ states_out, int max_log, int slots, int mode) {
+k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, const int2* __restrict__ segs, int nseg,
+                    const uint32_t* __restrict__ slot_off, const uint8_t* __restrict__ comp, const uint32_t* __restrict__ tabA,
+                    uint16_t* __restrict__ states_out, int mode) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int slot = lane * nwarps + warp;
-  const bool l16 = mode == 1 && max_log == 16;
-  const size_t tbytes = (size_t)(1u << max_log) * (mode == 0 ? 4 : 2) + (l16 ? (1u << 16) / 8 : 0);
-  uint32_t* rings = reinterpret_cast<uint32_t*>(smem + (size_t)slots * tbytes);
 
-  for (int base = blockIdx.x * slots; base < nlist; base += gridDim.x * slots) {
-    __syncthreads();   // the previous pass is done with the tables
-    // ---- stage the tables of this pass, all threads per table --------------------------------------------
-    const int npass = min(slots, nlist - base);
-    bool wide_any = false;
+  for (int sg = blockIdx.x; sg < nseg; sg += gridDim.x) {
+    __syncthreads();   // the previous segment is done with the tables
+    const int base = segs[sg].x, npass = segs[sg].y;
+    // ---- stage the tables of this segment, all threads per table --------------------------------------------
+    bool wide_any = false, any16 = false;
     for (int s = 0; s < npass; s++) {
       const MicUnit* V = &units[list[base + s]];
       if (V->status != MIC_OK) continue;
       const uint32_t L = V->table_log, S = 1u << L;
       const uint4* A4 = reinterpret_cast<const uint4*>(tabA + V->tab_off);
-      uint8_t* T = smem + (size_t)s * tbytes;
+      uint8_t* T = smem + slot_off[base + s];
       if (mode == 0) {
         uint4* T4 = reinterpret_cast<uint4*>(T);
         for (uint32_t i = tid; i < S / 4; i += blockDim.x) T4[i] = __ldg(A4 + i);
@@ -291,6 +293,7 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, i
         // direct cells (k_ans.cu:469-472): valid while newState >> nbBits < 4096 and tableLog <= 15
         uint2* T2 = reinterpret_cast<uint2*>(T);
         uint32_t wide = L > 15 ? 4096u : 0u;
+        any16 |= L > 15;
         for (uint32_t i = tid; i < S / 4; i += blockDim.x) {
           const uint4 e = __ldg(A4 + i);
           const uint32_t d0 = (e.x & 0xFFFF) >> (e.x >> 16), d1 = (e.y & 0xFFFF) >> (e.y >> 16);
@@ -302,18 +305,20 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, i
         wide_any |= wide >= 4096u;
       }
     }
-    // one cell format per CTA: direct cells if every table of the pass allows them, else nextState cells for all
+    // one cell format per CTA: direct cells if every table of the segment allows them, else nextState cells for all
     const bool d16 = mode == 1 && !__syncthreads_or(wide_any ? 1 : 0);
+    const bool l16 = mode == 1 && any16;     // uniform: every thread looked at every unit of the segment
     if (mode == 1 && !d16) {
       for (int s = 0; s < npass; s++) {
         const MicUnit* V = &units[list[base + s]];
         if (V->status != MIC_OK) continue;
         const uint32_t L = V->table_log, S = 1u << L;
         const uint4* A4 = reinterpret_cast<const uint4*>(tabA + V->tab_off);
-        uint8_t* T = smem + (size_t)s * tbytes;
+        uint8_t* T = smem + slot_off[base + s];
         uint2* T2 = reinterpret_cast<uint2*>(T);
-        uint32_t* F = reinterpret_cast<uint32_t*>(T + ((size_t)2 << max_log));
-        if (l16) {
+        uint32_t* F = reinterpret_cast<uint32_t*>(T + ((size_t)2 << L));
+        const bool u16 = L > 15;
+        if (u16) {
           for (uint32_t j = tid; j < (1u << 16) / 32; j += blockDim.x) F[j] = 0;
           __syncthreads();
         }
@@ -323,7 +328,7 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, i
           const uint32_t n0 = ((e.x & 0xFFFF) + S) >> (e.x >> 16), n1 = ((e.y & 0xFFFF) + S) >> (e.y >> 16);
           const uint32_t n2 = ((e.z & 0xFFFF) + S) >> (e.z >> 16), n3 = ((e.w & 0xFFFF) + S) >> (e.w >> 16);
           T2[i] = make_uint2((n0 & 0xFFFF) | (n1 << 16), (n2 & 0xFFFF) | (n3 << 16));
-          if (l16) {
+          if (u16) {
             const uint32_t hi = (n0 >> 16) | ((n1 >> 16) << 1) | ((n2 >> 16) << 2) | ((n3 >> 16) << 3);
             if (hi) atomicOr(&F[i >> 3], hi << ((i & 7u) * 4));
           }
@@ -335,23 +340,29 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, i
     if (slot < npass) {
       MicUnit* U = &units[list[base + slot]];
       if (U->status == MIC_OK) {
-        const uint8_t* mytab = smem + (size_t)slot * tbytes;
-        const uint32_t* myflags = reinterpret_cast<const uint32_t*>(mytab + ((size_t)2 << max_log));
-        uint32_t* ring = rings + slot * SRING_STRIDE;
+        const uint32_t L = U->table_log;
+        const uint8_t* mytab = smem + slot_off[base + slot];
+        const size_t cells = (size_t)(mode == 0 ? 4 : 2) << L;
+        const uint32_t* myflags = reinterpret_cast<const uint32_t*>(mytab + cells);
+        const size_t fl = (mode == 1 && L > 15) ? (1u << 16) / 8 : 0;
+        uint32_t* ring = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(mytab) + cells + fl);
         if (mode == 0) decode_unit<N, 0, false>(U, comp, states_out, mytab, myflags, ring);
         else if (d16) decode_unit<N, 2, false>(U, comp, states_out, mytab, myflags, ring);
-        else if (l16) decode_unit<N, 1, true>(U, comp, states_out, mytab, myflags, ring);
+        else if (l16 && L > 15) decode_unit<N, 1, true>(U, comp, states_out, mytab, myflags, ring);
         else decode_unit<N, 1, false>(U, comp, states_out, mytab, myflags, ring);
       }
     }
   }
 }
 
-size_t ans_serial_smem_bytes(int max_log, int mode, int slots) {
-  size_t t = (size_t)(1u << max_log) * (mode == 0 ? 4 : 2);
-  if (mode == 1 && max_log == 16) t += (1u << 16) / 8;
-  return (size_t)slots * (t + SRING_STRIDE * 4);
+// shared-memory bytes of one unit: cells, the bit array for bit 16 of nextState (tableLog 16 in 2-byte cells), the ring
+size_t ans_serial_unit_bytes(int table_log, int mode) {
+  size_t t = (size_t)(1u << table_log) * (mode == 0 ? 4 : 2);
+  if (mode == 1 && table_log == 16) t += (1u << 16) / 8;
+  return t + SRING_STRIDE * 4;
 }
+
+size_t ans_serial_smem_bytes(int max_log, int mode, int slots) { return (size_t)slots * ans_serial_unit_bytes(max_log, mode); }
 
 int ans_serial_threads(int slots) {
   // up to four warps so that each scheduler of the SM drives its own share of the units
@@ -359,15 +370,14 @@ int ans_serial_threads(int slots) {
   return 32 * warps;
 }
 
-void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, int nlist, int nstates, const uint8_t* d_comp,
-                              const uint32_t* d_tabA, uint16_t* d_states, int max_log, int mode, int slots, int grid,
-                              cudaStream_t st) {
-  if (nlist <= 0) return;
-  const size_t smem = ans_serial_smem_bytes(max_log, mode, slots);
-  const int threads = ans_serial_threads(slots);
+void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, const int2* d_segs, int nseg, const uint32_t* d_slot_off, int nstates,
+                              const uint8_t* d_comp, const uint32_t* d_tabA, uint16_t* d_states, int mode, int max_slots,
+                              size_t smem, int grid, cudaStream_t st) {
+  if (nseg <= 0) return;
+  const int threads = ans_serial_threads(max_slots);
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, threads, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots, mode);
+    kern<<<grid, threads, smem, st>>>(d_units, d_list, d_segs, nseg, d_slot_off, d_comp, d_tabA, d_states, mode);
   };
   if (nstates == 1) go(k_ans_decode_serial<1>);
   else if (nstates == 2) go(k_ans_decode_serial<2>);

@@ -36,7 +36,7 @@ namespace {
 
 constexpr int PTHR = 31;       // Fn::p of the threshold form
 constexpr int TINF = 1 << 20;  // threshold no pixel reaches: the function is the constant b
-constexpr int HAND_R = 8;      // ring slots per warp boundary
+constexpr int HAND_R = 16;     // ring slots per warp boundary
 
 // A function of the incoming left pixel x in [0, 65535], in one of two forms (all 32-bit):
 //   shift form      p <= 15:    f(x) = ((x + a) >> p) + b,  0 <= a < 2^p
@@ -116,7 +116,8 @@ __device__ __forceinline__ void st_volatile_s(unsigned* p, unsigned v) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(1024)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint16_t* __restrict__ D,
                 const uint32_t* __restrict__ M, uint16_t* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t s_scan_raw[];
@@ -177,6 +178,10 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
     int d[8];
     d[0] = dd.x & 0xFFFF; d[1] = dd.x >> 16; d[2] = dd.y & 0xFFFF; d[3] = dd.y >> 16;
     d[4] = dd.z & 0xFFFF; d[5] = dd.z >> 16; d[6] = dd.w & 0xFFFF; d[7] = dd.w >> 16;
+    if (nvalid != 8) {   // last block of the row / lanes past it: columns >= W hold stale scratch; make them e = 0
+#pragma unroll
+      for (int i = 0; i < 8; i++) d[i] = i < nvalid ? d[i] : thr;
+    }
 
     // ---- block function: incoming left pixel -> last pixel of the block --------------------------------------
     // pixel op: x -> ((x + top) >> hs) + e with hs = 0 on row 0 (pred = left; top[] is zero there).
@@ -185,7 +190,9 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
     // its incoming x is 0 by construction, so x -> x + top + e stands in for the constant), shifts are immediates, the
     // first scan round is shift o shift -> threshold and the second threshold o threshold.
     const int hs = y == 0 ? 0 : 1;
-    const bool plain = y > 0 && !__any_sync(0xffffffffu, mbits != 0u || nvalid != 8);
+    // (a partial last block and the lanes past the row end run the plain path too: nobody consumes their function, their
+    // pixels past W are never stored, and with e = 0 they stay in range)
+    const bool plain = y > 0 && !__any_sync(0xffffffffu, (mbits & ((1u << nvalid) - 1u)) != 0u);
     Fn f;
     if (plain) {
       const int c0 = x0 == 0 ? 1 : 0;
@@ -269,7 +276,7 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
       scan_round(1);
       scan_round(2);
     }
-    if (!__all_sync(0xffffffffu, lane < 3 || nvalid == 0 || fn_is_const(f))) {
+    if (!__all_sync(0xffffffffu, lane < 3 || nvalid != 8 || fn_is_const(f))) {
       scan_round(4);
       scan_round(8);
       scan_round(16);
@@ -320,7 +327,7 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
     // ---- hand the warp's last block to the next warp ----------------------------------------------------------
     if (has_next) {
       if (y >= HAND_R) {   // the slot is free once the consumer has finished row y - HAND_R
-        while (ld_volatile_s(&rows_done[warp + 1]) + HAND_R <= (unsigned)y) { }
+        while (ld_volatile_s(&rows_done[warp + 1]) + HAND_R <= (unsigned)y) __nanosleep(64);   // not on anybody's critical path
       }
       if (lane == 31) hand[warp * HAND_R + (y & (HAND_R - 1))] = blk;
       __threadfence_block();
@@ -357,13 +364,24 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
 size_t delta_rowscan_smem_bytes(int warps) { return (size_t)warps * (HAND_R * 16 + 4) + 16; }
 
 // one CTA per listed spatial unit; warps = ceil(chunks / 32) of the widest unit (at most 32: W <= 8178)
+template <int MAXT, int MINB>
+static void launch_rowscan_t(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M, uint16_t* d_out,
+                             int warps, cudaStream_t st) {
+  k_delta_rowscan<MAXT, MINB><<<nlist, 32 * warps, delta_rowscan_smem_bytes(warps), st>>>(d_units, d_list, nlist, d_D, d_M, d_out);
+}
+
 bool launch_delta_rowscan(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,
-                          uint16_t* d_out, int max_width, cudaStream_t st) {
+                          uint16_t* d_out, int max_width, bool all_aligned, cudaStream_t st) {
   if (nlist <= 0) return true;
-  const int nchunks = (max_width + 14) >> 3;
+  // all_aligned: every unit has W % 8 == 0 and a 16 B aligned first pixel (MIC3 tile planes): no chunk beyond W / 8, so a
+  // 256-wide tile is ONE warp per CTA (an idle second warp would halve the resident units: registers are per CTA)
+  const int nchunks = all_aligned ? (max_width >> 3) : ((max_width + 14) >> 3);
   const int warps = (nchunks + 31) >> 5;
   if (warps > 32) return false;     // wider than one CTA can chain: the caller uses the wavefront kernel
-  k_delta_rowscan<<<nlist, 32 * warps, delta_rowscan_smem_bytes(warps), st>>>(d_units, d_list, nlist, d_D, d_M, d_out);
+  // register budget by CTA size: three 12-warp CTAs (a 2577-wide strip is 11 warps) or eight 4-warp CTAs per SM
+  if (warps <= 4) launch_rowscan_t<128, 8>(d_units, d_list, nlist, d_D, d_M, d_out, warps, st);
+  else if (warps <= 12) launch_rowscan_t<384, 3>(d_units, d_list, nlist, d_D, d_M, d_out, warps, st);
+  else launch_rowscan_t<1024, 1>(d_units, d_list, nlist, d_D, d_M, d_out, warps, st);
   return true;
 }
 

@@ -29,11 +29,13 @@ void launch_ans_decode(MicUnit* d_units, const int* d_list, int nlist, int nstat
                        int grid, cudaStream_t st);
 size_t ans_decode_smem_bytes(int max_log, int smem_mode, int slots_per_cta);
 
-// Thread-per-unit decode of 1-, 2- and 4-state streams (k_ans_serial.cu).  mode: 0 = 4-byte cells, 1 = 2-byte cells;
-// slots = units per CTA (<= 128).
-void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, int nlist, int nstates, const uint8_t* d_comp,
-                              const uint32_t* d_tabA, uint16_t* d_states, int max_log, int mode, int slots, int grid,
-                              cudaStream_t st);
+// Thread-per-unit decode of 1-, 2- and 4-state streams (k_ans_serial.cu).  mode: 0 = 4-byte cells, 1 = 2-byte cells.
+// The list is cut into segments (first, count) whose tables fit one CTA; d_slot_off[i] = shared-memory byte offset of
+// list entry i inside its segment; smem = bytes of the largest segment; max_slots = entries of the largest one (<= 128).
+void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, const int2* d_segs, int nseg, const uint32_t* d_slot_off, int nstates,
+                              const uint8_t* d_comp, const uint32_t* d_tabA, uint16_t* d_states, int mode, int max_slots,
+                              size_t smem, int grid, cudaStream_t st);
+size_t ans_serial_unit_bytes(int table_log, int mode);
 size_t ans_serial_smem_bytes(int max_log, int mode, int slots);
 
 // RLE expand (+ escape split for spatial units).  Spatial units produce the
@@ -51,7 +53,7 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
 // (k_delta_scan.cu).  Units whose pixels wrap uint16 are flagged (MicUnit::k4_redo) for the wavefront kernel.
 // Returns false (nothing launched) when the widest unit needs more than 32 warps.
 bool launch_delta_rowscan(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,
-                          uint16_t* d_out, int max_width, cudaStream_t st);
+                          uint16_t* d_out, int max_width, bool all_aligned, cudaStream_t st);
 int delta_wavefront_threads(int max_width, int max_height);
 
 // In-place frame-axis running sum for temporal MIC2 (frames contiguous, fpx pixels each).

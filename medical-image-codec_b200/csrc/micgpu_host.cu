@@ -34,6 +34,11 @@ int nstates_index(unsigned n) { return n == 1 ? 0 : n == 2 ? 1 : n == 4 ? 2 : 3;
 struct AnsPlan {
   int nstates = 0, max_log = 0, mode = 0, slots = 0, grid = 0;
   bool serial = false;   // thread-per-unit kernel (k_ans_serial.cu)
+  // serial kernel: the list cut into segments whose tables fit one CTA together
+  std::vector<int2> segs;             // (first list entry, entries)
+  std::vector<uint32_t> slot_off;     // per list entry: byte offset inside its segment's shared memory
+  size_t seg_smem = 0;
+  size_t dev_off = 0;                 // byte offset of [segs | slot_off] in d_segs
 };
 
 // Streams with at most this many states go through the thread-per-unit kernel (MICGPU_K2_SERIAL_MAXN: 0 = never, 1, 2, 4).
@@ -68,9 +73,11 @@ struct micgpu_decoder {
   bool committed = false;
   int launches = 0;
   DevBuf d_units, d_list, d_tabA, d_tabS, d_states, d_D, d_M, d_k1, d_comp, d_out, d_queue;
+  DevBuf d_segs;            // thread-per-unit ANS kernel: segment tables
   DevBuf d_park, d_peer;    // multi-device temporal MIC2: this range's relative last frame; staged copies of the peers' frames
   DevBuf d_norm, d_psym;    // split table build: present-symbol lists (normalised count, symbol value) at each unit's tab_off
   bool k1_split = true, k1_fallback = false;
+  bool all_aligned = false;   // every spatial unit of the current run: width % 8 == 0 and a 16 B aligned first pixel
   DevBuf d_jobs, d_bytes;   // MIC3: fill / blit job tables, byte-typed pixel output
   DevBuf d_wA, d_wB, d_wflags;   // WaveletV2: int32 ping-pong planes, escape flags
   MicUnit* h_units = nullptr;   // pinned staging copy
@@ -90,7 +97,7 @@ struct micgpu_decoder {
   ~micgpu_decoder() {
     cudaSetDevice(device);
     d_units.release(); d_list.release(); d_tabA.release(); d_tabS.release(); d_states.release();
-    d_D.release(); d_M.release(); d_k1.release(); d_norm.release(); d_psym.release(); d_park.release(); d_peer.release(); d_queue.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
+    d_D.release(); d_M.release(); d_k1.release(); d_norm.release(); d_psym.release(); d_park.release(); d_peer.release(); d_segs.release(); d_queue.release(); d_comp.release(); d_out.release(); d_jobs.release(); d_bytes.release(); d_wA.release(); d_wB.release(); d_wflags.release();
     if (h_units) cudaFreeHost(h_units);
     if (stream) cudaStreamDestroy(stream);
     for (int p = 0; p < PARTS; p++) {
@@ -201,10 +208,32 @@ int plan_commit(micgpu_decoder* d) {
       if (f >= 1) {
         a.serial = true;
         a.mode = smode;
-        a.slots = std::max(1, std::min(f, want));
-        const size_t per_cta = ans_serial_smem_bytes(ml, smode, a.slots) + 1024;
+        // Segments: consecutive list entries (sorted by length) whose tables fit one CTA, at most `want` of them so that
+        // a small batch still spreads over every SM.  Tables keep their own size: 4 KB and 8 KB tables share a CTA.
+        a.segs.clear();
+        a.slot_off.assign(n, 0);
+        a.seg_smem = 0;
+        int max_slots = 1;
+        for (int i = 0; i < n;) {
+          size_t used = 0;
+          int cnt = 0;
+          while (i + cnt < n && cnt < want) {
+            const size_t ub = ans_serial_unit_bytes((int)d->units[d->lists[g][i + cnt]].table_log, smode);
+            if (used + ub > budget) break;
+            a.slot_off[i + cnt] = (uint32_t)used;
+            used += ub;
+            cnt++;
+          }
+          if (cnt == 0) { cnt = 1; used = ans_serial_unit_bytes((int)d->units[d->lists[g][i]].table_log, smode); }   // cannot happen: f >= 1
+          a.segs.push_back(make_int2(i, cnt));
+          a.seg_smem = std::max(a.seg_smem, used);
+          max_slots = std::max(max_slots, cnt);
+          i += cnt;
+        }
+        a.slots = max_slots;
+        const size_t per_cta = a.seg_smem + 1024;
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>((228 * 1024) / per_cta, 16));
-        a.grid = std::min((n + a.slots - 1) / a.slots, d->sm_count * ctas_per_sm);
+        a.grid = std::min((int)a.segs.size(), d->sm_count * ctas_per_sm);
         continue;
       }
     }
@@ -265,6 +294,21 @@ int plan_commit(micgpu_decoder* d) {
   for (auto& l : d->lists) flat.insert(flat.end(), l.begin(), l.end());
   flat.insert(flat.end(), d->spatial.begin(), d->spatial.end());
   if (!flat.empty()) CUDA_TRY(cudaMemcpy(d->d_list.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // segment tables of the thread-per-unit ANS kernel: [segs | slot offsets] per state-count group
+  {
+    std::vector<uint8_t> blob;
+    for (int g = 0; g < 4; g++) {
+      AnsPlan& a = d->ans[g];
+      if (!a.serial || a.grid == 0 || d->lists[g].empty()) continue;
+      a.dev_off = blob.size();
+      const size_t sb = a.segs.size() * sizeof(int2), ob = a.slot_off.size() * sizeof(uint32_t);
+      blob.resize(blob.size() + ((sb + ob + 15) & ~(size_t)15));
+      memcpy(blob.data() + a.dev_off, a.segs.data(), sb);
+      memcpy(blob.data() + a.dev_off + sb, a.slot_off.data(), ob);
+    }
+    if ((rc = d->d_segs.ensure(blob.size() + 64))) return rc;
+    if (!blob.empty()) CUDA_TRY(cudaMemcpy(d->d_segs.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  }
   d->committed = true;
   return 0;
 }
@@ -287,7 +331,7 @@ void prof_mark(micgpu_decoder* d, const char* name, cudaStream_t st) {
 int launch_k4(micgpu_decoder* d, MicUnit* du, const int* list, int n, void* d_out, cudaStream_t st) {
   static const bool wave_only = [] { const char* e = getenv("MICGPU_K4"); return e && e[0] == 'w'; }();
   if (n <= 0) return 0;
-  if (!wave_only && launch_delta_rowscan(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, st)) {
+  if (!wave_only && launch_delta_rowscan(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, d->all_aligned, st)) {
     launch_delta_wavefront(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, d->max_h, st, 1);
     return 2;
   }
@@ -304,8 +348,11 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   d->launches = 0;
   const int nu = (int)d->units.size();
   if (!nu) return 0;
-  for (MicUnit& u : d->units)
+  d->all_aligned = true;
+  for (MicUnit& u : d->units) {
     u.align0 = (unsigned)(((reinterpret_cast<uintptr_t>(d_out) >> 1) + u.out_off) & 7u);
+    if (u.kind == MIC_KIND_SPATIAL && (u.align0 || (u.width & 7u))) d->all_aligned = false;
+  }
   memcpy(d->h_units, d->units.data(), nu * sizeof(MicUnit));
   CUDA_TRY(cudaMemcpyAsync(d->d_units.p, d->h_units, nu * sizeof(MicUnit), cudaMemcpyHostToDevice, st));
   if (d->m_total) CUDA_TRY(cudaMemsetAsync(d->d_M.p, 0, d->m_total * sizeof(uint32_t), st));
@@ -338,10 +385,12 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
       static const char* PACKED[4] = {"k_ans_decode<1>", "k_ans_decode_packed<2>", "k_ans_decode_packed<4>", "k_ans_decode_packed<8>"};
       static const char* ONE[4] = {"k_ans_decode<1>", "k_ans_decode<2>", "k_ans_decode<4>", "k_ans_decode<8>"};
       prof_mark(d, a.serial ? SERIAL[g] : (a.mode != 2 ? PACKED[g] : ONE[g]), st);
-      if (a.serial)
-        launch_ans_decode_serial(du, dl + loff, n, a.nstates, comp, (const uint32_t*)d->d_tabA.p, (uint16_t*)d->d_states.p, a.max_log,
-                                 a.mode, a.slots, a.grid, st);
-      else
+      if (a.serial) {
+        const int2* segs = (const int2*)((const uint8_t*)d->d_segs.p + a.dev_off);
+        const uint32_t* soff = (const uint32_t*)((const uint8_t*)segs + a.segs.size() * sizeof(int2));
+        launch_ans_decode_serial(du, dl + loff, segs, (int)a.segs.size(), soff, a.nstates, comp, (const uint32_t*)d->d_tabA.p,
+                                 (uint16_t*)d->d_states.p, a.mode, a.slots, a.seg_smem, a.grid, st);
+      } else
         launch_ans_decode(du, dl + loff, n, a.nstates, comp, (const uint32_t*)d->d_tabA.p, (uint16_t*)d->d_states.p, a.max_log,
                           a.mode, a.slots, a.grid, st);
       d->launches++;
@@ -546,6 +595,18 @@ void partition_by_bytes(const uint64_t* sizes, uint64_t n, int parts, std::vecto
   cuts[parts] = n;
 }
 
+// Contexts of the multi-device calls, one per entry of the device list (entries may name the same device).
+std::mutex g_multi_mu;
+std::vector<micgpu_decoder*> g_multi;
+micgpu_decoder* multi_decoder(int dev, int slot) {
+  std::lock_guard<std::mutex> lk(g_multi_mu);
+  if (slot < 0 || slot >= 64) return nullptr;
+  if ((int)g_multi.size() <= slot) g_multi.resize(slot + 1, nullptr);
+  if (g_multi[slot] && g_multi[slot]->device != dev) { delete g_multi[slot]; g_multi[slot] = nullptr; }
+  if (!g_multi[slot]) g_multi[slot] = micgpu_decoder_create(dev);
+  return g_multi[slot];
+}
+
 micgpu_decoder* default_decoder(int dev) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (dev < 0 || dev >= 64) return nullptr;
@@ -599,12 +660,10 @@ int micgpu_init(const int* devices, int n) {
   } else {
     for (int i = 0; i < n; i++) {
       if (devices[i] < 0 || devices[i] >= have) return fail(MICGPU_E_CUDA, "device %d out of range [0,%d)", devices[i], have);
-      for (int q : v)
-        if (q == devices[i]) return fail(MICGPU_E_HEADER, "device %d listed twice", q);
-      v.push_back(devices[i]);
+      v.push_back(devices[i]);   // a device may appear more than once: that many host threads and contexts share it
     }
   }
-  if (v.size() > 64) return fail(MICGPU_E_UNSUPPORTED, "at most 64 devices");
+  if (v.size() > 32) return fail(MICGPU_E_UNSUPPORTED, "at most 32 device-list entries");
   std::lock_guard<std::mutex> lk(g_dev_mu);
   g_devices = v;
   return (int)v.size();
@@ -619,6 +678,11 @@ void micgpu_shutdown(void) {
   for (auto& d : g_default) {
     delete d;
     d = nullptr;
+  }
+  {
+    std::lock_guard<std::mutex> lk3(g_multi_mu);
+    for (auto& d : g_multi) delete d;
+    g_multi.clear();
   }
   std::lock_guard<std::mutex> lk2(g_pipe_mu);
   for (auto& row : g_pipe)
@@ -1146,7 +1210,7 @@ static int mic2_decode_multi(const std::vector<int>& devs, const uint8_t* mic2, 
   partition_by_bytes(sizes.data(), (uint64_t)mh0.n, nd, cuts);
   std::vector<micgpu_decoder*> D(nd);
   for (int k = 0; k < nd; k++)
-    if (!(D[k] = default_decoder(devs[k]))) return MICGPU_E_CUDA;
+    if (!(D[k] = multi_decoder(devs[k], k))) return MICGPU_E_CUDA;
   std::vector<std::unique_lock<std::mutex>> locks;
   for (int k = 0; k < nd; k++) locks.emplace_back(D[k]->mu);   // device-list order: no two calls can deadlock
   std::vector<int> rcs(nd, 0);
@@ -1746,11 +1810,11 @@ int micgpu_wsi_plan_kernel_times(micgpu_wsi_plan* p, int on, char* names, size_t
 namespace {
 
 // One device's share of a tile-range call: plan, one H2D copy of the span, kernels, one D2H copy.
-int wsi_range_on_device(int dev, const uint8_t* mic3, size_t len, uint64_t first, uint64_t n, uint8_t* out, int* status, std::string* msg) {
+int wsi_range_on_device(int dev, int slot, const uint8_t* mic3, size_t len, uint64_t first, uint64_t n, uint8_t* out, int* status, std::string* msg) {
   auto done = [&](int rc) { if (rc && msg) *msg = err_slot(); return rc; };
   if (n == 0) return 0;
   if (cudaSetDevice(dev) != cudaSuccess) return done(fail(MICGPU_E_CUDA, "cudaSetDevice(%d) failed", dev));
-  micgpu_decoder* d = pipe_decoder(dev, PIPE_DEPTH - 1);   // a context of its own: the plan keeps its scratch between calls
+  micgpu_decoder* d = multi_decoder(dev, 32 + slot);   // contexts of their own: the plan keeps its scratch between calls
   if (!d) return done(MICGPU_E_CUDA);
   std::lock_guard<std::mutex> lk(d->mu);
   micgpu_wsi_plan P;
@@ -1799,7 +1863,7 @@ int micgpu_wsi_decompress_tile_range(const uint8_t* mic3, size_t len, uint64_t f
   std::vector<int> devs = configured_devices();
   if (devs.size() <= 1 || n_tiles < 2 * devs.size()) {
     std::string msg;
-    return wsi_range_on_device(devs.empty() ? current_device() : devs[0], mic3, len, first_tile, n_tiles, out, status, nullptr);
+    return wsi_range_on_device(devs.empty() ? current_device() : devs[0], 0, mic3, len, first_tile, n_tiles, out, status, nullptr);
   }
   std::vector<uint64_t> sizes(n_tiles), cuts;
   for (uint64_t t = 0; t < n_tiles; t++) sizes[t] = rd64(mic3 + h.table_off + (size_t)(first_tile + t) * 16 + 8) + 1024;
@@ -1809,7 +1873,7 @@ int micgpu_wsi_decompress_tile_range(const uint8_t* mic3, size_t len, uint64_t f
   std::vector<std::thread> th;
   for (size_t k = 0; k < devs.size(); k++)
     th.emplace_back([&, k] {
-      rcs[k] = wsi_range_on_device(devs[k], mic3, len, first_tile + cuts[k], cuts[k + 1] - cuts[k], out + cuts[k] * tile_bytes,
+      rcs[k] = wsi_range_on_device(devs[k], (int)k, mic3, len, first_tile + cuts[k], cuts[k + 1] - cuts[k], out + cuts[k] * tile_bytes,
                                    status ? status + cuts[k] : nullptr, &msgs[k]);
     });
   for (auto& t : th) t.join();

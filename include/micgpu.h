@@ -203,7 +203,9 @@ int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t *const *blobs, const
 int micgpu_delta_rle_compress(const uint16_t *pixels, int width, int height, uint16_t max_value, uint16_t *out, size_t cap, size_t *out_len);
 int micgpu_rle_compress(const uint16_t *in, size_t n, uint16_t max_value, uint16_t *out, size_t cap, size_t *out_len);
 /* CompressSingleFrame (nstates 2), CompressSingleFrame4State (4), CompressSingleFrame8State (8) with the reference's
- * fallback ladder (multiframecompress.go:15-93); nstates 1 = Delta+RLE + FSECompressU16.  maxValue is the caller's. */
+ * fallback ladder (multiframecompress.go:15-93); nstates 1 = Delta+RLE + FSECompressU16; nstates MICGPU_CODER_RANS8 =
+ * Delta+RLE + RANSCompressU16EightState (rans8state.go:31, magic [0xFF,0x08], no fallback).  maxValue is the caller's. */
+#define MICGPU_CODER_RANS8 108
 int micgpu_compress_single_frame(const uint16_t *pixels, int width, int height, uint16_t max_value, int nstates, uint8_t *out, size_t cap,
                                  size_t *out_len);
 /* CompressParallelStrips / 4State / 8State (parallelstrips.go:55,128,199); num_strips must be > 0 (GOMAXPROCS is the caller's). */

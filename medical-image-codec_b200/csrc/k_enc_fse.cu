@@ -314,6 +314,7 @@ k_enc_tables(MicEncUnit* __restrict__ units, int nunits, const uint16_t* __restr
         posc[s] = b_pos;
         if (v == -1) {
           cell_sym[Sz - 1 - b_low] = (uint16_t)s;     // tableSymbol[highThreshold--] = u  (fsecompressu16.go:345-349)
+          posc[s] = t_pos + b_low;                    // rANS: low-probability symbols sit after all normal ones (ransu16.go:175-188)
           b_all += 1; b_low += 1;
         } else if (v > 0) {
           for (int q = 0; q < v; q++) rank_sym[b_pos + q] = (uint16_t)s;
@@ -322,6 +323,27 @@ k_enc_tables(MicEncUnit* __restrict__ units, int nunits, const uint16_t* __restr
       }
     }
     __syncthreads();
+    if (U->rans) {
+      // buildRansEncTable (ransu16.go:139-197): freq, bias = slots before the symbol (normal symbols first, then the
+      // low-probability ones), k0 = tableLog - highBits(freq); threshold = freq << k0 is recomputed by the encoder
+      uint2* TTr = sym_tt + U->tt_off;
+      for (unsigned i = tid; i < symlen; i += T_THREADS) {
+        const int v = norm[i];
+        uint2 e = make_uint2(0u, 0u);
+        if (v == -1) { e.x = 1u | (tl << 20); e.y = posc[i]; }
+        else if (v > 0) { e.x = (unsigned)v | ((tl - high_bits((unsigned)v)) << 20); e.y = posc[i]; }
+        TTr[i] = e;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const int h = s_hdr;
+        if (h < 0) U->status = h;
+        U->hdr_len = h < 0 ? 0u : (unsigned)h;
+        U->symbol_len = symlen;
+        U->table_log = h < 0 ? 0u : tl;
+      }
+      continue;
+    }
     {
       // spread: cell (j*step)&mask receives the symbol of rank #live(j' < j)  (fsecompressu16.go:373-395)
       const unsigned high_threshold = Sz - 1 - nlow;
@@ -403,6 +425,27 @@ k_enc_ans(MicEncUnit* __restrict__ units, const int* __restrict__ list, int nlis
     const uint16_t* ST = state_tab + U->tab_off;
     const uint2* TT = sym_tt + U->tt_off;
     uint32_t* T = Tbuf + U->t_off;
+    if (N == 8 && U->rans) {
+      // ransCompress8State (rans8state.go:106-220): states start at 0; xL = x + L, k = k0 - [xL < freq << k0] low bits leave,
+      // x = bias + (xL >> k) - freq (ransEncodeStep, ransu16.go:203-213).  Same emission order as the tANS tiers.
+      unsigned x = 0;
+      if ((unsigned)k < n) {
+        long long i = (long long)(n - 1) - (long long)((n - 1 - (unsigned)k) % N);
+        unsigned sym = S[i];
+        for (; i >= 0; i -= N) {
+          const unsigned nsym = i >= N ? S[i - N] : 0u;
+          const uint2 tt = __ldg(TT + sym);
+          const unsigned freq = tt.x & 0xFFFFFu, k0 = tt.x >> 20;
+          const unsigned xL = x + Sz;
+          const unsigned kk = k0 - (xL < (freq << k0) ? 1u : 0u);
+          T[i] = (xL & ((1u << kk) - 1u)) | (kk << 16);
+          x = tt.y + (xL >> kk) - freq;
+          sym = nsym;
+        }
+      }
+      T[n + k] = x & (Sz - 1u);
+      continue;
+    }
     unsigned state = Sz;                                   // cStateU16.init: 1 << tableLog
     // No bounds checks inside the chain (a compare + branch per symbol cost 10-40 % of the encode): K6 builds the tables
     // from the histogram of this very stream, so every symbol has cells whenever the unit's status is still OK here.
@@ -455,7 +498,7 @@ k_enc_pack(MicEncUnit* __restrict__ units, int nunits, const uint32_t* __restric
     }
     // prefix bytes
     if (N > 1 && tid < 6) {
-      const uint8_t magic = N == 2 ? 0x02 : N == 4 ? 0x04 : 0x84;
+      const uint8_t magic = N == 2 ? 0x02 : N == 4 ? 0x04 : (U->rans ? 0x08 : 0x84);
       F[tid] = tid == 0 ? 0xFF : tid == 1 ? magic : (uint8_t)(n >> (8 * (tid - 2)));
     }
     const uint8_t* H = hdrs + U->hdr_off;

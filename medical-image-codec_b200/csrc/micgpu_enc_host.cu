@@ -291,12 +291,14 @@ int micgpu_rle_compress(const uint16_t* in, size_t n, uint16_t max_value, uint16
 int micgpu_compress_single_frame(const uint16_t* pixels, int width, int height, uint16_t max_value, int nstates, uint8_t* out, size_t cap,
                                  size_t* out_len) {
   if (!pixels || !out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
-  if (nstates != 1 && nstates != 2 && nstates != 4 && nstates != 8) return fail(MICGPU_E_HEADER, "nstates must be 1, 2, 4 or 8");
+  const bool rans = nstates == MICGPU_CODER_RANS8;
+  if (nstates != 1 && nstates != 2 && nstates != 4 && nstates != 8 && !rans) return fail(MICGPU_E_HEADER, "nstates must be 1, 2, 4, 8 or MICGPU_CODER_RANS8");
   micgpu_encoder* e = default_encoder(current_device());
   if (!e) return MICGPU_E_CUDA;
   std::lock_guard<std::mutex> lk(e->mu);
   e->units.clear();
-  enc_add_unit(e, MIC_ENC_SPATIAL, 0, (unsigned)width, (unsigned)height, max_value, nstates);
+  const int ui = enc_add_unit(e, MIC_ENC_SPATIAL, 0, (unsigned)width, (unsigned)height, max_value, rans ? 8 : nstates);
+  if (rans) { e->units[ui].rans = 1; e->units[ui].no_ladder = 1; }   // RANSCompressU16EightState has no fallback (rans8state.go:31-70)
   const size_t npx = (size_t)width * height;
   int rc;
   CUDA_TRY(cudaSetDevice(e->device));

@@ -182,3 +182,26 @@ def test_temporal_carry_is_an_exclusive_scan():
     for r in range(1, 4):
         want = lasts[:r].astype(np.uint64).sum(axis=0).astype(np.uint16)      # mod 2^16
         assert np.array_equal(shard.mic2_temporal_carry(lasts, r), want)
+
+
+def test_partition_twin_matches_python(tmp_path):
+    """micgpu_partition_by_bytes is the C++ twin of shard.partition_by_bytes: same cuts on ragged size lists,
+    more parts than units, empty lists.  Pure host code: runs without a GPU."""
+    import ctypes as C
+    import importlib
+
+    import numpy as np
+
+    shard = importlib.import_module("medical-image-codec_b200.shard")
+    lib = C.CDLL(os.path.join(ROOT, "medical-image-codec_b200", "libmicgpu.so"))
+    lib.micgpu_partition_by_bytes.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    rng = np.random.default_rng(3)
+    cases = [[], [5], [1, 1, 1], [10, 1, 1, 1, 1, 1, 30, 2], list(rng.integers(1, 10**6, 257)), [7] * 64, list(rng.integers(1, 50, 5))]
+    for sizes in cases:
+        for parts in (1, 2, 3, 4, 8, 11):
+            arr = (C.c_uint64 * max(len(sizes), 1))(*[int(x) for x in sizes])
+            cuts = (C.c_uint64 * (parts + 1))()
+            assert lib.micgpu_partition_by_bytes(arr, len(sizes), parts, cuts) == 0
+            want = shard.partition_by_bytes([int(x) for x in sizes], parts)
+            got = [(int(cuts[i]), int(cuts[i + 1])) for i in range(parts)]
+            assert got == want, (sizes[:8], parts, got, want)

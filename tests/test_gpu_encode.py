@@ -264,3 +264,28 @@ def test_pics_batch_encode_threaded_contexts(mic, oracle, synth):
     assert len(blobs) == 17
     for i, b in enumerate(blobs):
         assert b == want[i % 2], f"image {i}"
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (300, 201), (97, 33), (130, 57), (211, 160), (128, 40)])
+def test_rans8_frame_bytes(mic, oracle, synth, shape):
+    """RANSCompressU16EightState (rans8state.go:31-220, ransu16.go:139-213) over the Delta+RLE symbols: the CUDA encoder's
+    frame equals the oracle's byte for byte (every tail residue of len mod 8 through the shapes) and decodes back."""
+    w, h = shape
+    img = synth.xr_image(40 + w, w, h).ravel()
+    mx = int(img.max())
+    sym = oracle.delta_rle_compress(img, w, h, mx)
+    want = oracle.fse_compress(sym, 108)
+    got = mic.CompressSingleFrame(img, w, h, mx, 108)
+    assert got[:2] == b"\xff\x08"
+    assert got == want
+    assert np.array_equal(mic.DecompressSingleFrame(got, w, h), img)
+
+
+def test_rans8_rejects_like_the_reference(mic, oracle):
+    # constant image: the symbol stream is one RLE run -> ErrIncompressible / ErrUseRLE, and no ladder behind rANS
+    img = np.full(64 * 64, 700, np.uint16)
+    sym = oracle.delta_rle_compress(img, 64, 64, 700)
+    with pytest.raises(Exception):
+        oracle.fse_compress(sym, 108)
+    with pytest.raises(mic.MicGpuError):
+        mic.CompressSingleFrame(img, 64, 64, 700, 108)

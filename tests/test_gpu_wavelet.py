@@ -24,6 +24,23 @@ def test_wavelet_v2_decode(mic, oracle, rows, cols, levels):
     assert np.array_equal(got, ref) and np.array_equal(got, src)
 
 
+@pytest.mark.parametrize("rows,cols,levels", [(127, 136, 4), (255, 264, 3), (65, 72, 6), (33, 4096, 4), (129, 520, 5), (64, 128, 1),
+                                              (1000, 16, 3), (97, 2056, 2)])
+def test_wavelet_v2_decode_tma_tiles(mic, oracle, rows, cols, levels):
+    """Shapes the fused TMA level kernel takes (cols % 8 == 0): odd row counts, tiles cut by the right / bottom border,
+    levels whose low band is odd x odd, one-tile and many-tile levels, boxes whose halo leaves the plane."""
+    rng = np.random.default_rng(rows * 7 + cols)
+    src = (_field(rows, cols, 3).astype(np.int64) + rng.integers(0, 500, rows * cols)).astype(np.uint16)
+    blob = oracle.wavelet_v2_compress(src, rows, cols, 4095, levels)
+    got, r, c = mic.WaveletV2RLEFSEDecompressU16(blob)
+    assert (r, c) == (rows, cols) and np.array_equal(got, src)
+    # two images of one geometry share the launch sequence (grid.z): the second must not see the first's planes
+    src2 = np.roll(src, 17)
+    blob2 = oracle.wavelet_v2_compress(src2, rows, cols, 4095, levels)
+    res = mic.WaveletV2DecompressBatch([blob, blob2])
+    assert np.array_equal(res[0][0], src) and np.array_equal(res[1][0], src2)
+
+
 def test_wavelet_mammo_like(mic, oracle, synth):
     # BASELINE config 3 content at reduced size: 14-bit, ~45 % zero background, 5 levels
     img = synth.mammo_image(1, 1024, 832).ravel()

@@ -52,5 +52,11 @@ te, blob = timed(lambda: mic.CompressWSI(rgb, W, H), 1)
 hdr = mic.ReadWSIHeader(blob)
 tiles = [(0, tx, ty) for ty in range(hdr["Levels"][0][3]) for tx in range(hdr["Levels"][0][2])]
 td, _ = timed(lambda: mic.DecompressWSITiles(blob, tiles), 2)
-out["c5_wsi_8192x6144"] = {"encode_GBps": rgb.nbytes / te / 1e9, "decode_level0_GBps": rgb.nbytes / td / 1e9, "ratio": rgb.nbytes / len(blob), "tiles": len(tiles)}
+first0, n0 = hdr["Levels"][0][4], hdr["Levels"][0][2] * hdr["Levels"][0][3]
+td2, _ = timed(lambda: mic.DecompressWSITileRange(blob, first0, n0), 2)
+td3, _ = timed(lambda: mic.DecompressWSITileRange(blob, 0, hdr["TotalTiles"]), 2)
+out["c5_wsi_8192x6144"] = {"encode_GBps": rgb.nbytes / te / 1e9, "decode_level0_GBps": rgb.nbytes / td / 1e9,
+                           "decode_level0_tile_range_GBps": n0 * 196608 / td2 / 1e9, "decode_all_levels_tile_range_GBps": hdr["TotalTiles"] * 196608 / td3 / 1e9,
+                           "ratio": rgb.nbytes / len(blob), "tiles": len(tiles), "total_tiles": hdr["TotalTiles"],
+                           "note": "tile_range = micgpu_wsi_decompress_tile_range (one H2D, one D2H, full tiles); pageable buffers"}
 print(json.dumps({k: {a: (round(b, 3) if isinstance(b, float) else b) for a, b in v.items()} for k, v in out.items()}, indent=1))

@@ -6,9 +6,27 @@
 namespace micgpu {
 
 // ---- K10 forward: TemporalDeltaEncode (temporaldelta.go:11-23): ZigZag(int16(cur - prev)) -------------------------
+// Two uint16 lanes per word: lane-wise subtract mod 2^16 and lane-wise ZigZag of the int16 difference.
+__device__ __forceinline__ uint32_t sub2_u16(uint32_t a, uint32_t b) {
+  return ((a | 0x80008000u) - (b & 0x7FFF7FFFu)) ^ ((a ^ ~b) & 0x80008000u);
+}
+__device__ __forceinline__ uint32_t zigzag2_i16(uint32_t d) {
+  return ((d << 1) & 0xFFFEFFFEu) ^ (((d >> 15) & 0x00010001u) * 0xFFFFu);   // (d << 1) ^ (d >> 15) in both halves
+}
+
 __global__ void __launch_bounds__(256)
-k_temporal_residual(const uint16_t* __restrict__ frames, uint16_t* __restrict__ res, unsigned long long fpx, int nframes) {
+k_temporal_residual(const uint16_t* __restrict__ frames, uint16_t* __restrict__ res, unsigned long long fpx, int nframes, int vec) {
   const unsigned long long total = fpx * (unsigned long long)(nframes - 1);
+  if (vec) {   // eight residuals per thread: two 16 B loads, one 16 B store (frame size and pointers are 16 B multiples)
+    const unsigned long long ngrp = total >> 3, gpf = fpx >> 3;
+    const uint4* F = reinterpret_cast<const uint4*>(frames);
+    uint4* R = reinterpret_cast<uint4*>(res);
+    for (unsigned long long gi = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngrp; gi += (unsigned long long)gridDim.x * blockDim.x) {
+      const uint4 p = __ldg(F + gi), c = __ldg(F + gi + gpf);
+      R[gi] = make_uint4(zigzag2_i16(sub2_u16(c.x, p.x)), zigzag2_i16(sub2_u16(c.y, p.y)), zigzag2_i16(sub2_u16(c.z, p.z)), zigzag2_i16(sub2_u16(c.w, p.w)));
+    }
+    return;
+  }
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
     const int d = (int)(short)((int)frames[i + fpx] - (int)frames[i]);
     res[i] = (uint16_t)((d << 1) ^ (d >> 15));
@@ -231,7 +249,8 @@ k_plane_raw(const GatherJob* __restrict__ jobs, int njobs, const uint16_t* __res
 
 void launch_temporal_residual(const uint16_t* d_frames, uint16_t* d_res, unsigned long long fpx, int nframes, int sm_count, cudaStream_t st) {
   if (nframes <= 1 || fpx == 0) return;
-  k_temporal_residual<<<sm_count * 8, 256, 0, st>>>(d_frames, d_res, fpx, nframes);
+  const int vec = (fpx % 8 == 0) && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0) && (reinterpret_cast<uintptr_t>(d_res) % 16 == 0);
+  k_temporal_residual<<<sm_count * 8, 256, 0, st>>>(d_frames, d_res, fpx, nframes, vec);
 }
 void launch_downsample2x(const uint8_t* d_src, uint8_t* d_dst, unsigned w, unsigned h, unsigned ch, unsigned bytes_per_sample, int sm_count, cudaStream_t st) {
   if (w / 2 == 0 || h / 2 == 0) return;

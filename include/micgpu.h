@@ -226,6 +226,17 @@ int micgpu_rgb_compress(const uint8_t *rgb, int width, int height, uint8_t *out,
 int micgpu_wsi_compress(const uint8_t *pixels, int width, int height, int channels, int bits_per_sample, int tile_w, int tile_h,
                         int pyramid_levels, uint8_t *out, size_t cap, size_t *out_len);
 void micgpu_encoder_shutdown(void);
+
+/* ---- .mic file wrappers (cmd/mic-compress/main.go:26-91 writes them, cmd/mic-wasm/main.go:52-131 reads them) -------- */
+/* 1 MIC1 (single 16-bit frame), 2 MIC2, 3 MIC3, 4 MICR (RGB), 5 PICS, 0 unknown: route to the call of that container. */
+int micgpu_file_kind(const uint8_t *file, size_t len);
+/* MIC1 = "MIC1", width, height, pipeline (1 = Delta+RLE+FSE), length (u32 LE each), one frame. */
+int micgpu_mic1_compress(const uint16_t *pixels, int width, int height, uint16_t max_value, int nstates, uint8_t *out, size_t cap,
+                         size_t *out_len);
+int micgpu_mic1_decompress(const uint8_t *file, size_t len, uint16_t *pixels_out, size_t cap_px, int *width, int *height);
+/* MICR = "MICR", width, height (u32 LE), CompressRGB blob. */
+int micgpu_micr_compress(const uint8_t *rgb, int width, int height, uint8_t *out, size_t cap, size_t *out_len);
+int micgpu_micr_decompress(const uint8_t *file, size_t len, uint8_t *rgb_out, size_t cap_bytes, int *width, int *height);
 /* ojph/mic_compress_c.h:26-37 (maxValue derived from the pixels, no fallback ladder) */
 int mic_compress_two_state(const uint16_t *pixels, int width, int height, uint8_t *out, size_t out_cap, size_t *out_len);
 int mic_compress_four_state(const uint16_t *pixels, int width, int height, uint8_t *out, size_t out_cap, size_t *out_len);

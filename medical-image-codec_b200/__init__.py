@@ -33,6 +33,9 @@ from .api import (  # noqa: F401
     DecompressWSITileRange,
     WsiPlan,
     Init,
+    WriteMIC1,
+    WriteMICR,
+    DecodeMicFile,
     ReadWSIHeader,
     WaveletV2DecompressBatch,
     WaveletV2RLEFSEDecompressU16,

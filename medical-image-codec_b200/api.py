@@ -79,6 +79,11 @@ lib.micgpu_pics_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.P
 lib.micgpu_decompress_single_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
 lib.micgpu_mic2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip, _ip, _ip]
 lib.micgpu_mic2_decompress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_file_kind.argtypes = [C.c_void_p, C.c_size_t]
+lib.micgpu_mic1_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+lib.micgpu_mic1_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_micr_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+lib.micgpu_micr_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_init.argtypes = [_ip, C.c_int]
 lib.micgpu_wsi_plan_tiles.restype = C.c_void_p
 lib.micgpu_wsi_plan_tiles.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64]
@@ -539,6 +544,57 @@ def CompressWSI(pixels, width: int, height: int, channels: int = 3, bits_per_sam
     _check(lib.micgpu_wsi_compress(a.ctypes.data, width, height, channels, bits_per_sample, tile_width, tile_height, pyramid_levels,
                                    out.ctypes.data, out.size, C.byref(ol)))
     return out[: ol.value].tobytes()
+
+
+# ---- .mic files (cmd/mic-compress / cmd/mic-wasm) ----------------------------------------------
+def WriteMIC1(pixels, width: int, height: int, max_value: int, nstates: int = 2) -> bytes:
+    """writeMicFile(compressImage[4State](...)) (cmd/mic-compress/main.go:26-105) -> the bytes of the .mic file."""
+    a = _u16(pixels)
+    out = np.empty(4 * a.size + 8192, np.uint8)
+    n = C.c_size_t()
+    _check(lib.micgpu_mic1_compress(a.ctypes.data, width, height, max_value, nstates, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def WriteMICR(rgb, width: int, height: int) -> bytes:
+    a = np.ascontiguousarray(rgb, dtype=np.uint8).ravel()
+    out = np.empty(8 * a.size + 8192, np.uint8)
+    n = C.c_size_t()
+    _check(lib.micgpu_micr_compress(a.ctypes.data, width, height, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def DecodeMicFile(data):
+    """decodeMicFile (cmd/mic-wasm/main.go:52-131): dispatch on the magic.  -> (kind, pixels, width, height) with kind in
+    MIC1 / MICR / PICS / MIC2 (all frames) / MIC3 (header dict instead of pixels)."""
+    a = _bytes_view(data)
+    kind = lib.micgpu_file_kind(a.ctypes.data, a.size)
+    if kind == 1:
+        if a.size < 20:
+            raise MicGpuError(-1, "MIC1 file too small")
+        w, h = _rd32(a, 4), _rd32(a, 8)
+        out = np.empty(max(w * h, 1), np.uint16)
+        ww, hh = C.c_int(), C.c_int()
+        _check(lib.micgpu_mic1_decompress(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(ww), C.byref(hh)))
+        return "MIC1", out[: ww.value * hh.value], ww.value, hh.value
+    if kind == 4:
+        if a.size < 12:
+            raise MicGpuError(-1, "MICR file too small")
+        w, h = _rd32(a, 4), _rd32(a, 8)
+        out = np.empty(max(w * h * 3, 1), np.uint8)
+        ww, hh = C.c_int(), C.c_int()
+        _check(lib.micgpu_micr_decompress(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(ww), C.byref(hh)))
+        return "MICR", out[: ww.value * hh.value * 3], ww.value, hh.value
+    if kind == 5:
+        px, w, h = DecompressParallelStrips(a)
+        return "PICS", px, w, h
+    if kind == 2:
+        frames, hdr = DecompressMultiFrame(a)
+        return "MIC2", frames, hdr["Width"], hdr["Height"]
+    if kind == 3:
+        hdr = ReadWSIHeader(a)
+        return "MIC3", hdr, hdr["Width"], hdr["Height"]
+    raise MicGpuError(-1, "invalid .mic magic")
 
 
 # ---- batch decoder over device-resident buffers -------------------------------------

@@ -836,3 +836,76 @@ void micgpu_encoder_shutdown(void) {
 }
 
 }  // extern "C"
+
+// ---- .mic file wrappers: what cmd/mic-compress writes and cmd/mic-wasm / web/mic-decoder.js read -------
+extern "C" {
+
+// magic of a .mic file: 1 MIC1 (single frame), 2 MIC2, 3 MIC3, 4 MICR (RGB), 5 PICS, 0 unknown (cmd/mic-wasm/main.go:68-99)
+int micgpu_file_kind(const uint8_t* file, size_t len) {
+  if (!file || len < 4) return 0;
+  if (!memcmp(file, "MIC1", 4)) return 1;
+  if (!memcmp(file, "MIC2", 4)) return 2;
+  if (!memcmp(file, "MIC3", 4)) return 3;
+  if (!memcmp(file, "MICR", 4)) return 4;
+  if (!memcmp(file, "PICS", 4)) return 5;
+  return 0;
+}
+
+static void put_u32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+static uint32_t get_u32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// writeMicFile (cmd/mic-compress/main.go:26-58): "MIC1", width, height, pipeline 1 (Delta+RLE+FSE), length, frame.
+// nstates picks compressImage / compressImage4State / the 8-state variant (main.go:93-105), ladder included.
+int micgpu_mic1_compress(const uint16_t* pixels, int width, int height, uint16_t max_value, int nstates, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!pixels || !out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  if (cap < 20) return fail(MICGPU_E_SIZE, "output buffer too small");
+  size_t flen = 0;
+  const int rc = micgpu_compress_single_frame(pixels, width, height, max_value, nstates, out + 20, cap - 20, &flen);
+  if (rc) return rc;
+  if (flen > 0xFFFFFFFFull) return fail(MICGPU_E_UNSUPPORTED, "frame does not fit the MIC1 length field");
+  memcpy(out, "MIC1", 4);
+  put_u32(out + 4, (uint32_t)width); put_u32(out + 8, (uint32_t)height); put_u32(out + 12, 1u); put_u32(out + 16, (uint32_t)flen);
+  if (out_len) *out_len = 20 + flen;
+  return 0;
+}
+
+// the MIC1 branch of decodeMicFile (cmd/mic-wasm/main.go:97-131)
+int micgpu_mic1_decompress(const uint8_t* file, size_t len, uint16_t* pixels_out, size_t cap_px, int* width, int* height) {
+  if (!file || !pixels_out) return fail(MICGPU_E_HEADER, "null argument");
+  if (len < 4 || memcmp(file, "MIC1", 4) != 0) return fail(MICGPU_E_HEADER, "invalid .mic magic");
+  if (len < 20) return fail(MICGPU_E_HEADER, "MIC1 file too small");
+  const uint32_t w = get_u32(file + 4), h = get_u32(file + 8), pipeline = get_u32(file + 12), clen = get_u32(file + 16);
+  if (pipeline != 1) return fail(MICGPU_E_UNSUPPORTED, "unsupported pipeline type");
+  if (w == 0 || h == 0 || w > 0x7FFFFFFFu || h > 0x7FFFFFFFu) return fail(MICGPU_E_HEADER, "MIC1: invalid dimensions");
+  if (clen > len - 20) return fail(MICGPU_E_HEADER, "MIC1: compressed data extends beyond file");
+  if ((unsigned long long)w * h > cap_px) return fail(MICGPU_E_SIZE, "output buffer too small");
+  if (width) *width = (int)w;
+  if (height) *height = (int)h;
+  return micgpu_decompress_single_frame(file + 20, clen, pixels_out, (int)w, (int)h);
+}
+
+// writeMICRFile (cmd/mic-compress/main.go:61-91): "MICR", width, height, CompressRGB blob
+int micgpu_micr_compress(const uint8_t* rgb, int width, int height, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!rgb || !out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  if (cap < 12) return fail(MICGPU_E_SIZE, "output buffer too small");
+  size_t blen = 0;
+  const int rc = micgpu_rgb_compress(rgb, width, height, out + 12, cap - 12, &blen);
+  if (rc) return rc;
+  memcpy(out, "MICR", 4);
+  put_u32(out + 4, (uint32_t)width); put_u32(out + 8, (uint32_t)height);
+  if (out_len) *out_len = 12 + blen;
+  return 0;
+}
+
+int micgpu_micr_decompress(const uint8_t* file, size_t len, uint8_t* rgb_out, size_t cap_bytes, int* width, int* height) {
+  if (!file || !rgb_out) return fail(MICGPU_E_HEADER, "null argument");
+  if (len < 12 || memcmp(file, "MICR", 4) != 0) return fail(MICGPU_E_HEADER, "invalid MICR magic");
+  const uint32_t w = get_u32(file + 4), h = get_u32(file + 8);
+  if (w == 0 || h == 0 || w > 0x7FFFFFFFu || h > 0x7FFFFFFFu) return fail(MICGPU_E_HEADER, "MICR: invalid dimensions");
+  if ((unsigned long long)w * h * 3 > cap_bytes) return fail(MICGPU_E_SIZE, "output buffer too small");
+  if (width) *width = (int)w;
+  if (height) *height = (int)h;
+  return micgpu_rgb_decompress(file + 12, len - 12, (int)w, (int)h, rgb_out);
+}
+
+}  // extern "C"

@@ -31,10 +31,16 @@ namespace micgpu {
 
 constexpr int K3_THREADS = 256;
 constexpr int K3_WARPS = K3_THREADS / 32;
-constexpr int IN_N = 4096;
-constexpr int OUT_CH = 4096;
+// Chunk size: every chunk costs ~6 CTA barriers around short phases, so bigger chunks mean fewer barrier stalls per symbol
+// (measured: 47 % issue utilisation at 4096 with most stall samples on the barriers); 8192 still leaves 4 CTAs per SM.
+#ifndef MICGPU_K3_CHUNK
+#define MICGPU_K3_CHUNK 4096
+#endif
+constexpr int IN_N = MICGPU_K3_CHUNK;
+constexpr int OUT_CH = MICGPU_K3_CHUNK;
 constexpr int NWIN = OUT_CH / 32;
-constexpr int MAXR = 256;   // runs per chunk
+constexpr int WPL = NWIN / 32;   // 32-element windows per lane in the single-warp scans
+constexpr int MAXR = OUT_CH / 16;   // runs per chunk
 
 struct WalkState {
   int ipos;        // next input symbol to parse
@@ -47,7 +53,7 @@ struct WalkState {
   int done, err;
 };
 
-__global__ void __launch_bounds__(K3_THREADS, 5)
+__global__ void __launch_bounds__(K3_THREADS, MICGPU_K3_CHUNK > 4096 ? 4 : (MICGPU_K3_CHUNK < 4096 ? 6 : 5))
 k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict__ states,
              const uint16_t* __restrict__ tabS, uint16_t* __restrict__ D, uint32_t* __restrict__ M,
              uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue, int ubase) {
@@ -178,6 +184,33 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         int nr = 0;
         bool slow_once = false;
         while (o < budget && nr < MAXR) {
+          // Long-run path: headers whose run is longer than 32 elements are followed one by one with uniform (broadcast)
+          // loads -- one shared-memory load and a dozen instructions per header, ~70 cycles against ~200 for the
+          // shuffle block below, which pays off only when a 32-symbol load covers several headers.  8-bit planes
+          // (MIC3 tiles: midCount 127, a header every <= 124 symbols) spend most of this kernel's time in here.
+          while (c_rem == 0 && o < budget && nr < MAXR && ip + 2 <= we && ip + 2 <= nsym) {
+            const unsigned c = s_in[ip - wb];
+            const int room = budget - o;
+            if (c == 0) break;                                  // malformed: the scalar iteration reports it
+            if (c <= mid) {
+              if (c <= 32u) break;                              // short runs: the shuffle block
+              const unsigned v = s_in[ip + 1 - wb];
+              const int take = min((int)c, room);
+              if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = -(int)(v + 1u); }
+              nr++; o += take; ip += 2;
+              if (take < (int)c) { c_rem = c - (unsigned)take; kind = 0; value = v; }
+            } else {
+              const int len = (int)(c - mid);
+              if (len <= 32) break;
+              const int first = ip + 1;
+              const int take = min(min(len, room), we - first);   // we - first >= 1 here
+              if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = first - wb; }
+              nr++; o += take;
+              if (take < len) { c_rem = (unsigned)(len - take); kind = 1; ip += 1 + take; }
+              else ip += 1 + len;
+            }
+          }
+          if (!(o < budget && nr < MAXR)) break;
           // Fast block: 32 symbols in registers, one per lane; the header chain inside them is followed with one
           // shuffle per run (c is warp-uniform after the shuffle, so every branch below is uniform).  The scalar
           // iteration further down costs ~450 cycles per run (two dependent shared-memory loads, three stores, a dozen
@@ -405,10 +438,10 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       __syncthreads();
       // C2: exclusive prefix-max of "last non-delimiter position" over windows
       if (warp == 0) {
-        int loc[4], run = -1;
+        int loc[WPL], run = -1;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int w = lane * 4 + q;
+        for (int q = 0; q < WPL; q++) {
+          const int w = lane * WPL + q;
           const unsigned non = w < nwin ? s_non[w] : 0u;
           loc[q] = non ? (w * 32 + 31 - __clz(non)) : -1;
           run = max(run, loc[q]);
@@ -422,8 +455,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         int excl = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) excl = -1;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int w = lane * 4 + q;
+        for (int q = 0; q < WPL; q++) {
+          const int w = lane * WPL + q;
           if (w < nwin) s_wprev[w] = excl;
           excl = max(excl, loc[q]);
         }
@@ -445,10 +478,10 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
       __syncthreads();
       // C4: pixels per window -> exclusive scan
       if (warp == 0) {
-        int cnt[4], sum = 0;
+        int cnt[WPL], sum = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int w = lane * 4 + q;
+        for (int q = 0; q < WPL; q++) {
+          const int w = lane * WPL + q;
           int c = 0;
           if (w < nwin) {
             const int nvalid = min(32, nout - w * 32);
@@ -467,8 +500,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         }
         int excl = inc - sum;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int w = lane * 4 + q;
+        for (int q = 0; q < WPL; q++) {
+          const int w = lane * WPL + q;
           if (w < nwin) s_pixbase[w] = excl;
           excl += cnt[q];
         }

@@ -30,8 +30,13 @@ MICGPU_PARTS=1 python tools/mic3_bench.py --side 8192 --steps 1 --warmup 1 --no-
       -o $O/prof_mic3 python tools/mic3_bench.py --side 8192 --steps 1 --warmup 1 --no-e2e --no-cpu > $O/ncu_mic3.log 2>&1
 # front-end kernels (wavelet lifting, temporal, tile planes, pyramid): one launch each
 python tools/frontend_kernels.py > $O/frontends.json 2> $O/frontends.err && \
-  ncu --set full --clock-control none -k regex:"k_wt53|k_wavelet|k_temporal|k_tile_planes|k_downsample|k_plane" -c 24 \
+  ncu --set full --clock-control none -k regex:"k_wt53|k_wavelet|k_temporal|k_tile_planes|k_downsample|k_plane" -c 16 \
       -o $O/prof_frontends python tools/frontend_kernels.py > $O/ncu_frontends.log 2>&1
+# gpurun merges at most 64 MiB back: keep the raw-metric CSV of every capture, the reports only of the two main workloads
+for r in prof_pics8 prof_pics8_2state prof_mic3 prof_frontends; do
+  [ -f $O/$r.ncu-rep ] && ncu -i $O/$r.ncu-rep --page raw --csv > $O/$r.raw.csv 2>/dev/null
+done
+rm -f $O/prof_frontends.ncu-rep $O/prof_pics8_2state.ncu-rep
 python tools/bench_configs.py > $O/configs.json 2> $O/configs.err
 python tools/mic2_multi.py > $O/mic2_96.json 2> $O/mic2_96.err
-tail -2 $O/pytest_gpu.txt; cat $O/smoke.txt | tail -1; cat $O/bench.json | cut -c1-600
+du -sh $O; tail -2 $O/pytest_gpu.txt; cat $O/smoke.txt | tail -1; cat $O/bench.json | cut -c1-600

@@ -40,7 +40,11 @@ def short_name(full: str) -> str:
 
 
 def read_report(path: str):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    """path: a .ncu-rep, or the output of `ncu -i rep --page raw --csv` saved on the GPU box (capture_round.sh)"""
+    if path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}

@@ -1079,6 +1079,82 @@ int orc_delta_rle_decompress(const u16 *in, size_t n, int width, int height, u16
 }
 
 /* ------------------------------------------------------------------------ */
+/* L2: gradient-adaptive Delta + RLE (deltagradrlecompressu16.go, deltagradcompressu16.go:149-166) */
+/* ------------------------------------------------------------------------ */
+static i32 grad_predict(i32 w, i32 n, i32 nw, i32 ne) { /* deltagradcompressu16.go:149-166, gradShift = 3 (:147) */
+  i32 avg = (w + n) >> 1;
+  i32 gw = w - nw; if (gw < 0) gw = -gw;
+  i32 gn = n - nw; if (gn < 0) gn = -gn;
+  i32 g = gw + gn;
+  if (g == 0) return avg;
+  i32 corr = (ne - nw) >> 3;
+  i32 limit = g >> 1;
+  if (corr > limit) corr = limit;
+  else if (corr < -limit) corr = -limit;
+  return avg + corr;
+}
+
+/* neighbours of (x, y) in `a`; deltagradrlecompressu16.go:36-52 (encoder) and :97-121 (decoder) use the same cases */
+static i32 grad_context(const u16 *a, int width, int x, int y) {
+  size_t index = (size_t)y * (size_t)width + (size_t)x;
+  if (x == 0 && y == 0) return 0;
+  if (y == 0) return (i32)a[index - 1];
+  if (x == 0) return (i32)a[index - (size_t)width];
+  i32 w = (i32)a[index - 1], n = (i32)a[index - (size_t)width], nw = (i32)a[index - (size_t)width - 1];
+  i32 ne = nw;
+  if (x + 1 < width) ne = (i32)a[index - (size_t)width + 1];
+  return grad_predict(w, n, nw, ne);
+}
+
+int orc_grad_delta_rle_compress(const u16 *in, int width, int height, u16 max_value, u16 **out, size_t *out_len) { /* :26-68 */
+  *out = NULL; *out_len = 0;
+  if (max_value == 0) return ORC_ERR_ARG;
+  int depth = len16(max_value);
+  u16 thr = (u16)((1 << (depth - 1)) - 1);
+  u16 delim = (u16)((1 << depth) - 1);
+  rle_enc r;
+  rle_init(&r, delim);
+  rle_encode(&r, max_value);
+  for (int y = 0; y < height; y++) {
+    for (int x = 0; x < width; x++) {
+      u16 v = in[(size_t)y * (size_t)width + (size_t)x];
+      i32 diff = (i32)v - grad_context(in, width, x, y);
+      i32 ad = diff < 0 ? -diff : diff;
+      if ((u16)ad >= thr) {
+        rle_encode(&r, delim);
+        rle_encode(&r, v);
+      } else {
+        rle_encode(&r, (u16)((i32)thr + diff));
+      }
+    }
+  }
+  rle_flush(&r);
+  free(r.b);
+  *out = r.out.p; *out_len = r.out.n;
+  return 0;
+}
+
+int orc_grad_delta_rle_decompress(const u16 *in, size_t n, int width, int height, u16 *o) { /* :70-133 */
+  if (n < 2) return ORC_ERR_CORRUPT;
+  rle_dec r;
+  rle_dec_init(&r, in, n);
+  u16 max_value = rle_next2(&r);
+  int depth = len16(max_value);
+  if (depth == 0) return ORC_ERR_CORRUPT;
+  u16 thr = (u16)((1 << (depth - 1)) - 1);
+  u16 delim = (u16)((1 << depth) - 1);
+  for (int y = 0; y < height; y++) {
+    for (int x = 0; x < width; x++) {
+      size_t index = (size_t)y * (size_t)width + (size_t)x;
+      u16 v = rle_next2(&r);
+      if (v == delim) o[index] = rle_next2(&r);
+      else o[index] = (u16)(grad_context(o, width, x, y) + ((i32)v - (i32)thr));
+    }
+  }
+  return r.overrun ? ORC_ERR_CORRUPT : 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* L2: ZigZag, temporal, YCoCg-R, pyramid                                    */
 /* ------------------------------------------------------------------------ */
 u16 orc_zigzag(int16_t x) { return (u16)((i32)((u32)(i32)x << 1) ^ ((i32)x >> 15)); }
@@ -1260,6 +1336,26 @@ int orc_decompress_single_frame(const u8 *in, size_t len, int width, int height,
   return rc;
 }
 
+/* CompressSingleFrameGrad / DecompressSingleFrameGrad (multiframecompress.go:111-142): two-state first, then one-state */
+int orc_compress_single_frame_grad(const u16 *px, int width, int height, u16 max_value, u8 **out, size_t *out_len) {
+  *out = NULL; *out_len = 0;
+  u16 *sym; size_t ns;
+  int rc = orc_grad_delta_rle_compress(px, width, height, max_value, &sym, &ns);
+  if (rc) return rc;
+  rc = fse_ladder(sym, ns, 2, out, out_len);
+  free(sym);
+  return rc;
+}
+
+int orc_decompress_single_frame_grad(const u8 *in, size_t len, int width, int height, u16 *px_out) {
+  u16 *sym; size_t ns;
+  int rc = orc_fse_decompress_auto(in, len, &sym, &ns);
+  if (rc) return rc;
+  rc = orc_grad_delta_rle_decompress(sym, ns, width, height, px_out);
+  free(sym);
+  return rc;
+}
+
 int orc_compress_residual_frame(const u16 *res, size_t n, u16 max_value, u8 **out, size_t *out_len) {
   *out = NULL; *out_len = 0;
   u16 *sym; size_t ns;
@@ -1435,6 +1531,111 @@ int orc_pics_decompress(const u8 *in, size_t len, u16 **px_out, int *width, int 
     if (y1 > h) y1 = h;
     if (y0 >= h) { rc = ORC_ERR_CORRUPT; break; }
     rc = orc_decompress_single_frame(in + start, sl, w, y1 - y0, o + (size_t)y0 * w);
+  }
+  if (rc) { free(o); return rc; }
+  *px_out = o; *width = w; *height = h;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* L4: PICA (parallelstripsadaptive.go:54-289)                               */
+/* ------------------------------------------------------------------------ */
+/* adaptiveStripBoundaries (:214-289): equal-cost partition of the rows by their summed |vertical delta|.  The sums are
+ * integers below 2^53, so the float64 arithmetic of the reference is reproduced exactly by C doubles. */
+int orc_pica_boundaries(const u16 *px, int width, int height, int num_strips, int *starts) {
+  if (num_strips >= height) {
+    for (int i = 0; i < height; i++) starts[i] = i;
+    return height;
+  }
+  if (num_strips == 1) { starts[0] = 0; return 1; }
+  double *cum = (double *)calloc((size_t)height + 1, sizeof(double));
+  for (int y = 0; y < height; y++) {
+    u64 sum = 0;
+    if (y >= 1)
+      for (int x = 0; x < width; x++) {
+        i32 d = (i32)px[(size_t)y * width + x] - (i32)px[(size_t)(y - 1) * width + x];
+        sum += (u64)(d < 0 ? -d : d);
+      }
+    cum[y + 1] = cum[y] + (double)sum;
+  }
+  double total = cum[height];
+  starts[0] = 0;
+  if (total == 0) {
+    for (int i = 1; i < num_strips; i++) starts[i] = i * height / num_strips;
+  } else {
+    for (int i = 1; i < num_strips; i++) {
+      double target = total * (double)i / (double)num_strips;
+      int lo = starts[i - 1] + 1, hi = height;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cum[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      if (lo >= height) lo = height - 1;
+      starts[i] = lo;
+    }
+  }
+  free(cum);
+  return num_strips;
+}
+
+int orc_pica_compress(const u16 *px, int width, int height, u16 max_value, int num_strips, u8 **out, size_t *out_len) { /* :54-139 */
+  *out = NULL; *out_len = 0;
+  if (num_strips <= 0) return ORC_ERR_ARG; /* GOMAXPROCS default is a host property; callers pass it */
+  if (num_strips > height) num_strips = height;
+  if (num_strips < 1) num_strips = 1;
+  int *starts = (int *)calloc((size_t)height + 1, sizeof(int));
+  int actual = orc_pica_boundaries(px, width, height, num_strips, starts);
+  u8 **blobs = (u8 **)calloc((size_t)actual, sizeof(u8 *));
+  size_t *lens = (size_t *)calloc((size_t)actual, sizeof(size_t));
+  u32 *flags = (u32 *)calloc((size_t)actual, sizeof(u32));
+  int rc = 0;
+  for (int s = 0; s < actual && !rc; s++) {
+    int y0 = starts[s], y1 = s + 1 < actual ? starts[s + 1] : height;
+    const u16 *strip = px + (size_t)y0 * width;
+    u8 *ba = NULL, *bg = NULL; size_t la = 0, lg = 0;
+    int e1 = orc_compress_single_frame(strip, width, y1 - y0, max_value, 2, &ba, &la);
+    int e2 = orc_compress_single_frame_grad(strip, width, y1 - y0, max_value, &bg, &lg);
+    if (e2 == 0 && (e1 != 0 || lg <= la)) { blobs[s] = bg; lens[s] = lg; flags[s] = 1; free(ba); }
+    else { blobs[s] = ba; lens[s] = la; flags[s] = 0; free(bg); rc = e1; }
+  }
+  if (!rc) {
+    bbuf o = {0};
+    bb_append(&o, "PICA", 4);
+    bb_u32(&o, (u32)width); bb_u32(&o, (u32)height); bb_u32(&o, (u32)actual);
+    u32 off = 0;
+    for (int s = 0; s < actual; s++) {
+      bb_u32(&o, (u32)starts[s]); bb_u32(&o, off); bb_u32(&o, (u32)lens[s]); bb_u32(&o, flags[s]);
+      off += (u32)lens[s];
+    }
+    for (int s = 0; s < actual; s++) bb_append(&o, blobs[s], lens[s]);
+    *out = o.p; *out_len = o.n;
+  }
+  for (int s = 0; s < actual; s++) free(blobs[s]);
+  free(blobs); free(lens); free(flags); free(starts);
+  return rc;
+}
+
+int orc_pica_decompress(const u8 *in, size_t len, u16 **px_out, int *width, int *height) { /* :143-212 */
+  *px_out = NULL;
+  if (len < 16 || memcmp(in, "PICA", 4) != 0) return ORC_ERR_CORRUPT;
+  int w = (int)rd32(in + 4), h = (int)rd32(in + 8), ns = (int)rd32(in + 12);
+  if (ns < 0) return ORC_ERR_CORRUPT;
+  size_t header = 16 + (size_t)ns * 16;
+  if (len < header) return ORC_ERR_CORRUPT;
+  if (w <= 0 || h <= 0 || ns <= 0) return ORC_ERR_CORRUPT;
+  u16 *o = (u16 *)calloc((size_t)w * h, sizeof(u16));
+  int rc = 0;
+  for (int s = 0; s < ns && !rc; s++) {
+    const u8 *e = in + 16 + (size_t)s * 16;
+    long long y0 = (long long)rd32(e), so = rd32(e + 4), sl = rd32(e + 8);
+    u32 fl = rd32(e + 12);
+    long long y1 = s + 1 < ns ? (long long)rd32(e + 16) : h;
+    size_t start = header + (size_t)so, end = start + (size_t)sl;
+    if (end > len || start > end) { rc = ORC_ERR_CORRUPT; break; }
+    /* Go would panic on a slice out of range for rows outside the image; the oracle reports corruption */
+    if (y1 <= y0 || y0 < 0 || y1 > h) { rc = ORC_ERR_CORRUPT; break; }
+    if (fl & 1u) rc = orc_decompress_single_frame_grad(in + start, (size_t)sl, w, (int)(y1 - y0), o + (size_t)y0 * w);
+    else rc = orc_decompress_single_frame(in + start, (size_t)sl, w, (int)(y1 - y0), o + (size_t)y0 * w);
   }
   if (rc) { free(o); return rc; }
   *px_out = o; *width = w; *height = h;

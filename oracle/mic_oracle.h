@@ -101,6 +101,16 @@ int orc_wavelet_v2_decompress(const uint8_t *in, size_t len, uint16_t **px_out, 
 /* CompressParallelStrips[4State/8State] / DecompressParallelStrips (parallelstrips.go:55-330) */
 int orc_pics_compress(const uint16_t *px, int width, int height, uint16_t max_value, int num_strips, int nstates, uint8_t **out, size_t *out_len);
 int orc_pics_decompress(const uint8_t *in, size_t len, uint16_t **px_out, int *width, int *height);
+/* GradDeltaRleCompressU16 / GradDeltaRleDecompressU16 (deltagradrlecompressu16.go:26-133) */
+int orc_grad_delta_rle_compress(const uint16_t *px, int width, int height, uint16_t max_value, uint16_t **out, size_t *out_len);
+int orc_grad_delta_rle_decompress(const uint16_t *in, size_t n, int width, int height, uint16_t *px_out);
+/* CompressSingleFrameGrad / DecompressSingleFrameGrad (multiframecompress.go:111-142) */
+int orc_compress_single_frame_grad(const uint16_t *px, int width, int height, uint16_t max_value, uint8_t **out, size_t *out_len);
+int orc_decompress_single_frame_grad(const uint8_t *in, size_t len, int width, int height, uint16_t *px_out);
+/* adaptiveStripBoundaries, CompressParallelStripsAdaptive / DecompressParallelStripsAdaptive (parallelstripsadaptive.go:54-289) */
+int orc_pica_boundaries(const uint16_t *px, int width, int height, int num_strips, int *starts /* >= min(num_strips, height) */);
+int orc_pica_compress(const uint16_t *px, int width, int height, uint16_t max_value, int num_strips, uint8_t **out, size_t *out_len);
+int orc_pica_decompress(const uint8_t *in, size_t len, uint16_t **px_out, int *width, int *height);
 /* CompressMultiFrame / DecompressMultiFrame / DecompressFrame (multiframecompress.go:179-315) */
 int orc_mic2_compress(const uint16_t *frames, int width, int height, int nframes, uint16_t max_value, int temporal, uint8_t **out, size_t *out_len);
 int orc_mic2_decompress(const uint8_t *in, size_t len, uint16_t **frames_out, int *width, int *height, int *nframes, int *temporal);

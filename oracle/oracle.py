@@ -254,6 +254,50 @@ class Oracle:
         self._chk(self.lib.orc_pics_decompress(_ptr(a, _u8p), C.c_size_t(a.size), C.byref(p), C.byref(w), C.byref(h)), "pics_decompress")
         return self._take_u16(p, C.c_size_t(w.value * h.value)), w.value, h.value
 
+    def pica_boundaries(self, px, width, height, num_strips):
+        a = _as_u16(px)
+        starts = (C.c_int * max(1, min(num_strips, height)))()
+        n = self.lib.orc_pica_boundaries(_ptr(a, _u16p), width, height, num_strips, starts)
+        return list(starts[:n])
+
+    def pica_compress(self, px, width, height, max_value, num_strips) -> bytes:
+        a = _as_u16(px)
+        assert a.size == width * height
+        p, n = _u8p(), C.c_size_t()
+        self._chk(self.lib.orc_pica_compress(_ptr(a, _u16p), width, height, C.c_uint16(max_value), num_strips, C.byref(p), C.byref(n)), "pica_compress")
+        return self._take_u8(p, n)
+
+    def pica_decompress(self, blob):
+        a = _as_u8(blob)
+        p = _u16p()
+        w, h = C.c_int(), C.c_int()
+        self._chk(self.lib.orc_pica_decompress(_ptr(a, _u8p), C.c_size_t(a.size), C.byref(p), C.byref(w), C.byref(h)), "pica_decompress")
+        return self._take_u16(p, C.c_size_t(w.value * h.value)), w.value, h.value
+
+    def compress_single_frame_grad(self, px, width, height, max_value) -> bytes:
+        a = _as_u16(px)
+        p, n = _u8p(), C.c_size_t()
+        self._chk(self.lib.orc_compress_single_frame_grad(_ptr(a, _u16p), width, height, C.c_uint16(max_value), C.byref(p), C.byref(n)), "compress_single_frame_grad")
+        return self._take_u8(p, n)
+
+    def decompress_single_frame_grad(self, blob, width, height):
+        a = _as_u8(blob)
+        out = np.empty(width * height, np.uint16)
+        self._chk(self.lib.orc_decompress_single_frame_grad(_ptr(a, _u8p), C.c_size_t(a.size), width, height, _ptr(out, _u16p)), "decompress_single_frame_grad")
+        return out
+
+    def grad_delta_rle_compress(self, px, width, height, max_value):
+        a = _as_u16(px)
+        p, n = _u16p(), C.c_size_t()
+        self._chk(self.lib.orc_grad_delta_rle_compress(_ptr(a, _u16p), width, height, C.c_uint16(max_value), C.byref(p), C.byref(n)), "grad_delta_rle_compress")
+        return self._take_u16(p, n)
+
+    def grad_delta_rle_decompress(self, sym, width, height):
+        a = _as_u16(sym)
+        out = np.empty(width * height, np.uint16)
+        self._chk(self.lib.orc_grad_delta_rle_decompress(_ptr(a, _u16p), C.c_size_t(a.size), width, height, _ptr(out, _u16p)), "grad_delta_rle_decompress")
+        return out
+
     def mic2_compress(self, frames, width, height, max_value, temporal) -> bytes:
         a = _as_u16(frames)
         nframes = a.size // (width * height)

@@ -81,6 +81,10 @@ int micgpu_decoder_add_unit(micgpu_decoder *d, const uint8_t *frame, size_t fram
  * blob is assumed to be copied at comp_off; pixels land at out_off. */
 int micgpu_decoder_add_pics(micgpu_decoder *d, const uint8_t *pics, size_t len, uint64_t comp_off, uint64_t out_off,
                             int *width, int *height);
+/* Add every strip of a PICA container (parallelstripsadaptive.go:143-212): content-adaptive strip rows, per-strip
+ * predictor flag (bit 0 = gradient-adaptive, deltagradrlecompressu16.go:70-133). */
+int micgpu_decoder_add_pica(micgpu_decoder *d, const uint8_t *pica, size_t len, uint64_t comp_off, uint64_t out_off,
+                            int *width, int *height);
 /* Add every frame of an independent-mode MIC2 container (multiframecompress.go:227-262). */
 int micgpu_decoder_add_mic2(micgpu_decoder *d, const uint8_t *mic2, size_t len, uint64_t comp_off, uint64_t out_off,
                             int *width, int *height, int *frames, int *temporal);
@@ -139,6 +143,11 @@ int micgpu_pics_decompress_batch(int n, const uint8_t *const *blobs, const size_
                                  const size_t *caps, int *status);
 /* DecompressSingleFrame (multiframecompress.go:97): any of the 1/2/4/8-state or rANS-8 streams. */
 int micgpu_decompress_single_frame(const uint8_t *frame, size_t len, uint16_t *pixels_out, int width, int height);
+/* DecompressSingleFrameGrad (multiframecompress.go:129-142): the gradient-adaptive predictor of
+ * deltagradrlecompressu16.go:70-133 / gradPredict (deltagradcompressu16.go:149-166). */
+int micgpu_decompress_single_frame_grad(const uint8_t *frame, size_t len, uint16_t *pixels_out, int width, int height);
+/* DecompressParallelStripsAdaptive (parallelstripsadaptive.go:143). */
+int micgpu_pica_decompress(const uint8_t *pica, size_t len, uint16_t *pixels_out, size_t cap_px, int *width, int *height);
 /* DecompressMultiFrame / DecompressFrame (multiframecompress.go:227,266). */
 int micgpu_mic2_decompress(const uint8_t *mic2, size_t len, uint16_t *frames_out, size_t cap_px, int *width, int *height,
                            int *frames, int *temporal);
@@ -213,6 +222,15 @@ int micgpu_pics_compress(const uint16_t *pixels, int width, int height, uint16_t
                          size_t cap, size_t *out_len);
 int micgpu_pics_compress_batch(int n, const uint16_t *const *pixels, int width, int height, const uint16_t *max_values, int num_strips,
                                int nstates, uint8_t *const *outs, const size_t *caps, size_t *out_lens, int *status);
+/* CompressSingleFrameGrad (multiframecompress.go:111-127): gradient-adaptive Delta + RLE, 2-state FSE with 1-state fallback. */
+int micgpu_compress_single_frame_grad(const uint16_t *pixels, int width, int height, uint16_t max_value, uint8_t *out, size_t cap,
+                                      size_t *out_len);
+/* CompressParallelStripsAdaptive (parallelstripsadaptive.go:54-139): adaptive strip rows (equal-cost partition of the
+ * inter-row |delta| sums), both predictors per strip, the smaller frame kept; num_strips must be > 0. */
+int micgpu_pica_compress(const uint16_t *pixels, int width, int height, uint16_t max_value, int num_strips, uint8_t *out, size_t cap,
+                         size_t *out_len);
+/* adaptiveStripBoundaries (parallelstripsadaptive.go:214-289): starts_out holds min(num_strips, height) ints. */
+int micgpu_pica_boundaries(const uint16_t *pixels, int width, int height, int num_strips, int *starts_out, int *n_out);
 /* CompressMultiFrame (multiframecompress.go:179): frames contiguous, independent or temporal (ZigZag residual) mode. */
 int micgpu_mic2_compress(const uint16_t *frames, int width, int height, int nframes, uint16_t max_value, int temporal, uint8_t *out,
                          size_t cap, size_t *out_len);

@@ -16,6 +16,11 @@ from .api import (  # noqa: F401
     WaveletV2RLEFSECompressU16,
     WaveletV2SIMDRLEFSECompressU16,
     CompressParallelStripsBatch,
+    CompressParallelStripsAdaptive,
+    CompressSingleFrameGrad,
+    DecompressParallelStripsAdaptive,
+    DecompressSingleFrameGrad,
+    AdaptiveStripBoundaries,
     CompressSingleFrame,
     CompressSingleFrame4State,
     CompressSingleFrame8State,

@@ -77,6 +77,9 @@ lib.micgpu_decoder_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_
 lib.micgpu_pics_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_pics_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip]
 lib.micgpu_decompress_single_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+lib.micgpu_decompress_single_frame_grad.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+lib.micgpu_pica_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_decoder_add_pica.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, _ip, _ip]
 lib.micgpu_mic2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip, _ip, _ip]
 lib.micgpu_mic2_decompress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_file_kind.argtypes = [C.c_void_p, C.c_size_t]
@@ -117,6 +120,9 @@ lib.micgpu_delta_rle_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint
 lib.micgpu_rle_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_uint16, C.c_void_p, C.c_size_t, _szp]
 lib.micgpu_compress_single_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
 lib.micgpu_pics_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_compress_single_frame_grad.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_pica_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_pica_boundaries.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _ip]
 lib.micgpu_pics_compress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_int,
                                            C.POINTER(C.c_void_p), _szp, _szp, _ip]
 lib.micgpu_mic2_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
@@ -233,6 +239,28 @@ def DecompressSingleFrame(compressed, width: int, height: int) -> np.ndarray:
     out = np.empty(width * height, np.uint16)
     _check(lib.micgpu_decompress_single_frame(a.ctypes.data, a.size, out.ctypes.data, width, height))
     return out
+
+
+def DecompressSingleFrameGrad(compressed, width: int, height: int) -> np.ndarray:
+    """multiframecompress.go:129 (gradient-adaptive predictor)."""
+    a = _bytes_view(compressed)
+    out = np.empty(width * height, np.uint16)
+    _check(lib.micgpu_decompress_single_frame_grad(a.ctypes.data, a.size, out.ctypes.data, width, height))
+    return out
+
+
+def DecompressParallelStripsAdaptive(compressed):
+    """parallelstripsadaptive.go:143 -> (pixels[h*w] uint16, width, height)."""
+    a = _bytes_view(compressed)
+    if a.size < 16 or bytes(a[:4]) != b"PICA":
+        raise MicGpuError(E_HEADER, "pica: invalid magic")
+    w, h = _rd32(a, 4), _rd32(a, 8)
+    if w <= 0 or h <= 0 or w * h > (1 << 34):
+        raise MicGpuError(E_HEADER, "pica: invalid dimensions")
+    out = np.empty(w * h, np.uint16)
+    ow, oh = C.c_int(), C.c_int()
+    _check(lib.micgpu_pica_decompress(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(ow), C.byref(oh)))
+    return out, ow.value, oh.value
 
 
 def DecompressMultiFrame(data):
@@ -473,6 +501,35 @@ def CompressParallelStrips(pixels, width: int, height: int, max_value: int, num_
     n = C.c_size_t()
     _check(lib.micgpu_pics_compress(a.ctypes.data, width, height, max_value, num_strips, nstates, out.ctypes.data, out.size, C.byref(n)))
     return out[: n.value].tobytes()
+
+
+def CompressSingleFrameGrad(pixels, width: int, height: int, max_value: int) -> bytes:
+    """CompressSingleFrameGrad (multiframecompress.go:111)."""
+    a = _u16(pixels)
+    out = np.empty(4 * a.size + 8192, np.uint8)
+    n = C.c_size_t()
+    _check(lib.micgpu_compress_single_frame_grad(a.ctypes.data, width, height, max_value, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def CompressParallelStripsAdaptive(pixels, width: int, height: int, max_value: int, num_strips: int) -> bytes:
+    """CompressParallelStripsAdaptive (parallelstripsadaptive.go:54)."""
+    a = _u16(pixels)
+    if a.size != width * height:
+        raise MicGpuError(E_HEADER, f"pica: pixel count {a.size} != width*height {width * height}")
+    out = np.empty(4 * a.size + 8192 * max(min(num_strips, height), 1), np.uint8)
+    n = C.c_size_t()
+    _check(lib.micgpu_pica_compress(a.ctypes.data, width, height, max_value, num_strips, out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def AdaptiveStripBoundaries(pixels, width: int, height: int, num_strips: int):
+    """adaptiveStripBoundaries (parallelstripsadaptive.go:214)."""
+    a = _u16(pixels)
+    starts = (C.c_int * max(1, min(num_strips, height)))()
+    n = C.c_int()
+    _check(lib.micgpu_pica_boundaries(a.ctypes.data, width, height, num_strips, starts, C.byref(n)))
+    return list(starts[: n.value])
 
 
 def CompressParallelStripsBatch(images, width: int, height: int, max_values, num_strips: int, nstates: int = 2):

@@ -89,7 +89,7 @@ k_delta_wavefront(MicUnit* __restrict__ units, const int* __restrict__ list, int
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = blockDim.x >> 5;
   const MicUnit* U = &units[list[blockIdx.x]];
-  if (U->status != MIC_OK) return;
+  if (U->status != MIC_OK || U->predictor != 0u) return;   // gradient-predictor units belong to k_grad_wavefront
   if (redo_only && !U->k4_redo) return;   // only the units the row-scan kernel (k_delta_scan.cu) handed back
   const int W = (int)U->width, H = (int)U->height;
   const unsigned wp = U->wp;

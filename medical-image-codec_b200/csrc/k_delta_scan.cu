@@ -128,7 +128,7 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
   __syncthreads();
 
   MicUnit* U = &units[list[blockIdx.x]];
-  if (U->status != MIC_OK) return;
+  if (U->status != MIC_OK || U->predictor != 0u) return;   // gradient-predictor units belong to k_grad_wavefront
   const int W = (int)U->width, H = (int)U->height;
   const unsigned wp = U->wp;
   const int thr = (int)U->thr;

@@ -3,7 +3,8 @@
 // Replaces DeltaRleCompressU16.Compress (deltarlecompressu16.go:24-68) and the stateful buffer machine
 // RleCompressU16.{Init,Encode,Flush,Compress} (rlecompressu16.go:15-93); C twin delta_rle_encode.
 //
-// E1 (k_enc_delta): V = [maxValue, symbols...]: per pixel pred = avg(top,left) from the SOURCE pixels, so it is
+// E1 (k_enc_delta): V = [maxValue, symbols...]: per pixel pred = avg(top,left) -- or the gradient-adaptive predictor of
+//   deltagradrlecompressu16.go:26-68 when MicEncUnit::predictor is 1 -- from the SOURCE pixels, so it is
 //   embarrassingly parallel; an escaped pixel contributes two symbols (delim, raw), positions by block scan.
 // E2 (k_enc_rle_*): the reference encoder is a serial state machine, but its output has a closed form:
 //   * every maximal run of >= 3 equal symbols is coded in "same" mode, everything between two such runs is a
@@ -58,6 +59,7 @@ k_enc_delta(MicEncUnit* __restrict__ units, int nunits, const uint16_t* __restri
     const uint16_t* px = src + U->src_off;
     uint16_t* V = Vbuf + U->v_off;
     const unsigned maxv = U->max_value;
+    const bool grad = U->predictor == 1u;
     const int depth = 32 - __clz(maxv);
     if (maxv == 0 || maxv > 65535 || depth < 4) {   // Go: 1<<-1 panics for 0; depths 1-3 give midCount <= 3 and a broken RLE
       if (threadIdx.x == 0) U->status = MIC_ENC_UNSUPPORTED;
@@ -78,7 +80,16 @@ k_enc_delta(MicEncUnit* __restrict__ units, int nunits, const uint16_t* __restri
           const unsigned long long p = p0 + q;
           if (p < npx) {
             int pred = 0;
-            if (x > 0 && y > 0) pred = ((int)px[p - 1] + (int)px[p - W]) >> 1;
+            if (x > 0 && y > 0) {
+              if (grad) {   // gradPredict (deltagradcompressu16.go:149-166), neighbours from the source like the avg case
+                const int w = px[p - 1], n = px[p - W], nw = px[p - W - 1];
+                const int ne = x + 1 < W ? (int)px[p - W + 1] : nw;
+                const int g = abs(w - nw) + abs(n - nw), limit = g >> 1;
+                pred = ((w + n) >> 1) + min(max((ne - nw) >> 3, -limit), limit);
+              } else {
+                pred = ((int)px[p - 1] + (int)px[p - W]) >> 1;
+              }
+            }
             else if (x > 0) pred = px[p - 1];
             else if (y > 0) pred = px[p - W];
             const int v = px[p];

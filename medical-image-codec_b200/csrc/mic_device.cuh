@@ -55,6 +55,11 @@ void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, cons
 bool launch_delta_rowscan(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,
                           uint16_t* d_out, int max_width, bool all_aligned, cudaStream_t st);
 int delta_wavefront_threads(int max_width, int max_height);
+// Gradient-adaptive predictor (k_grad.cu): one CTA per listed unit with MicUnit::predictor == 1 (the others return at once).
+void launch_grad_wavefront(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M, uint16_t* d_out,
+                           int max_height, cudaStream_t st);
+// PICA row statistics (adaptiveStripBoundaries): cost[y] = sum_x |px[y][x] - px[y-1][x]|, cost[0] = 0
+void launch_row_costs(const uint16_t* d_px, int width, int height, unsigned long long* d_cost, cudaStream_t st);
 
 // In-place frame-axis running sum for temporal MIC2 (frames contiguous, fpx pixels each).
 void launch_temporal_accumulate(uint16_t* d_frames, unsigned long long fpx, int nframes, int first_is_residual, int sm_count,

@@ -38,6 +38,7 @@ struct MicEncUnit {
   unsigned int kind;
   unsigned int nstates;         // requested tier 8/4/2/1
   unsigned int no_ladder;       // 1: a rejected tier is final (WaveletV2 uses FSECompressU16FourState with no fallback)
+  unsigned int predictor;       // spatial kind: 0 = avg(top,left), 1 = gradient-adaptive (GradDeltaRleCompressU16, deltagradrlecompressu16.go:26-68)
   unsigned int rans;            // 1: RANSCompressU16EightState (rans8state.go:31): nstates 8, magic 0x08, no fallback ladder
   unsigned int v_cap, s_cap, out_cap;
   // ---- device-filled ----------------------------------------------------

@@ -45,6 +45,9 @@ struct MicUnit {
                                 // is stored at padded column a_y + x with a_y = (align0 + y*width) mod 8
   unsigned int exact_len;       // RLE kind: 1 = the expanded length must equal `width` (a MIC2 residual frame is exactly
                                 // one frame, multiframecompress.go:165-175); 0 = `width` is only a capacity
+  unsigned int predictor;       // spatial kind: 0 = avg(top,left) (deltarlecompressu16.go), 1 = gradient-adaptive
+                                // (deltagradrlecompressu16.go; PICA strips with picaFlagGradPredictor, DecompressSingleFrameGrad)
+  unsigned int pad0;
   // ---- device-filled ----------------------------------------------------
   unsigned int bits_off;        // byte offset of the bitstream inside the frame
   unsigned int bits_len;        // bitstream length in bytes

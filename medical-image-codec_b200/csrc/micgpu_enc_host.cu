@@ -229,6 +229,17 @@ int enc_run(micgpu_encoder* e, const uint16_t* d_src, const EncHook& after_uploa
   return 0;
 }
 
+int err_code_of(int st) {
+  switch (st) {
+    case MIC_ENC_OK: return 0;
+    case MIC_ENC_INCOMPRESSIBLE: return MICGPU_E_INCOMPRESSIBLE;
+    case MIC_ENC_USE_RLE: return MICGPU_E_USE_RLE;
+    case MIC_ENC_CAPACITY: return MICGPU_E_SIZE;
+    case MIC_ENC_UNSUPPORTED: return MICGPU_E_UNSUPPORTED;
+    default: return MICGPU_E_INTERNAL;
+  }
+}
+
 int enc_status_to_rc(int st) {
   switch (st) {
     case MIC_ENC_OK: return 0;
@@ -310,6 +321,147 @@ int micgpu_compress_single_frame(const uint16_t* pixels, int width, int height, 
   if (r.frame_len > cap) return fail(MICGPU_E_SIZE, "output buffer too small");
   CUDA_TRY(cudaMemcpy(out, (uint8_t*)e->d_frames.p + r.out_off, r.frame_len, cudaMemcpyDeviceToHost));
   if (out_len) *out_len = r.frame_len;
+  return 0;
+}
+
+// CompressSingleFrameGrad (multiframecompress.go:111-127): gradient-adaptive Delta + RLE, two-state FSE, one-state fallback
+int micgpu_compress_single_frame_grad(const uint16_t* pixels, int width, int height, uint16_t max_value, uint8_t* out, size_t cap,
+                                      size_t* out_len) {
+  if (!pixels || !out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->units.clear();
+  const int ui = enc_add_unit(e, MIC_ENC_SPATIAL, 0, (unsigned)width, (unsigned)height, max_value, 2);
+  e->units[ui].predictor = 1;
+  const size_t npx = (size_t)width * height;
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if ((rc = e->d_src.ensure(npx * 2 + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_src.p, pixels, npx * 2, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = enc_run(e, (const uint16_t*)e->d_src.p))) return rc;
+  const MicEncUnit& r = e->h_units[0];
+  if (r.status != MIC_ENC_OK) return enc_status_to_rc(r.status);
+  if (r.frame_len > cap) return fail(MICGPU_E_SIZE, "output buffer too small");
+  CUDA_TRY(cudaMemcpy(out, (uint8_t*)e->d_frames.p + r.out_off, r.frame_len, cudaMemcpyDeviceToHost));
+  if (out_len) *out_len = r.frame_len;
+  return 0;
+}
+
+// adaptiveStripBoundaries (parallelstripsadaptive.go:214-289) from the per-row costs the GPU summed.  The reference
+// accumulates in float64; the sums are integers far below 2^53, so the doubles here take exactly the same values.
+static void pica_boundaries(const unsigned long long* cost, int height, int num_strips, std::vector<int>& starts) {
+  starts.clear();
+  if (num_strips >= height) {
+    for (int i = 0; i < height; i++) starts.push_back(i);
+    return;
+  }
+  if (num_strips == 1) { starts.push_back(0); return; }
+  std::vector<double> cum((size_t)height + 1, 0.0);
+  for (int y = 0; y < height; y++) cum[y + 1] = cum[y] + (double)cost[y];
+  const double total = cum[height];
+  starts.assign(num_strips, 0);
+  if (total == 0) {
+    for (int i = 1; i < num_strips; i++) starts[i] = (int)((long long)i * height / num_strips);
+    return;
+  }
+  for (int i = 1; i < num_strips; i++) {
+    const double target = total * (double)i / (double)num_strips;
+    int lo = starts[i - 1] + 1, hi = height;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= height) lo = height - 1;
+    starts[i] = lo;
+  }
+}
+
+// CompressParallelStripsAdaptive (parallelstripsadaptive.go:54-139): content-adaptive strip boundaries, every strip coded
+// with both predictors (two units per strip, one launch sequence for all of them), the smaller frame kept (the gradient
+// one on a tie), "PICA" container.  starts_out (optional, >= min(num_strips, height) ints) receives the strip start rows.
+int micgpu_pica_compress(const uint16_t* pixels, int width, int height, uint16_t max_value, int num_strips, uint8_t* out, size_t cap,
+                         size_t* out_len) {
+  if (!pixels || !out || width <= 0 || height <= 0 || num_strips <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  int ns = std::min(num_strips, height);
+  if (ns < 1) ns = 1;
+  const size_t npx = (size_t)width * height;
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if ((rc = e->d_src.ensure(npx * 2 + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_src.p, pixels, npx * 2, cudaMemcpyHostToDevice, e->stream));
+  std::vector<unsigned long long> cost((size_t)height, 0);
+  if (ns > 1 && ns < height) {
+    if ((rc = e->d_stats.ensure((size_t)height * sizeof(unsigned long long)))) return rc;
+    launch_row_costs((const uint16_t*)e->d_src.p, width, height, (unsigned long long*)e->d_stats.p, e->stream);
+    CUDA_TRY(cudaMemcpyAsync(cost.data(), e->d_stats.p, (size_t)height * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
+  std::vector<int> starts;
+  pica_boundaries(cost.data(), height, ns, starts);
+  const int actual = (int)starts.size();
+  e->units.clear();
+  for (int s = 0; s < actual; s++) {
+    const int y0 = starts[s], y1 = s + 1 < actual ? starts[s + 1] : height;
+    for (int g = 0; g < 2; g++) {
+      // a boundary list may repeat a row (targets beyond the last row collapse onto height-1): such a strip has no rows,
+      // the reference then fails in FSE on the one-symbol stream; enc_plan marks a zero-height unit unsupported
+      const int ui = enc_add_unit(e, MIC_ENC_SPATIAL, (unsigned long long)y0 * width, (unsigned)width, (unsigned)std::max(0, y1 - y0), max_value, 2);
+      e->units[ui].predictor = (unsigned)g;
+    }
+  }
+  if ((rc = enc_run(e, (const uint16_t*)e->d_src.p))) return rc;
+  size_t total = 16 + (size_t)actual * 16;
+  std::vector<int> pick(actual);
+  for (int s = 0; s < actual; s++) {
+    const MicEncUnit &a = e->h_units[2 * s], &g = e->h_units[2 * s + 1];
+    const bool ga = g.status == MIC_ENC_OK && (a.status != MIC_ENC_OK || g.frame_len <= a.frame_len);
+    if (!ga && a.status != MIC_ENC_OK) { enc_status_to_rc(a.status); return fail(err_code_of(a.status), "pica: strip %d: %s", s, std::string(err_slot()).c_str()); }
+    pick[s] = 2 * s + (ga ? 1 : 0);
+    total += e->h_units[pick[s]].frame_len;
+  }
+  if (total > cap) return fail(MICGPU_E_SIZE, "output buffer too small");
+  auto put = [&](size_t off, uint32_t v) { out[off] = (uint8_t)v; out[off + 1] = (uint8_t)(v >> 8); out[off + 2] = (uint8_t)(v >> 16); out[off + 3] = (uint8_t)(v >> 24); };
+  memcpy(out, "PICA", 4);
+  put(4, (uint32_t)width); put(8, (uint32_t)height); put(12, (uint32_t)actual);
+  const size_t hdr = 16 + (size_t)actual * 16;
+  size_t off = 0;
+  for (int s = 0; s < actual; s++) {
+    const MicEncUnit& r = e->h_units[pick[s]];
+    const size_t eo = 16 + (size_t)s * 16;
+    put(eo, (uint32_t)starts[s]); put(eo + 4, (uint32_t)off); put(eo + 8, r.frame_len); put(eo + 12, (uint32_t)(pick[s] & 1));
+    CUDA_TRY(cudaMemcpyAsync(out + hdr + off, (uint8_t*)e->d_frames.p + r.out_off, r.frame_len, cudaMemcpyDeviceToHost, e->stream));
+    off += r.frame_len;
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (out_len) *out_len = total;
+  return 0;
+}
+
+// the strip start rows CompressParallelStripsAdaptive would choose (test / tooling hook for adaptiveStripBoundaries)
+int micgpu_pica_boundaries(const uint16_t* pixels, int width, int height, int num_strips, int* starts_out, int* n_out) {
+  if (!pixels || !starts_out || width <= 0 || height <= 0 || num_strips <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const int ns = std::max(1, std::min(num_strips, height));
+  const size_t npx = (size_t)width * height;
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if ((rc = e->d_src.ensure(npx * 2 + 64))) return rc;
+  if ((rc = e->d_stats.ensure((size_t)height * sizeof(unsigned long long)))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_src.p, pixels, npx * 2, cudaMemcpyHostToDevice, e->stream));
+  launch_row_costs((const uint16_t*)e->d_src.p, width, height, (unsigned long long*)e->d_stats.p, e->stream);
+  std::vector<unsigned long long> cost((size_t)height, 0);
+  CUDA_TRY(cudaMemcpyAsync(cost.data(), e->d_stats.p, (size_t)height * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  std::vector<int> starts;
+  pica_boundaries(cost.data(), height, ns, starts);
+  for (size_t i = 0; i < starts.size(); i++) starts_out[i] = starts[i];
+  if (n_out) *n_out = (int)starts.size();
   return 0;
 }
 

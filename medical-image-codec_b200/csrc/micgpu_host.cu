@@ -68,6 +68,7 @@ struct micgpu_decoder {
   AnsPlan ans[4];
   unsigned long long sym_total = 0, tab_total = 0, d_total = 0, m_total = 0, out_need = 0;
   int max_log_all = 5, max_w = 1, max_h = 1;
+  int n_grad = 0;             // spatial units coded with the gradient-adaptive predictor
   int k1_grid = 1;
   unsigned long long k1_stride = 0;
   bool committed = false;
@@ -139,6 +140,7 @@ int plan_commit(micgpu_decoder* d) {
   d->sym_total = d->tab_total = d->d_total = d->m_total = 0;
   d->max_log_all = 5;
   d->max_w = d->max_h = 1;
+  d->n_grad = 0;
   for (auto& l : d->lists) l.clear();
   d->spatial.clear();
   for (size_t i = 0; i < d->units.size(); i++) {
@@ -162,6 +164,7 @@ int plan_commit(micgpu_decoder* d) {
       u.m_off = d->m_total;
       d->m_total += (unsigned long long)(u.wp >> 5) * u.height;
       d->spatial.push_back((int)i);
+      if (u.predictor) d->n_grad++;
       d->max_w = std::max(d->max_w, (int)u.width);
       d->max_h = std::max(d->max_h, (int)u.height);
     } else {
@@ -328,15 +331,22 @@ void prof_mark(micgpu_decoder* d, const char* name, cudaStream_t st) {
 // K4 over a slice of the spatial list: the row-scan kernel, then the wavefront kernel for the units it handed back
 // (uint16 wrap: none on encoder-made streams) -- or the wavefront kernel alone with MICGPU_K4=wave / for units wider than
 // one CTA can chain.  Returns the number of launches.
+// gradient-predictor units of the slice (PICA strips, DecompressSingleFrameGrad): the avg kernels skip them, this one skips the rest
+int launch_k4_grad(micgpu_decoder* d, MicUnit* du, const int* list, int n, void* d_out, cudaStream_t st) {
+  if (!d->n_grad) return 0;
+  launch_grad_wavefront(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_h, st);
+  return 1;
+}
+
 int launch_k4(micgpu_decoder* d, MicUnit* du, const int* list, int n, void* d_out, cudaStream_t st) {
   static const bool wave_only = [] { const char* e = getenv("MICGPU_K4"); return e && e[0] == 'w'; }();
   if (n <= 0) return 0;
   if (!wave_only && launch_delta_rowscan(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, d->all_aligned, st)) {
     launch_delta_wavefront(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, d->max_h, st, 1);
-    return 2;
+    return 2 + launch_k4_grad(d, du, list, n, d_out, st);
   }
   launch_delta_wavefront(du, list, n, (const uint16_t*)d->d_D.p, (const uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_w, d->max_h, st, 0);
-  return 1;
+  return 1 + launch_k4_grad(d, du, list, n, d_out, st);
 }
 
 int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, void* d_out, size_t out_elems, cudaStream_t st) {
@@ -511,6 +521,53 @@ int add_pics_locked(micgpu_decoder* d, const uint8_t* pics, size_t len, uint64_t
   const unsigned long long covered = std::min<unsigned long long>((unsigned long long)ph.nstrips * ph.strip_h, (unsigned long long)ph.h);
   if (covered < (unsigned long long)ph.h)
     d->zero_ranges.push_back({out_off + covered * ph.w, ((unsigned long long)ph.h - covered) * ph.w});
+  d->out_need = std::max<unsigned long long>(d->out_need, out_off + (unsigned long long)ph.w * ph.h);
+  if (w) *w = ph.w;
+  if (h) *h = ph.h;
+  return 0;
+}
+
+// PICA (parallelstripsadaptive.go:143-212): "PICA" w h nStrips | nStrips x {y0, offset, length, flags} u32 | blobs.
+// Strip s covers rows [y0_s, y0_{s+1}) (the last one runs to h); flags bit 0 = gradient-adaptive predictor.
+struct PicaHeader {
+  int w, h, nstrips;
+  size_t header_size;
+};
+
+int parse_pica(const uint8_t* p, size_t len, PicaHeader& ph) {
+  if (len < 16 || memcmp(p, "PICA", 4) != 0) return fail(MICGPU_E_HEADER, "pica: invalid magic");
+  ph.w = (int)rd32(p + 4); ph.h = (int)rd32(p + 8); ph.nstrips = (int)rd32(p + 12);
+  if (ph.nstrips < 0 || (size_t)ph.nstrips > (len - 16) / 16) return fail(MICGPU_E_HEADER, "pica: truncated header");
+  if (ph.w <= 0 || ph.h <= 0 || ph.nstrips <= 0) return fail(MICGPU_E_HEADER, "pica: invalid dimensions");
+  ph.header_size = 16 + (size_t)ph.nstrips * 16;
+  return 0;
+}
+
+int add_pica_locked(micgpu_decoder* d, const uint8_t* pica, size_t len, uint64_t comp_off, uint64_t out_off, int* w, int* h) {
+  PicaHeader ph;
+  int rc = parse_pica(pica, len, ph);
+  if (rc) return rc;
+  // validate the whole strip table before any unit is added (a half-populated plan must not survive an error)
+  for (int s = 0; s < ph.nstrips; s++) {
+    const uint8_t* e = pica + 16 + (size_t)s * 16;
+    const uint64_t y0 = rd32(e), so = rd32(e + 4), sl = rd32(e + 8);
+    const uint64_t y1 = s + 1 < ph.nstrips ? (uint64_t)rd32(e + 16) : (uint64_t)ph.h;
+    const uint64_t start = ph.header_size + so, end = start + sl;
+    if (end > len) return fail(MICGPU_E_HEADER, "strip %d: offset out of bounds", s);
+    // the reference slices out[y0*w:] and sizes the strip as y1 - y0 rows: anything else panics there
+    if (y0 >= y1 || y1 > (uint64_t)ph.h) return fail(MICGPU_E_HEADER, "pica: strip %d covers rows [%llu, %llu) of %d", s, (unsigned long long)y0, (unsigned long long)y1, ph.h);
+  }
+  for (int s = 0; s < ph.nstrips; s++) {
+    const uint8_t* e = pica + 16 + (size_t)s * 16;
+    const uint32_t y0 = rd32(e), so = rd32(e + 4), sl = rd32(e + 8), fl = rd32(e + 12);
+    const uint32_t y1 = s + 1 < ph.nstrips ? rd32(e + 16) : (uint32_t)ph.h;
+    const size_t start = ph.header_size + so;
+    const int ui = add_unit_locked(d, pica + start, sl, comp_off + start, MIC_KIND_SPATIAL, (uint32_t)ph.w, y1 - y0, out_off + (uint64_t)y0 * ph.w);
+    d->units[ui].predictor = fl & 1u;
+  }
+  // rows above the first strip stay as make() left them (zero)
+  const uint32_t first_y0 = rd32(pica + 16);
+  if (first_y0 > 0) d->zero_ranges.push_back({out_off, (unsigned long long)first_y0 * ph.w});
   d->out_need = std::max<unsigned long long>(d->out_need, out_off + (unsigned long long)ph.w * ph.h);
   if (w) *w = ph.w;
   if (h) *h = ph.h;
@@ -747,6 +804,13 @@ int micgpu_decoder_add_pics(micgpu_decoder* d, const uint8_t* pics, size_t len, 
   if (!d || !pics) return fail(MICGPU_E_HEADER, "null argument");
   std::lock_guard<std::mutex> lk(d->mu);
   return add_pics_locked(d, pics, len, comp_off, out_off, width, height);
+}
+
+int micgpu_decoder_add_pica(micgpu_decoder* d, const uint8_t* pica, size_t len, uint64_t comp_off, uint64_t out_off,
+                            int* width, int* height) {
+  if (!d || !pica) return fail(MICGPU_E_HEADER, "null argument");
+  std::lock_guard<std::mutex> lk(d->mu);
+  return add_pica_locked(d, pica, len, comp_off, out_off, width, height);
 }
 
 int micgpu_decoder_add_mic2(micgpu_decoder* d, const uint8_t* mic2, size_t len, uint64_t comp_off, uint64_t out_off,
@@ -1146,6 +1210,44 @@ int micgpu_decompress_single_frame(const uint8_t* frame, size_t len, uint16_t* p
   d->zero_ranges.clear();
   d->out_need = 0;
   add_unit_locked(d, frame, len, 0, MIC_KIND_SPATIAL, (uint32_t)width, (uint32_t)height, 0);
+  int rc = plan_commit(d);
+  if (rc) return rc;
+  return run_host_locked(d, frame, len, pixels_out, (size_t)width * height);
+}
+
+// DecompressParallelStripsAdaptive (parallelstripsadaptive.go:143-212)
+int micgpu_pica_decompress(const uint8_t* pica, size_t len, uint16_t* pixels_out, size_t cap_px, int* width, int* height) {
+  if (!pica || !pixels_out) return fail(MICGPU_E_HEADER, "null argument");
+  PicaHeader ph;
+  int rc = parse_pica(pica, len, ph);
+  if (rc) return rc;
+  if (width) *width = ph.w;
+  if (height) *height = ph.h;
+  if ((unsigned long long)ph.w * ph.h > cap_px) return fail(MICGPU_E_SIZE, "output buffer holds %zu pixels, image has %llu", cap_px, (unsigned long long)ph.w * ph.h);
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  d->units.clear();
+  d->temporal.clear();
+  d->zero_ranges.clear();
+  d->out_need = 0;
+  if ((rc = add_pica_locked(d, pica, len, 0, 0, nullptr, nullptr))) return rc;
+  if ((rc = plan_commit(d))) return rc;
+  return run_host_locked(d, pica, len, pixels_out, (size_t)ph.w * ph.h);
+}
+
+// DecompressSingleFrameGrad (multiframecompress.go:129-142)
+int micgpu_decompress_single_frame_grad(const uint8_t* frame, size_t len, uint16_t* pixels_out, int width, int height) {
+  if (!frame || !pixels_out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  d->units.clear();
+  d->temporal.clear();
+  d->zero_ranges.clear();
+  d->out_need = 0;
+  const int ui = add_unit_locked(d, frame, len, 0, MIC_KIND_SPATIAL, (uint32_t)width, (uint32_t)height, 0);
+  d->units[ui].predictor = 1;
   int rc = plan_commit(d);
   if (rc) return rc;
   return run_host_locked(d, frame, len, pixels_out, (size_t)width * height);

@@ -42,6 +42,20 @@ def xr_image(seed: int, w: int = 2577, h: int = 2048) -> np.ndarray:
     return v.astype(np.uint16)
 
 
+def smooth_image(seed: int, w: int, h: int, noisy_from: int | None = None) -> np.ndarray:
+    """12-bit smooth field with changing slopes + noise[0,6): content the gradient-adaptive predictor wins on
+    (deltagradcompressu16.go:149-166).  Rows >= noisy_from (if given) are radiograph rows (xr_image) instead, where avg(top,left) wins,
+    so a PICA container of the image carries both predictor flags."""
+    y = np.arange(h, dtype=np.float64)[:, None]
+    x = np.arange(w, dtype=np.float64)[None, :]
+    v = (2000.0 + 1500.0 * np.sin(x / 23.0 + seed) * np.cos(y / 31.0)).astype(np.int64)
+    v += (np.arange(h, dtype=np.int64)[:, None] * np.arange(w, dtype=np.int64)[None, :]) % 7
+    v += noise(seed, w * h, 6).reshape(h, w)
+    if noisy_from is not None:
+        v[noisy_from:, :] = xr_image(seed + 1, w, 3 * h)[h + noisy_from:2 * h, :]   # middle rows: no top / bottom border
+    return v.astype(np.uint16)
+
+
 def mammo_image(seed: int, rows: int = 4096, cols: int = 3328) -> np.ndarray:
     """Config 3: 14-bit mammogram: breast-shaped mask (~45 % zero background) + smooth field + noise[0,32)."""
     y = np.arange(rows, dtype=np.float64)[:, None] / rows

@@ -359,3 +359,92 @@ def test_oracle_matches_reference_twin_bytes(oracle, reftwin, synth):
             assert a == reftwin.compress(img, w, h, ns)
             assert np.array_equal(reftwin.decompress(a, w, h, ns, simd=True), img)
             assert np.array_equal(reftwin.decompress(a, w, h, ns, simd=False), img)
+
+
+# ---- gradient-adaptive predictor and PICA ----------------------------------------------------------------
+def test_grad_predictor_reference_vector(oracle):
+    # TestGradDeltaCompress (deltagradcompressu16_test.go:12-30): the 3x3 ramp round-trips; the symbols are checked by hand:
+    # row 0 predicts from the left, column 0 from the top, the interior from gradPredict (deltagradcompressu16.go:149-166)
+    px = np.array([100, 110, 120, 105, 115, 125, 110, 120, 130], np.uint16)
+    sym = oracle.grad_delta_rle_compress(px, 3, 3, 8000)
+    thr = (1 << 12) - 1                       # bits.Len16(8000) = 13
+    assert sym[0] == (1 << 13) - 1            # RleCompressU16.Init word: the delimiter (deltagradrlecompressu16.go:30)
+    assert np.array_equal(oracle.grad_delta_rle_decompress(sym, 3, 3), px)
+    # gradPredict(w=105, n=110, nw=100, ne=120): avg 107, g = 5 + 10 = 15, corr = 20 >> 3 = 2 (limit 7) -> 109; 115 - 109 = 6
+    # (1,2): w=115 n=120 nw=110 ne=nw (last column) -> avg 117, corr 0 -> 117; 125 - 117 = 8
+    d = [int(v) - thr for v in _expand_rle(sym)[1:]]
+    assert d == [100, 10, 10, 5, 6, 8, 5, 6, 8]
+
+
+def _expand_rle(sym):
+    """RleDecompressU16.DecodeNext2 over a spatial symbol stream (rledecompressu16.go:59-97), in Python for tiny inputs."""
+    sym = [int(v) for v in sym]
+    depth = sym[0].bit_length()
+    mid = (1 << (depth - 1)) - 1
+    out, i = [], 1
+    while i < len(sym):
+        c = sym[i]
+        if c <= mid:
+            out += [sym[i + 1]] * c
+            i += 2
+        else:
+            n = c - mid
+            out += sym[i + 1:i + 1 + n]
+            i += 1 + n
+    return out
+
+
+@pytest.mark.parametrize("name,w,h,avg,grad,pics4,pica4,ngrad", [
+    # docs/adaptive-compression.md:32-33,74-75 (published ratios; the MR rows of that table are 0.2 % below what the
+    # reference encoder's byte counts give here for BOTH predictors, the CT rows match to the last digit)
+    ("MR_256_256", 256, 256, 2.348, 2.374, 2.284, 2.309, 3),
+    ("CT_512_512", 512, 512, 2.237, 2.182, 2.145, 2.112, 0),
+])
+def test_grad_and_pica_published_ratios(oracle, name, w, h, avg, grad, pics4, pica4, ngrad):
+    px = np.fromfile(os.path.join(GOLDEN, f"{name}_image.bin"), dtype="<u2")
+    mx, raw = int(px.max()), w * h * 2
+    g = oracle.compress_single_frame_grad(px, w, h, mx)
+    a = oracle.compress_single_frame(px, w, h, mx, 2)
+    assert np.array_equal(oracle.decompress_single_frame_grad(g, w, h), px)
+    assert abs(raw / len(a) - avg) < 0.006 and abs(raw / len(g) - grad) < 0.006
+    pica = oracle.pica_compress(px, w, h, mx, 4)
+    pics = oracle.pics_compress(px, w, h, mx, 4, 2)
+    assert abs(raw / len(pics) - pics4) < 0.0006 and abs(raw / len(pica) - pica4) < 0.0006
+    n = int.from_bytes(pica[12:16], "little")
+    flags = [int.from_bytes(pica[28 + 16 * i:32 + 16 * i], "little") for i in range(n)]
+    assert n == 4 and sum(flags) == ngrad          # "Grad strips" column of the same table
+    got, gw, gh = oracle.pica_decompress(pica)
+    assert (gw, gh) == (w, h) and np.array_equal(got, px)
+
+
+def test_pica_layout_and_boundaries(oracle, synth):
+    img = synth.smooth_image(9, 320, 200, noisy_from=120)
+    px, mx = img.ravel(), int(img.max())
+    blob = oracle.pica_compress(px, 320, 200, mx, 3)
+    assert blob[:4] == b"PICA" and [int.from_bytes(blob[4 + 4 * i:8 + 4 * i], "little") for i in range(3)] == [320, 200, 3]
+    starts = oracle.pica_boundaries(px, 320, 200, 3)
+    ent = [[int.from_bytes(blob[16 + 16 * s + 4 * k:20 + 16 * s + 4 * k], "little") for k in range(4)] for s in range(3)]
+    assert [e[0] for e in ent] == starts and starts[0] == 0 and starts == sorted(starts)
+    off = 0
+    for s, (y0, o, ln, fl) in enumerate(ent):     # offsets are running sums, every strip decodes on its own
+        assert o == off and fl in (0, 1)
+        off += ln
+        y1 = ent[s + 1][0] if s + 1 < 3 else 200
+        frame = blob[16 + 48 + o:16 + 48 + o + ln]
+        dec = oracle.decompress_single_frame_grad(frame, 320, y1 - y0) if fl else oracle.decompress_single_frame(frame, 320, y1 - y0)
+        assert np.array_equal(dec, px[y0 * 320:y1 * 320])
+        # the kept frame is the smaller of the two (the gradient one on a tie), parallelstripsadaptive.go:98-107
+        a = oracle.compress_single_frame(px[y0 * 320:y1 * 320], 320, y1 - y0, mx, 2)
+        g = oracle.compress_single_frame_grad(px[y0 * 320:y1 * 320], 320, y1 - y0, mx)
+        assert frame == (g if len(g) <= len(a) else a) and fl == int(len(g) <= len(a))
+    assert len(blob) == 16 + 48 + off
+    # clamps and degenerate partitions (parallelstripsadaptive.go:62-70,215-224,243-251)
+    assert oracle.pica_boundaries(px, 320, 200, 1) == [0]
+    assert oracle.pica_boundaries(px, 320, 200, 500) == list(range(200))
+    flat = np.full(64 * 40, 777, np.uint16)
+    assert oracle.pica_boundaries(flat, 64, 40, 4) == [0, 10, 20, 30]   # total cost 0 -> equal heights
+    got, w, h = oracle.pica_decompress(blob)
+    assert (w, h) == (320, 200) and np.array_equal(got, px)
+    for bad in (b"PICS" + blob[4:], blob[:15], blob[:12] + (0).to_bytes(4, "little") + blob[16:], blob[:40]):
+        with pytest.raises(Exception):
+            oracle.pica_decompress(bad)

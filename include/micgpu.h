@@ -174,6 +174,24 @@ int micgpu_wsi_decompress_tiles(const uint8_t *mic3, size_t len, int n, const in
 /* DecompressWSIRegion (wsicompress.go:220-296) */
 int micgpu_wsi_decompress_region(const uint8_t *mic3, size_t len, int level, int x, int y, int w, int h, uint8_t *out, size_t cap,
                                  int *out_w, int *out_h);
+/* ---- region / viewport serving from a resident slide (DecompressWSIRegion wsicompress.go:220-296) -------
+ * micgpu_wsi_open validates the header, the level descriptors and the tile table once and keeps the tile data area in
+ * device memory; every later call parses nothing but the blob headers of the tiles it touches.  A batch of rectangles
+ * -- any mix of pyramid levels -- is ONE launch sequence: the union of the touched tiles is decoded once, cropped and
+ * composed on the device, and only the requested pixels are copied out.  Rectangles are clamped to their level exactly
+ * like DecompressWSIRegion; out_ws / out_hs receive the clamped sizes.  The caller's mic3 buffer may be released after
+ * micgpu_wsi_open returns.  Calls on one handle are serialised; use one handle per device for multi-GPU serving. */
+typedef struct micgpu_wsi_slide micgpu_wsi_slide;
+micgpu_wsi_slide *micgpu_wsi_open(int device, const uint8_t *mic3, size_t len);
+void micgpu_wsi_close(micgpu_wsi_slide *s);
+int micgpu_wsi_slide_info(const micgpu_wsi_slide *s, micgpu_wsi_info *info);
+int micgpu_wsi_slide_region(micgpu_wsi_slide *s, int level, int x, int y, int w, int h, uint8_t *out, size_t cap, int *out_w, int *out_h);
+int micgpu_wsi_slide_regions(micgpu_wsi_slide *s, int n, const int *levels, const int *xs, const int *ys, const int *ws, const int *hs,
+                             uint8_t *const *outs, const size_t *caps, int *out_ws, int *out_hs, int *status);
+/* the same with DEVICE output pointers (pixels stay on the GPU for a renderer) */
+int micgpu_wsi_slide_regions_device(micgpu_wsi_slide *s, int n, const int *levels, const int *xs, const int *ys, const int *ws,
+                                    const int *hs, void *const *d_outs, const size_t *caps, int *out_ws, int *out_hs, int *status);
+int micgpu_wsi_slide_stats(const micgpu_wsi_slide *s, uint64_t *requests, uint64_t *tiles_decoded, int *last_launches);
 /* ---- tile ranges: plan once, run many (viewer / batch conversion path) ------------------------------------------
  * Tiles [first_tile, first_tile + n_tiles) of the container's tile table (level l starts at first_tile[l], row-major:
  * wsiformat.go:145-155), each decoded as a FULL tile_w x tile_h block of pixels, tile_bytes apart (edge tiles keep the

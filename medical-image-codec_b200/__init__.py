@@ -37,6 +37,7 @@ from .api import (  # noqa: F401
     DecompressWSITiles,
     DecompressWSITileRange,
     WsiPlan,
+    WsiSlide,
     Init,
     WriteMIC1,
     WriteMICR,

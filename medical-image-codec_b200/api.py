@@ -77,6 +77,12 @@ lib.micgpu_decoder_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_
 lib.micgpu_pics_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_pics_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip]
 lib.micgpu_decompress_single_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+lib.micgpu_wsi_open.restype = C.c_void_p
+lib.micgpu_wsi_open.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+lib.micgpu_wsi_close.argtypes = [C.c_void_p]
+lib.micgpu_wsi_slide_regions.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _ip, _ip, _ip, C.c_void_p, C.c_void_p, _ip, _ip, _ip]
+lib.micgpu_wsi_slide_regions_device.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _ip, _ip, _ip, C.c_void_p, C.c_void_p, _ip, _ip, _ip]
+lib.micgpu_wsi_slide_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _ip]
 lib.micgpu_decompress_single_frame_grad.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
 lib.micgpu_pica_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_decoder_add_pica.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, _ip, _ip]
@@ -363,6 +369,52 @@ def DecompressWSITileRange(data, first_tile: int, n_tiles: int):
     st = (C.c_int * max(n_tiles, 1))()
     _check(lib.micgpu_wsi_decompress_tile_range(a.ctypes.data, a.size, C.c_uint64(first_tile), C.c_uint64(n_tiles), out.ctypes.data, out.size, st))
     return out[: n_tiles * tile_bytes].reshape(n_tiles, tile_bytes)
+
+
+class WsiSlide:
+    """micgpu_wsi_open / micgpu_wsi_slide_regions: a slide resident in device memory, headers parsed once; serves batches
+    of rectangles from any pyramid levels (the DecompressWSIRegion call of a viewer, wsicompress.go:220)."""
+
+    def __init__(self, data, device: int = 0):
+        a = _bytes_view(data)
+        self.p = lib.micgpu_wsi_open(device, a.ctypes.data, a.size)
+        if not self.p:
+            raise MicGpuError(-1, last_error())
+        self.header = ReadWSIHeader(a)
+        self.bpp = _wsi_bpp(self.header)
+
+    def close(self):
+        if self.p:
+            lib.micgpu_wsi_close(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def regions(self, rects, raise_on_error: bool = True):
+        """rects: list of (level, x, y, w, h) -> list of (uint8 array, width, height, status)."""
+        n = len(rects)
+        outs = [np.empty(max(r[3], 1) * max(r[4], 1) * self.bpp, np.uint8) for r in rects]
+        col = lambda k: (C.c_int * n)(*[int(r[k]) for r in rects])
+        op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        cp = (C.c_size_t * n)(*[o.size for o in outs])
+        ow, oh, st = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)()
+        rc = lib.micgpu_wsi_slide_regions(self.p, n, col(0), col(1), col(2), col(3), col(4), op, cp, ow, oh, st)
+        if rc and raise_on_error:
+            raise MicGpuError(rc, last_error())
+        return [(outs[i][: ow[i] * oh[i] * self.bpp], ow[i], oh[i], st[i]) for i in range(n)]
+
+    def region(self, level: int, x: int, y: int, w: int, h: int):
+        px, ow, oh, _ = self.regions([(level, x, y, w, h)])[0]
+        return px, ow, oh
+
+    def stats(self):
+        rq, td, ll = C.c_uint64(), C.c_uint64(), C.c_int()
+        _check(lib.micgpu_wsi_slide_stats(self.p, C.byref(rq), C.byref(td), C.byref(ll)))
+        return {"requests": rq.value, "tiles_decoded": td.value, "last_launches": ll.value}
 
 
 class WsiPlan:

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "host_common.h"
@@ -1905,6 +1906,178 @@ int micgpu_wsi_plan_kernel_times(micgpu_wsi_plan* p, int on, char* names, size_t
   if (!p) return fail(MICGPU_E_HEADER, "null plan");
   if (on >= 0) return micgpu_decoder_set_profiling(p->dec, on);
   return micgpu_decoder_kernel_times(p->dec, names, names_cap, ms, cap);
+}
+
+}  // extern "C"
+
+// ---- MIC3 region / viewport serving: the slide stays resident, headers are parsed once ----------------
+// DecompressWSIRegion (wsicompress.go:220-296) re-reads the header and re-extracts blobs on every call; a viewer asks for
+// many small rectangles of one slide, often from several pyramid levels at once.  A slide handle validates the header,
+// the level descriptors and the tile table ONCE, keeps the tile data area in device memory (a 100000 x 80000 slide is a
+// few GB of the 180 GB), and serves a batch of rectangles -- any levels -- as one launch sequence: the union of the
+// tiles they touch is decoded once (a tile shared by two rectangles is one unit set with two blit jobs), cropped and
+// composed on the device, and only the requested pixels travel back.
+struct micgpu_wsi_slide {
+  micgpu_decoder* dec = nullptr;
+  std::vector<uint8_t> file;       // private host copy: tile blob headers (plane lengths, modes, FSE framing) are read per request
+  Mic3Header h;
+  std::vector<Mic3Level> levels;
+  DevBuf d_data;                   // file[data_off .. len) (+256 readable bytes)
+  uint64_t requests = 0, tiles_decoded = 0;
+  ~micgpu_wsi_slide() {
+    if (dec) { cudaSetDevice(dec->device); d_data.release(); delete dec; }
+  }
+};
+
+extern "C" {
+
+micgpu_wsi_slide* micgpu_wsi_open(int device, const uint8_t* mic3, size_t len) {
+  if (!mic3) { fail(MICGPU_E_HEADER, "null argument"); return nullptr; }
+  Mic3Header h;
+  if (parse_mic3(mic3, len, h)) return nullptr;
+  micgpu_decoder* d = micgpu_decoder_create(device);
+  if (!d) return nullptr;
+  micgpu_wsi_slide* S = new micgpu_wsi_slide();
+  S->dec = d;
+  S->h = h;
+  S->file.assign(mic3, mic3 + len);
+  for (int l = 0; l < h.nlv; l++) S->levels.push_back(mic3_level(mic3, h, l));
+  const size_t dbytes = len - h.data_off;
+  if (S->d_data.ensure(dbytes + 256) ||
+      cudaMemcpyAsync(S->d_data.p, mic3 + h.data_off, dbytes, cudaMemcpyHostToDevice, d->stream) != cudaSuccess ||
+      cudaMemsetAsync((uint8_t*)S->d_data.p + dbytes, 0, 256, d->stream) != cudaSuccess || cudaStreamSynchronize(d->stream) != cudaSuccess) {
+    fail(MICGPU_E_CUDA, "MIC3: could not place %zu bytes of tile data in device memory", dbytes);
+    delete S;
+    return nullptr;
+  }
+  return S;
+}
+
+void micgpu_wsi_close(micgpu_wsi_slide* s) { delete s; }
+
+int micgpu_wsi_slide_info(const micgpu_wsi_slide* s, micgpu_wsi_info* info) {
+  if (!s || !info) return fail(MICGPU_E_HEADER, "null argument");
+  return micgpu_wsi_read_header(s->file.data(), s->file.size(), info);
+}
+
+// n rectangles (level, x, y, w, h), clamped to their level like DecompressWSIRegion; outs[i] receives out_ws[i] x
+// out_hs[i] pixels, row-major, bytes_per_pixel each.  status[i] (optional) is the per-rectangle result; the return value
+// is the first failure.  d_outs != NULL: outs[] are DEVICE pointers (a renderer that keeps pixels on the GPU).
+static int slide_regions(micgpu_wsi_slide* S, int n, const int* levels, const int* xs, const int* ys, const int* ws, const int* hs,
+                         uint8_t* const* outs, const size_t* caps, int* out_ws, int* out_hs, int* status, bool device_out) {
+  if (!S || n < 0 || (n && (!levels || !xs || !ys || !ws || !hs || !outs || !caps))) return fail(MICGPU_E_HEADER, "bad argument");
+  if (n == 0) return 0;
+  micgpu_decoder* d = S->dec;
+  std::lock_guard<std::mutex> lk(d->mu);
+  const Mic3Header& hd = S->h;
+  const uint8_t* file = S->file.data();
+  const size_t flen = S->file.size();
+  const int bpp = bytes_per_pixel(hd.channels, hd.bps);
+  std::vector<TileReq> tiles;
+  std::vector<std::vector<int>> region_tiles(n);
+  std::unordered_map<uint64_t, int> tile_of;       // tile table index -> entry of `tiles`
+  std::vector<int> rst(n, 0), rw(n, 0), rh(n, 0);
+  std::vector<size_t> ooff(n, 0);
+  size_t otot = 0;
+  for (int i = 0; i < n; i++) {
+    const int level = levels[i], x = xs[i], y = ys[i];
+    int w = ws[i], h = hs[i];
+    if (level < 0 || level >= hd.nlv) { rst[i] = fail(MICGPU_E_HEADER, "MIC3: level %d out of range [0, %d)", level, hd.nlv); continue; }
+    const Mic3Level& lv = S->levels[level];
+    if (x < 0 || y < 0) { rst[i] = fail(MICGPU_E_HEADER, "MIC3: negative region origin"); continue; }
+    if ((long long)x + w > lv.w) w = (int)std::max<long long>(0, (long long)lv.w - x);
+    if ((long long)y + h > lv.h) h = (int)std::max<long long>(0, (long long)lv.h - y);
+    if (w <= 0 || h <= 0) { rst[i] = fail(MICGPU_E_HEADER, "MIC3: empty region"); continue; }
+    if ((size_t)w * h * bpp > caps[i]) { rst[i] = fail(MICGPU_E_SIZE, "region %d: output buffer too small", i); continue; }
+    rw[i] = w; rh[i] = h;
+    ooff[i] = otot;
+    const int stx = x / hd.tile_w, sty = y / hd.tile_h, etx = (x + w - 1) / hd.tile_w, ety = (y + h - 1) / hd.tile_h;
+    for (int ty = sty; ty <= ety && !rst[i]; ty++)
+      for (int tx = stx; tx <= etx; tx++) {
+        const uint64_t idx = (uint64_t)lv.first + (uint64_t)ty * lv.tx + tx;
+        auto it = tile_of.find(idx);
+        int ti;
+        if (it == tile_of.end()) {
+          TileReq T;
+          T.tile_w = hd.tile_w; T.tile_h = hd.tile_h; T.channels = hd.channels; T.bps = hd.bps; T.ct = hd.ct;
+          T.blob = file; T.len = 0;
+          if ((T.status = mic3_tile_blob(file, flen, hd, (long long)idx, &T.blob, &T.len)) == 0)
+            T.comp_off = (uint64_t)(T.blob - file) - hd.data_off;
+          ti = (int)tiles.size();
+          tiles.push_back(std::move(T));
+          tile_of.emplace(idx, ti);
+        } else {
+          ti = it->second;
+        }
+        region_tiles[i].push_back(ti);
+        const int tsx = tx * hd.tile_w, tsy = ty * hd.tile_h;
+        const int tw = std::min(hd.tile_w, lv.w - tsx), th = std::min(hd.tile_h, lv.h - tsy);
+        const int ox0 = std::max(x, tsx), oy0 = std::max(y, tsy), ox1 = std::min(x + w, tsx + tw), oy1 = std::min(y + h, tsy + th);
+        if (ox1 > ox0 && oy1 > oy0)
+          tiles[ti].blits.push_back(Blit{(unsigned)(ox0 - tsx), (unsigned)(oy0 - tsy), (unsigned)(ox1 - ox0), (unsigned)(oy1 - oy0),
+                                         otot + ((unsigned long long)(oy0 - y) * w + (ox0 - x)) * bpp, (unsigned)(w * bpp)});
+      }
+    otot += ((size_t)w * h * bpp + 15) & ~(size_t)15;
+  }
+  int rc = 0;
+  if (!tiles.empty()) {
+    WsiWork W;
+    wsi_build(d, tiles, otot, W);
+    if ((rc = plan_commit(d))) return rc;
+    CUDA_TRY(cudaSetDevice(d->device));
+    if ((rc = d->d_out.ensure(std::max<uint64_t>(W.ptot, 1) * sizeof(uint16_t)))) return rc;
+    if ((rc = d->d_bytes.ensure(std::max<size_t>(otot, 1)))) return rc;
+    cudaStream_t st = d->stream;
+    if ((rc = wsi_upload_jobs(d, W, st))) return rc;
+    if ((rc = wsi_launch(d, W, S->d_data.p, flen - hd.data_off, d->d_out.p, d->d_bytes.p, st))) { cudaStreamSynchronize(st); return rc; }
+    std::vector<int> ust(d->units.size());
+    unit_status_locked(d, ust.data(), (int)ust.size(), st);    // synchronises
+    for (auto& ut : W.unit_tile)
+      if (ust[ut.first] && !tiles[ut.second].status) tiles[ut.second].status = ust[ut.first];
+    S->tiles_decoded += tiles.size();
+  }
+  S->requests += (uint64_t)n;
+  int first = 0;
+  for (int i = 0; i < n; i++) {
+    for (int ti : region_tiles[i])
+      if (!rst[i] && tiles[ti].status) rst[i] = tiles[ti].status;
+    if (!rst[i]) {
+      const size_t nb = (size_t)rw[i] * rh[i] * bpp;
+      if (cudaMemcpyAsync(outs[i], (uint8_t*)d->d_bytes.p + ooff[i], nb, device_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, d->stream) != cudaSuccess)
+        rst[i] = fail(MICGPU_E_CUDA, "copy of region %d failed", i);
+    }
+    if (out_ws) out_ws[i] = rst[i] ? 0 : rw[i];
+    if (out_hs) out_hs[i] = rst[i] ? 0 : rh[i];
+    if (status) status[i] = rst[i];
+    if (!first && rst[i]) first = rst[i];
+  }
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  if (first) fail(first, "MIC3: a region of the batch failed (status %d)", first);
+  return first;
+}
+
+int micgpu_wsi_slide_regions(micgpu_wsi_slide* s, int n, const int* levels, const int* xs, const int* ys, const int* ws, const int* hs,
+                             uint8_t* const* outs, const size_t* caps, int* out_ws, int* out_hs, int* status) {
+  return slide_regions(s, n, levels, xs, ys, ws, hs, outs, caps, out_ws, out_hs, status, false);
+}
+
+int micgpu_wsi_slide_regions_device(micgpu_wsi_slide* s, int n, const int* levels, const int* xs, const int* ys, const int* ws,
+                                    const int* hs, void* const* d_outs, const size_t* caps, int* out_ws, int* out_hs, int* status) {
+  return slide_regions(s, n, levels, xs, ys, ws, hs, (uint8_t* const*)d_outs, caps, out_ws, out_hs, status, true);
+}
+
+int micgpu_wsi_slide_region(micgpu_wsi_slide* s, int level, int x, int y, int w, int h, uint8_t* out, size_t cap, int* out_w, int* out_h) {
+  int st = 0;
+  return slide_regions(s, 1, &level, &x, &y, &w, &h, &out, &cap, out_w, out_h, &st, false);
+}
+
+// counters of a handle: rectangles served, tiles decoded (after sharing), kernels of the last batch
+int micgpu_wsi_slide_stats(const micgpu_wsi_slide* s, uint64_t* requests, uint64_t* tiles_decoded, int* last_launches) {
+  if (!s) return fail(MICGPU_E_HEADER, "null slide");
+  if (requests) *requests = s->requests;
+  if (tiles_decoded) *tiles_decoded = s->tiles_decoded;
+  if (last_launches) *last_launches = s->dec->launches;
+  return 0;
 }
 
 }  // extern "C"

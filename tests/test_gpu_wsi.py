@@ -158,3 +158,74 @@ def test_tile_range_reports_the_damaged_tile(mic, oracle, slide):
     for i in range(n):
         if i != 4:
             assert st[i] == 0 and np.array_equal(out[i * tile_bytes:(i + 1) * tile_bytes], good[i]), i
+
+
+# ---- region / viewport serving from a resident slide ------------------------------------------------------
+def test_slide_viewport_batches(mic, oracle, slide):
+    """One handle, headers parsed once, the caller's buffer released; batches of rectangles across pyramid levels equal
+    DecompressWSIRegion of the oracle (wsicompress.go:220-296) rectangle by rectangle, clamping included."""
+    rgb, blob = slide
+    buf = bytearray(blob)
+    s = mic.WsiSlide(buf)
+    for i in range(len(buf)):           # the handle keeps what it needs: scribble over the caller's copy
+        buf[i] = 0xAA
+    hdr = s.header
+    rects = [(0, 0, 0, 700, 533),                    # the whole level
+             (0, 250, 250, 20, 20),                  # corner shared by four tiles
+             (0, 255, 100, 2, 300),                  # a two-pixel column across a tile seam
+             (0, 600, 500, 400, 400),                # clamped on both axes
+             (0, 699, 532, 1, 1)]                    # the last pixel
+    for l, (w, h, _, _, _) in enumerate(hdr["Levels"][1:], start=1):
+        rects += [(l, 0, 0, w, h), (l, w // 3, h // 4, max(1, w // 2), max(1, h // 2))]
+    before = s.stats()
+    got = s.regions(rects)
+    after = s.stats()
+    assert after["requests"] - before["requests"] == len(rects)
+    # the five level-0 rectangles share the level's nine tiles: every tile is decoded once per batch
+    ntiles_all = sum(tx * ty for (_, _, tx, ty, _) in hdr["Levels"])
+    assert after["tiles_decoded"] - before["tiles_decoded"] <= ntiles_all
+    for r, (px, w, h, st) in zip(rects, got):
+        ref, rw, rh = oracle.wsi_decompress_region(blob, *r)
+        assert st == 0 and (w, h) == (rw, rh) and np.array_equal(px, ref), r
+    full = got[0][0].reshape(533, 700, 3)
+    assert np.array_equal(full, rgb)
+    # single-rectangle call, repeated: same bytes every time (scratch is recycled between requests)
+    for _ in range(3):
+        px, w, h = s.region(0, 100, 90, 333, 222)
+        assert (w, h) == (333, 222) and np.array_equal(px.reshape(h, w, 3), rgb[90:312, 100:433])
+    s.close()
+
+
+def test_slide_bad_requests_do_not_poison_the_batch(mic, oracle, slide):
+    rgb, blob = slide
+    s = mic.WsiSlide(blob)
+    rects = [(0, 10, 10, 50, 40), (7, 0, 0, 5, 5), (0, -1, 0, 5, 5), (0, 700, 0, 5, 5), (0, 0, 0, 0, 9), (1, 3, 2, 40, 30)]
+    res = s.regions(rects, raise_on_error=False)
+    assert [r[3] == 0 for r in res] == [True, False, False, False, False, True]
+    for r, (px, w, h, st) in zip(rects, res):
+        if st == 0:
+            ref, rw, rh = oracle.wsi_decompress_region(blob, *r)
+            assert (w, h) == (rw, rh) and np.array_equal(px, ref)
+        else:
+            assert (w, h) == (0, 0)
+    with pytest.raises(mic.MicGpuError):
+        s.regions(rects)
+    s.close()
+    # a damaged tile fails the rectangles that touch it and only those
+    hdr = mic.ReadWSIHeader(blob)
+    n_tiles = hdr["TotalTiles"]
+    table = 48 + 20 * len(hdr["Levels"])
+    data = table + 16 * n_tiles
+    off4 = int.from_bytes(blob[table + 16 * 4:table + 16 * 4 + 8], "little")      # tile (1,1) of level 0
+    dmg = bytearray(blob)
+    for k in range(40, 60):
+        dmg[data + off4 + k] ^= 0x5A
+    s = mic.WsiSlide(bytes(dmg))
+    res = s.regions([(0, 0, 0, 200, 200), (0, 300, 300, 100, 100), (0, 520, 10, 100, 100)], raise_on_error=False)
+    assert res[0][3] == 0 and res[2][3] == 0
+    assert np.array_equal(res[0][0].reshape(200, 200, 3), rgb[:200, :200])
+    if res[1][3] == 0:      # the damage may decode to wrong pixels without tripping a check (Go behaves the same way)
+        assert not np.array_equal(res[1][0].reshape(100, 100, 3), rgb[300:400, 300:400])
+    s.close()
+    with pytest.raises(mic.MicGpuError):
+        mic.WsiSlide(b"MIC3" + bytes(blob[4:40]))

@@ -25,22 +25,28 @@
 //     marker/compaction passes (they rewrite the same D range);
 //   * units are handed out through an atomic queue: CTAs are resident five per SM, a static stride left the last
 //     wave half empty.
+#include <algorithm>
+#include <cstdlib>
+
 #include "mic_device.cuh"
 
 namespace micgpu {
 
-constexpr int K3_THREADS = 256;
-constexpr int K3_WARPS = K3_THREADS / 32;
-// Chunk size: every chunk costs ~6 CTA barriers around short phases, so bigger chunks mean fewer barrier stalls per symbol
-// (measured: 47 % issue utilisation at 4096 with most stall samples on the barriers); 8192 still leaves 4 CTAs per SM.
-#ifndef MICGPU_K3_CHUNK
-#define MICGPU_K3_CHUNK 4096
-#endif
-constexpr int IN_N = MICGPU_K3_CHUNK;
-constexpr int OUT_CH = MICGPU_K3_CHUNK;
-constexpr int NWIN = OUT_CH / 32;
-constexpr int WPL = NWIN / 32;   // 32-element windows per lane in the single-warp scans
-constexpr int MAXR = OUT_CH / 16;   // runs per chunk
+// Launch shapes.  Every chunk costs ~6 CTA barriers around short phases and the header walk is one warp's serial work,
+// so the trade is: bigger chunks = fewer barrier stalls per symbol, smaller CTAs = more walkers and more CTAs to overlap
+// on one SM.  <256, 4096> (5 CTAs/SM) serves the strips; the smaller shapes are for run-heavy planes (MIC3 8-bit tiles,
+// residual frames), where 7 of 8 warps wait for the walker (profiles/README.md).  MICGPU_K3_SHAPE picks one for A/B runs.
+template <int THREADS, int CHUNK>
+struct K3Shape {
+  static constexpr int K3_THREADS = THREADS;
+  static constexpr int K3_WARPS = THREADS / 32;
+  static constexpr int IN_N = CHUNK;
+  static constexpr int OUT_CH = CHUNK;
+  static constexpr int NWIN = CHUNK / 32;
+  static constexpr int WPL = (NWIN + 31) / 32;   // 32-element windows per lane in the single-warp scans
+  static constexpr int MAXR = CHUNK / 16;        // runs per chunk
+  static constexpr int MINB = (THREADS * 48 * 5 <= 65536 && CHUNK <= 4096) ? (65536 / (THREADS * 48) > 16 ? 16 : 65536 / (THREADS * 48)) : 4;
+};
 
 struct WalkState {
   int ipos;        // next input symbol to parse
@@ -53,10 +59,14 @@ struct WalkState {
   int done, err;
 };
 
-__global__ void __launch_bounds__(K3_THREADS, MICGPU_K3_CHUNK > 4096 ? 4 : (MICGPU_K3_CHUNK < 4096 ? 6 : 5))
+template <int THREADS, int CHUNK>
+__global__ void __launch_bounds__(THREADS, K3Shape<THREADS, CHUNK>::MINB)
 k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict__ states,
              const uint16_t* __restrict__ tabS, uint16_t* __restrict__ D, uint32_t* __restrict__ M,
              uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue, int ubase) {
+  using SH = K3Shape<THREADS, CHUNK>;
+  constexpr int K3_THREADS = SH::K3_THREADS, K3_WARPS = SH::K3_WARPS, IN_N = SH::IN_N, OUT_CH = SH::OUT_CH, NWIN = SH::NWIN,
+                WPL = SH::WPL, MAXR = SH::MAXR;
   __shared__ __align__(16) uint16_t s_in[IN_N];
   __shared__ __align__(16) uint16_t s_e_raw[OUT_CH + 16];
   // the compaction buffer of the exact (slow) path shares s_in: that path is rare and forces the window to be restaged
@@ -567,16 +577,31 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
   }
 }
 
+template <int THREADS, int CHUNK>
+static void launch_rle_expand_t(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS, uint16_t* d_D,
+                                uint32_t* d_M, uint16_t* d_out, int tab_log, int grid, unsigned int* d_queue, cudaStream_t st) {
+  const size_t smem = (size_t)2 << tab_log;
+  cudaFuncSetAttribute(k_rle_expand<THREADS, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_rle_expand<THREADS, CHUNK><<<grid, THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue, ubase);
+}
+
 void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
                        uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, unsigned int* d_queue,
-                       cudaStream_t st) {
+                       cudaStream_t st, int shape) {
   if (nunits <= 0) return;
   cudaMemsetAsync(d_queue, 0, sizeof(unsigned int), st);
   // stage tabS in shared memory up to tableLog 14 (32 KB); larger tables are gathered through L1/L2
   const int tab_log = max_log <= 14 ? max_log : 14;
-  const size_t smem = (size_t)2 << tab_log;
-  cudaFuncSetAttribute(k_rle_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_rle_expand<<<grid, K3_THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue, ubase);
+  static const int forced = [] { const char* e = getenv("MICGPU_K3_SHAPE"); return e ? atoi(e) : -1; }();
+  if (forced >= 0) shape = forced;
+  // the grid the caller sized is per 256-thread CTA (8 per SM at most); smaller CTAs come in proportionally larger numbers
+  switch (shape) {
+    case 1: launch_rle_expand_t<128, 4096>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 2), d_queue, st); break;
+    case 2: launch_rle_expand_t<128, 2048>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 2), d_queue, st); break;
+    case 3: launch_rle_expand_t<64, 2048>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 4), d_queue, st); break;
+    case 4: launch_rle_expand_t<64, 1024>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 4), d_queue, st); break;
+    default: launch_rle_expand_t<256, 4096>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, grid, d_queue, st); break;
+  }
 }
 
 }  // namespace micgpu

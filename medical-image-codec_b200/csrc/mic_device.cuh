@@ -44,7 +44,7 @@ size_t ans_serial_smem_bytes(int max_log, int mode, int slots);
 // Units [ubase, ubase + nunits) are handed to the CTAs through the atomic counter *d_queue (reset by the launcher).
 void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
                        uint16_t* d_D, uint32_t* d_M, uint16_t* d_out, int max_log, int grid, unsigned int* d_queue,
-                       cudaStream_t st);
+                       cudaStream_t st, int shape = 0);
 
 // Inverse avg(top,left) predictor as an anti-diagonal wavefront; one CTA per spatial unit.
 void launch_delta_wavefront(MicUnit* d_units, const int* d_list, int nlist, const uint16_t* d_D, const uint32_t* d_M,

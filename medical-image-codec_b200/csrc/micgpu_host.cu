@@ -408,12 +408,16 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
     }
     loff += n;
   }
+  // K3 launch shape (k_rle.cu): small tables mean 8-bit planes (MIC3 tiles), whose run headers come every <= 124 symbols:
+  // the header walk of one warp is the bound there, and CTAs of 128 threads / 2048-element chunks put 2.4x the walkers
+  // on an SM (measured on 4096 tiles: K3 1.86 -> 1.45 ms; strips lose 10 % with it, profiles/README.md)
+  const int k3_shape = d->max_log_all <= 12 ? 2 : 0;
   static const int parts_cfg = [] { const char* e = getenv("MICGPU_PARTS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > micgpu_decoder::PARTS ? micgpu_decoder::PARTS : v); }();
   const int parts = (d->profiling || nu < 256) ? 1 : parts_cfg;   // per-kernel timing needs one stream
   if (parts == 1) {
     prof_mark(d, "k_rle_expand", st);
     launch_rle_expand(du, 0, nu, (const uint16_t*)d->d_states.p, (const uint16_t*)d->d_tabS.p, (uint16_t*)d->d_D.p,
-                      (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(nu, d->sm_count * 8), (unsigned int*)d->d_queue.p, st);
+                      (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(nu, d->sm_count * 8), (unsigned int*)d->d_queue.p, st, k3_shape);
     d->launches++;
     if (!d->spatial.empty()) {
       prof_mark(d, "k_delta_rowscan", st);
@@ -434,7 +438,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
       CUDA_TRY(cudaStreamWaitEvent(ps, d->ev_fork, 0));
       launch_rle_expand(du, u0, u1 - u0, (const uint16_t*)d->d_states.p, (const uint16_t*)d->d_tabS.p, (uint16_t*)d->d_D.p,
                         (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(u1 - u0, d->sm_count * 8),
-                        (unsigned int*)d->d_queue.p + p, ps);
+                        (unsigned int*)d->d_queue.p + p, ps, k3_shape);
       d->launches++;
       // the spatial list is sorted by unit index: this range's units are one contiguous slice of it
       const int s0 = (int)(std::lower_bound(d->spatial.begin(), d->spatial.end(), u0) - d->spatial.begin());

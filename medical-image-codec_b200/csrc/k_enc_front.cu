@@ -175,14 +175,70 @@ __device__ __forceinline__ void seg_locate_enc(const WaveletGeom& G, unsigned k,
   *x = G.seg_x0[s] + (r - ry * w);
 }
 
-// collectSubbandOrder + waveletCoeffsToU16 (waveletfsecompressu16.go:28-41,202-241): one CTA per image, chunked;
-// a coefficient beyond +-32767 becomes the triple 65535, hi16, lo16, so positions come from a block scan.
+// collectSubbandOrder + waveletCoeffsToU16 (waveletfsecompressu16.go:28-41,202-241).  A coefficient beyond +-32767 becomes
+// the triple 65535, hi16, lo16 and shifts everything after it, so output positions are a prefix sum -- but such
+// coefficients are rare (16-bit data, several levels).  Three kernels: a flag pass (any escape in the image?  the flag is
+// parked in MicEncUnit::v_len, which the RLE stage only writes later), the plain pass for images without one (word k is
+// coefficient k of the subband order: every CTA of the grid works, eight coefficients per thread), and the chunked
+// one-CTA-per-image scan for the images that do have one (it was the only path: 58 ms for two mammograms).
+__global__ void __launch_bounds__(256)
+k_wavelet_pack_flag(const int32_t* __restrict__ A, MicEncUnit* __restrict__ units, const int* __restrict__ unit_of_img, unsigned total) {
+  const int img = blockIdx.y;
+  const int32_t* in = A + (unsigned long long)img * total;
+  int has = 0;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    const int v = in[k];
+    has |= (v < -32767 || v > 32767);
+  }
+  if (__syncthreads_or(has) && threadIdx.x == 0) atomicOr(&units[unit_of_img[img]].v_len, 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_wavelet_pack_plain(const int32_t* __restrict__ A, uint16_t* __restrict__ Vbuf, MicEncUnit* __restrict__ units,
+                     const int* __restrict__ unit_of_img, WaveletGeom G) {
+  const int img = blockIdx.y;
+  MicEncUnit* U = &units[unit_of_img[img]];
+  if (U->v_len) return;                      // has escapes: k_wavelet_pack
+  const unsigned total = G.rows * G.cols;
+  const int32_t* in = A + (unsigned long long)img * total;
+  uint16_t* V = Vbuf + U->src_off;
+  for (unsigned k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8u; k0 < total; k0 += gridDim.x * blockDim.x * 8u) {
+    // eight consecutive words of the subband order: locate the first, then walk along the subband row
+    unsigned y, x;
+    seg_locate_enc(G, k0, &y, &x);
+    int sgm = 0;
+#pragma unroll 1
+    for (int i = 1; i < G.nseg; i++)
+      if (k0 >= G.seg_start[i]) sgm = i;
+    unsigned xend = G.seg_x0[sgm] + G.seg_w[sgm];
+    unsigned send = sgm + 1 < G.nseg ? G.seg_start[sgm + 1] : total;
+    const unsigned n = min(8u, total - k0);
+    for (unsigned q = 0; q < n; q++) {
+      const unsigned k = k0 + q;
+      if (k >= send) {                        // next subband (empty subbands share a start: re-locate)
+        seg_locate_enc(G, k, &y, &x);
+        sgm = 0;
+#pragma unroll 1
+        for (int i = 1; i < G.nseg; i++)
+          if (k >= G.seg_start[i]) sgm = i;
+        xend = G.seg_x0[sgm] + G.seg_w[sgm];
+        send = sgm + 1 < G.nseg ? G.seg_start[sgm + 1] : total;
+      }
+      const int v = in[(unsigned long long)y * G.cols + x];
+      V[k] = (uint16_t)((v >> 31) ^ (v << 1));          // zigzagEncode16
+      if (++x >= xend) { x = G.seg_x0[sgm]; y++; }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) U->width = total;   // actual length of V; the RLE stage reads it from here
+}
+
 __global__ void __launch_bounds__(256)
 k_wavelet_pack(const int32_t* __restrict__ A, uint16_t* __restrict__ Vbuf, MicEncUnit* __restrict__ units, const int* __restrict__ unit_of_img,
                WaveletGeom G) {
   __shared__ unsigned s_warp[8];
   const int img = blockIdx.x;
   MicEncUnit* U = &units[unit_of_img[img]];
+  if (!U->v_len) return;                     // no escapes: k_wavelet_pack_plain wrote the stream
   const unsigned total = G.rows * G.cols;
   const int32_t* in = A + (unsigned long long)img * total;
   uint16_t* V = Vbuf + U->src_off;
@@ -281,6 +337,10 @@ void launch_wavelet_forward(const uint16_t* d_px, int32_t* d_A, int32_t* d_B, in
 }
 void launch_wavelet_pack(const int32_t* d_A, uint16_t* d_V, MicEncUnit* d_units, const int* d_unit_of_img, int nimg, const WaveletGeom& G, cudaStream_t st) {
   if (nimg <= 0) return;
+  const unsigned total = G.rows * G.cols;
+  k_wavelet_pack_flag<<<dim3(64, nimg), 256, 0, st>>>(d_A, d_units, d_unit_of_img, total);
+  const unsigned blocks = (total / 8 + 255) / 256;
+  k_wavelet_pack_plain<<<dim3(blocks < 2048 ? (blocks ? blocks : 1) : 2048, nimg), 256, 0, st>>>(d_A, d_V, d_units, d_unit_of_img, G);
   k_wavelet_pack<<<nimg, 256, 0, st>>>(d_A, d_V, d_units, d_unit_of_img, G);
 }
 void launch_gather_bytes(const GatherJob* d_jobs, int njobs, const uint8_t* d_src, uint8_t* d_dst, cudaStream_t st) {

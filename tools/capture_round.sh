@@ -30,7 +30,7 @@ MICGPU_PARTS=1 python tools/mic3_bench.py --side 8192 --steps 1 --warmup 1 --no-
       -o $O/prof_mic3 python tools/mic3_bench.py --side 8192 --steps 1 --warmup 1 --no-e2e --no-cpu > $O/ncu_mic3.log 2>&1
 # front-end kernels (wavelet lifting, temporal, tile planes, pyramid): one launch each
 python tools/frontend_kernels.py > $O/frontends.json 2> $O/frontends.err && \
-  ncu --set full --clock-control none -k regex:"k_wt53|k_wavelet|k_temporal|k_tile_planes|k_downsample|k_plane" -c 16 \
+  ncu --set full --clock-control none -k regex:"k_wt53|k_wavelet|k_temporal|k_tile_planes|k_tile_blit|k_downsample|k_plane|k_grad|k_row_costs" -c 90 \
       -o $O/prof_frontends python tools/frontend_kernels.py > $O/ncu_frontends.log 2>&1
 # gpurun merges at most 64 MiB back: keep the raw-metric CSV of every capture, the reports only of the two main workloads
 for r in prof_pics8 prof_pics8_2state prof_mic3 prof_frontends; do

@@ -89,7 +89,7 @@ struct micgpu_decoder {
   // of the issue slots, so the wavefront of one range fills gaps of the run expansion of the next (measured: -3 %)
   static constexpr int PARTS = 8;   // upper bound; MICGPU_PARTS picks fewer (default 4)
   cudaStream_t part_stream[PARTS] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[PARTS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[PARTS] = {}, ev_k3[PARTS] = {};
   // optional per-kernel timing (CUDA events on the launch stream)
   bool profiling = false;
   std::vector<cudaEvent_t> ev;
@@ -105,6 +105,7 @@ struct micgpu_decoder {
     for (int p = 0; p < PARTS; p++) {
       if (part_stream[p]) cudaStreamDestroy(part_stream[p]);
       if (ev_join[p]) cudaEventDestroy(ev_join[p]);
+      if (ev_k3[p]) cudaEventDestroy(ev_k3[p]);
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
     for (auto e : ev) cudaEventDestroy(e);
@@ -412,6 +413,10 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   // the header walk of one warp is the bound there, and CTAs of 128 threads / 2048-element chunks put 2.4x the walkers
   // on an SM (measured on 4096 tiles: K3 1.86 -> 1.45 ms; strips lose 10 % with it, profiles/README.md)
   const int k3_shape = d->max_log_all <= 12 ? 2 : 0;
+  // CTAs of K3 per SM when unit ranges overlap on their own streams: K3 is a persistent queue kernel, so fewer CTAs leave
+  // registers for the K4 CTAs of the previous range to co-reside (MICGPU_K3_CPS for A/B runs)
+  static const bool k3_chain = [] { const char* e = getenv("MICGPU_K3_CHAIN"); return e && e[0] == '1'; }();
+  static const int k3_cps = [] { const char* e = getenv("MICGPU_K3_CPS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
   static const int parts_cfg = [] { const char* e = getenv("MICGPU_PARTS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > micgpu_decoder::PARTS ? micgpu_decoder::PARTS : v); }();
   const int parts = (d->profiling || nu < 256) ? 1 : parts_cfg;   // per-kernel timing needs one stream
   if (parts == 1) {
@@ -429,6 +434,7 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
       for (int p = 0; p < micgpu_decoder::PARTS; p++) {
         CUDA_TRY(cudaStreamCreateWithFlags(&d->part_stream[p], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&d->ev_join[p], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d->ev_k3[p], cudaEventDisableTiming));
       }
     }
     CUDA_TRY(cudaEventRecord(d->ev_fork, st));
@@ -436,10 +442,14 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
       const int u0 = (int)((long long)nu * p / parts), u1 = (int)((long long)nu * (p + 1) / parts);
       cudaStream_t ps = d->part_stream[p];
       CUDA_TRY(cudaStreamWaitEvent(ps, d->ev_fork, 0));
+      // MICGPU_K3_CHAIN=1: the K3 kernels of the ranges run one after the other, so K3 of range p+1 shares the SMs with K4
+      // of range p instead of with the other K3 kernels
+      if (k3_chain && p > 0) CUDA_TRY(cudaStreamWaitEvent(ps, d->ev_k3[p - 1], 0));
       launch_rle_expand(du, u0, u1 - u0, (const uint16_t*)d->d_states.p, (const uint16_t*)d->d_tabS.p, (uint16_t*)d->d_D.p,
-                        (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(u1 - u0, d->sm_count * 8),
+                        (uint32_t*)d->d_M.p, (uint16_t*)d_out, d->max_log_all, std::min(u1 - u0, d->sm_count * k3_cps),
                         (unsigned int*)d->d_queue.p + p, ps, k3_shape);
       d->launches++;
+      if (k3_chain) CUDA_TRY(cudaEventRecord(d->ev_k3[p], ps));
       // the spatial list is sorted by unit index: this range's units are one contiguous slice of it
       const int s0 = (int)(std::lower_bound(d->spatial.begin(), d->spatial.end(), u0) - d->spatial.begin());
       const int s1 = (int)(std::lower_bound(d->spatial.begin(), d->spatial.end(), u1) - d->spatial.begin());

@@ -30,6 +30,9 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "mic_device.cuh"
 
 namespace micgpu {
@@ -672,8 +675,15 @@ template <int N, int MODE>
 static void launch_packed(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, const uint32_t* d_tabA,
                           uint16_t* d_states, int max_log, int slots, int grid, cudaStream_t st) {
   constexpr int UPW = 32 / N;
-  const int warps = (slots + UPW - 1) / UPW;
+  int warps = (slots + UPW - 1) / UPW;
+  // MICGPU_K2_UPW: units per warp (default 32 / N).  Slots are dealt round-robin over the warps, so more warps simply
+  // leave the upper lanes of each on the idle cell: fewer lanes per table lookup (fewer bank conflicts) against more
+  // warps per scheduler.
+  static const int upw_cfg = [] { const char* e = getenv("MICGPU_K2_UPW"); return e ? atoi(e) : 0; }();
+  if (upw_cfg >= 1 && upw_cfg < UPW) warps = std::min(32, (slots + upw_cfg - 1) / upw_cfg);
   size_t smem = ans_decode_smem_bytes(max_log, MODE, slots);
+  const int base_warps = (slots + 3) / 4;
+  if (warps > base_warps) smem += 64 * (size_t)(warps - base_warps);   // byte-exchange area: 64 B per warp
   cudaFuncSetAttribute(k_ans_decode_packed<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_ans_decode_packed<N, MODE><<<grid, 32 * warps, smem, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_states, max_log, slots);
 }

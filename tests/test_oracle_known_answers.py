@@ -448,3 +448,23 @@ def test_pica_layout_and_boundaries(oracle, synth):
     for bad in (b"PICS" + blob[4:], blob[:15], blob[:12] + (0).to_bytes(4, "little") + blob[16:], blob[:40]):
         with pytest.raises(Exception):
             oracle.pica_decompress(bad)
+
+
+@pytest.mark.parametrize("name,w,h,wav5,pics", [
+    # README.md:268-269 ("Wavelet" column, WaveletV2SIMD at 5 levels as in waveletu16_test.go:391) and
+    # docs/parallel-strips.md:98-99 (1 / 2 / 4 / 8 strips, two-state strips)
+    ("MR_256_256", 256, 256, 2.38, (2.35, 2.33, 2.28, 2.21)),
+    ("CT_512_512", 512, 512, 1.67, (2.24, 2.21, 2.15, 1.96)),
+])
+def test_published_ratios_wavelet_and_strip_counts(oracle, name, w, h, wav5, pics):
+    """The WaveletV2 stream has no golden vector and the reference's C twin does not cover it: its size on the two images
+    the repository ships is pinned to the three digits the reference publishes (a coefficient-order, escape or RLE
+    mistake moves the ratio in the first or second digit).  The same for PICS at every published strip count."""
+    px = np.fromfile(os.path.join(GOLDEN, f"{name}_image.bin"), dtype="<u2")
+    mx, raw = int(px.max()), w * h * 2
+    blob = oracle.wavelet_v2_compress(px, h, w, mx, 5)
+    assert abs(raw / len(blob) - wav5) < 0.005
+    got, rows, cols = oracle.wavelet_v2_decompress(blob)
+    assert (rows, cols) == (h, w) and np.array_equal(got, px)
+    for n, want in zip((1, 2, 4, 8), pics):
+        assert abs(raw / len(oracle.pics_compress(px, w, h, mx, n, 2)) - want) < 0.0051   # published to two decimals (2.325 -> 2.33)

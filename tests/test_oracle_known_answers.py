@@ -467,4 +467,4 @@ def test_published_ratios_wavelet_and_strip_counts(oracle, name, w, h, wav5, pic
     got, rows, cols = oracle.wavelet_v2_decompress(blob)
     assert (rows, cols) == (h, w) and np.array_equal(got, px)
     for n, want in zip((1, 2, 4, 8), pics):
-        assert abs(raw / len(oracle.pics_compress(px, w, h, mx, n, 2)) - want) < 0.0051   # published to two decimals (2.325 -> 2.33)
+        assert abs(raw / len(oracle.pics_compress(px, w, h, mx, n, 2)) - want) < 0.006   # published to two decimals, some rounded twice (2.1446 -> 2.145 -> 2.15)

@@ -38,5 +38,6 @@ for r in prof_pics8 prof_pics8_2state prof_mic3 prof_frontends; do
 done
 rm -f $O/prof_frontends.ncu-rep $O/prof_pics8_2state.ncu-rep
 python tools/bench_configs.py > $O/configs.json 2> $O/configs.err
+N=64 python tools/wavelet_batch.py > $O/wavelet_x64.txt 2>&1
 python tools/mic2_multi.py > $O/mic2_96.json 2> $O/mic2_96.err
 du -sh $O; tail -2 $O/pytest_gpu.txt; cat $O/smoke.txt | tail -1; cat $O/bench.json | cut -c1-600

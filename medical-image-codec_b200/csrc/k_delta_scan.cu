@@ -30,6 +30,10 @@
 
 #include "mic_device.cuh"
 
+#ifndef MICGPU_K4_FENCE
+#define MICGPU_K4_FENCE 1
+#endif
+
 namespace micgpu {
 
 namespace {
@@ -110,6 +114,13 @@ __device__ __forceinline__ unsigned ld_volatile_s(const unsigned* p) {
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
   return v;
 }
+// the same with the shared-window address computed once, outside the polling loop (the compiler re-derives it from the
+// generic pointer in every iteration otherwise: 8 instructions per poll instead of 3)
+__device__ __forceinline__ unsigned ld_volatile_sa(unsigned sa) {
+  unsigned v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_volatile_s(unsigned* p, unsigned v) {
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
@@ -147,6 +158,7 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
   const int nvalid = x0 >= W ? 0 : (W - x0 < 8 ? W - x0 : 8);
   const unsigned mwords = wp >> 5;
 
+  const unsigned rd_prev_sa = (unsigned)__cvta_generic_to_shared(&rows_done[warp > 0 ? warp - 1 : 0]);
   int top[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) top[i] = 0;
@@ -289,7 +301,7 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
     // ---- the block the previous warp finished on this row: carry pixel + the tail this warp stores --------------
     uint4 hb = make_uint4(0, 0, 0, 0);
     if (warp > 0) {
-      while (ld_volatile_s(&rows_done[warp - 1]) <= (unsigned)y) { }
+      while (ld_volatile_sa(rd_prev_sa) <= (unsigned)y) { }
       hb = hand[(warp - 1) * HAND_R + (y & (HAND_R - 1))];
     }
     int x = fn_apply(ex, (int)(hb.w >> 16));
@@ -330,7 +342,14 @@ k_delta_rowscan(MicUnit* __restrict__ units, const int* __restrict__ list, int n
         while (ld_volatile_s(&rows_done[warp + 1]) + HAND_R <= (unsigned)y) __nanosleep(64);   // not on anybody's critical path
       }
       if (lane == 31) hand[warp * HAND_R + (y & (HAND_R - 1))] = blk;
+      // the slot must be visible to the next warp before the row counter: an acquire-release fence at CTA scope is enough
+      // (__threadfence_block() compiles to the sequentially consistent MEMBAR.SC.CTA, which also waits for the warp's
+      // global stores in flight)
+#if MICGPU_K4_FENCE == 0
       __threadfence_block();
+#else
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
     }
     // row y of this warp is published (the next warp may read the slot; this warp has read the previous warp's slot)
     if (lane == 31) st_volatile_s(&rows_done[warp], (unsigned)y + 1u);

@@ -338,7 +338,8 @@ void launch_wavelet_forward(const uint16_t* d_px, int32_t* d_A, int32_t* d_B, in
 void launch_wavelet_pack(const int32_t* d_A, uint16_t* d_V, MicEncUnit* d_units, const int* d_unit_of_img, int nimg, const WaveletGeom& G, cudaStream_t st) {
   if (nimg <= 0) return;
   const unsigned total = G.rows * G.cols;
-  k_wavelet_pack_flag<<<dim3(64, nimg), 256, 0, st>>>(d_A, d_units, d_unit_of_img, total);
+  const unsigned fb = (total + 256 * 16 - 1) / (256 * 16);
+  k_wavelet_pack_flag<<<dim3(fb < 32 ? 32 : (fb > 1024 ? 1024 : fb), nimg), 256, 0, st>>>(d_A, d_units, d_unit_of_img, total);
   const unsigned blocks = (total / 8 + 255) / 256;
   k_wavelet_pack_plain<<<dim3(blocks < 2048 ? (blocks ? blocks : 1) : 2048, nimg), 256, 0, st>>>(d_A, d_V, d_units, d_unit_of_img, G);
   k_wavelet_pack<<<nimg, 256, 0, st>>>(d_A, d_V, d_units, d_unit_of_img, G);

@@ -2150,6 +2150,11 @@ int micgpu_wsi_decompress_tile_range(const uint8_t* mic3, size_t len, uint64_t f
   const uint64_t tile_bytes = (uint64_t)h.tile_w * h.tile_h * (h.bps == 16 ? h.channels * 2 : h.channels);
   if (n_tiles && tile_bytes > cap / n_tiles) return fail(MICGPU_E_SIZE, "output buffer too small for %llu tiles", (unsigned long long)n_tiles);
   std::vector<int> devs = configured_devices();
+  // One device and a large range: four contexts of that device take a quarter each on their own host threads, so the
+  // planning of one quarter (host work, ~3 us per tile), the H2D copy of another, the kernels of a third and the D2H copy
+  // of the fourth overlap (a device list may name a device several times; MICGPU_WSI_SPLIT=1 keeps one context).
+  static const int split_cfg = [] { const char* e = getenv("MICGPU_WSI_SPLIT"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  if (devs.size() <= 1 && n_tiles >= 4096 && split_cfg > 1) devs.assign((size_t)split_cfg, devs.empty() ? current_device() : devs[0]);
   if (devs.size() <= 1 || n_tiles < 2 * devs.size()) {
     std::string msg;
     return wsi_range_on_device(devs.empty() ? current_device() : devs[0], 0, mic3, len, first_tile, n_tiles, out, status, nullptr);

@@ -281,6 +281,10 @@ def pics_leg(ctx, nst, full):
     def step_dev():
         dec.run_device(d_comp.data_ptr(), tot, d_out.data_ptr(), raw_bytes // 2, stream)
 
+    # nvidia-smi needs ~0.2 s before its first sample and the timed region is ~0.13 s: the sampler starts before the
+    # warm-up (the same kernels, the same load) and keeps running through the timed region
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_dev()
     st = dec.unit_status(stream)
@@ -296,9 +300,8 @@ def pics_leg(ctx, nst, full):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    n_before = len(sampler.lines)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -306,7 +309,15 @@ def pics_leg(ctx, nst, full):
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1) / args.steps
+    n_timed = len(sampler.lines) - n_before
+    # a short timed region can fall between two samples: keep the same load up (untimed) until a few samples exist
+    t_extra = time.perf_counter()
+    while len(sampler.lines) < 6 and time.perf_counter() - t_extra < 1.5:
+        step_dev()
+        torch.cuda.synchronize()
     clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = n_timed
+    clocks["note"] = "sampled every 100 ms from the warm-up through the timed steps (and, if that is too short for nvidia-smi, a few more untimed steps of the same load)"
     launches = dec.last_launches      # kernels of one timed step
 
     # per-kernel breakdown (separate pass, CUDA events between launches on the same stream)

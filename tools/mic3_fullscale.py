@@ -116,8 +116,11 @@ def main():
     for devs in ([0], list(range(ndev))) if ndev > 1 else ([0],):
         mic.Init(devs)
         t_all, checked, ok, per_call = 0.0, 0, True, []
-        # untimed first call: every device context allocates its grow-only scratch once (several GB of cudaMalloc)
-        lib.micgpu_wsi_decompress_tile_range(pin, size, C.c_uint64(0), C.c_uint64(min(a.chunk, total)), pout, min(a.chunk, total) * tb, st)
+        # untimed first pass over every range: the contexts' grow-only scratch reaches its final size (a range of an upper
+        # level has more coded planes per tile than one of level 0, and a reallocation is a cudaFree + cudaMalloc of GBs)
+        for f in range(0, total, a.chunk):
+            n = min(a.chunk, total - f)
+            lib.micgpu_wsi_decompress_tile_range(pin, size, C.c_uint64(f), C.c_uint64(n), pout, n * tb, st)
         for f in range(0, total, a.chunk):
             n = min(a.chunk, total - f)
             t0 = time.perf_counter()

@@ -221,6 +221,10 @@ int micgpu_rgb_decompress(const uint8_t *blob, size_t len, int width, int height
 /* ---- WaveletV2 streams ---------------------------------------------------------- */
 /* WaveletV2[SIMD]RLEFSEDecompressU16 (waveletfsecompressu16.go:374,493): rows/cols come from the 11-byte header. */
 int micgpu_wavelet_v2_decompress(const uint8_t *blob, size_t len, uint16_t *pixels_out, size_t cap_px, int *rows, int *cols);
+/* The V1 wavelet layouts: WaveletFSEDecompressU16 (with_rle = 0, waveletfsecompressu16.go:124-163) and
+ * WaveletRLEFSEDecompressU16 (with_rle = 1, :624-669): coefficients in raster order, interleaved in-place lifting
+ * (waveletInverse2DRegion :180-189).  Decode only: the reference replaced these encoders by WaveletV2. */
+int micgpu_wavelet_v1_decompress(const uint8_t *blob, size_t len, int with_rle, uint16_t *pixels_out, size_t cap_px, int *rows, int *cols);
 int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t *const *blobs, const size_t *lens, uint16_t *const *outs, const size_t *caps,
                                        int *rows, int *cols, int *status);
 

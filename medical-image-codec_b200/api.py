@@ -120,6 +120,7 @@ lib.micgpu_wsi_decompress_tiles.argtypes = [C.c_void_p, C.c_size_t, C.c_int, _ip
 lib.micgpu_wsi_decompress_region.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_rgb_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
 lib.micgpu_wavelet_v2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_wavelet_v1_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_wavelet_v2_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip, _ip, _ip]
 _szp = C.POINTER(C.c_size_t)
 lib.micgpu_delta_rle_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_void_p, C.c_size_t, _szp]
@@ -487,6 +488,29 @@ def WaveletV2RLEFSEDecompressU16(compressed):
 
 
 WaveletV2SIMDRLEFSEDecompressU16 = WaveletV2RLEFSEDecompressU16
+
+
+def _wavelet_v1(compressed, with_rle: int):
+    a = _bytes_view(compressed)
+    if a.size < (15 if with_rle else 11):
+        raise MicGpuError(E_HEADER, "compressed data too short")
+    rows, cols = _rd32(a, 0), _rd32(a, 4)
+    if rows <= 0 or cols <= 0 or rows * cols > (1 << 31):
+        raise MicGpuError(E_HEADER, "bad wavelet header")
+    out = np.empty(rows * cols, np.uint16)
+    r, c = C.c_int(), C.c_int()
+    _check(lib.micgpu_wavelet_v1_decompress(a.ctypes.data, a.size, with_rle, out.ctypes.data, out.size, C.byref(r), C.byref(c)))
+    return out, r.value, c.value
+
+
+def WaveletFSEDecompressU16(compressed):
+    """waveletfsecompressu16.go:124 (V1 layout: FSE-4 only, raster order) -> (pixels, rows, cols)."""
+    return _wavelet_v1(compressed, 0)
+
+
+def WaveletRLEFSEDecompressU16(compressed):
+    """waveletfsecompressu16.go:624 (V1 layout with RLE) -> (pixels, rows, cols)."""
+    return _wavelet_v1(compressed, 1)
 
 
 def WaveletV2DecompressBatch(blobs):

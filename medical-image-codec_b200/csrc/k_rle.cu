@@ -96,6 +96,17 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     const unsigned W = U->width, H = U->height, wp = U->wp, align0 = U->align0;
     const unsigned long long npx = (unsigned long long)W * H;
 
+    if (U->kind == MIC_KIND_RAW) {
+      // no RLE layer: symbol i is output word i (capacity `width`)
+      if ((unsigned long long)nsym > npx) {
+        if (tid == 0) U->status = MIC_E_SIZE;
+        continue;
+      }
+      uint16_t* dst = out + U->out_off;
+      for (int i = tid; i < nsym; i += K3_THREADS) dst[i] = __ldg(Sy + __ldg(st + i));
+      if (tid == 0) U->thr = (unsigned)nsym;
+      continue;
+    }
     if (nsym < (spatial ? 2 : 3)) {
       if (tid == 0) U->status = MIC_E_RLE;
       continue;

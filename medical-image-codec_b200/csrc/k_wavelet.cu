@@ -147,6 +147,43 @@ struct Lift {
   }
 };
 
+// V1 layouts (waveletInverse2DRegion, waveletfsecompressu16.go:180-189): the 1-D lifting works IN PLACE on interleaved
+// samples (even = low, odd = high; wt53Inverse1D waveletu16.go:75-122) and a level covers the top-left r x c corner of the
+// interleaved buffer.  Out of place here, one output sample per thread:
+//   x[2i]   = v[2i]   - ((dL + dR + 2) >> 2)   dR = v[2i+1] (or v[2i-1] at the end of an odd-length signal, 0 if n == 1), dL = v[2i-1] (or dR at i == 0)
+//   x[2i+1] = v[2i+1] + ((x[2i] + x[2i+2]) >> 1)   (x[2i] again at the right edge)
+// AXIS 0: along columns (stride = row pitch), AXIS 1: along rows.
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+k_wt53_il_inv(const int32_t* __restrict__ A, int32_t* __restrict__ B, unsigned r, unsigned c, unsigned cols, unsigned long long img_stride) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned y = blockIdx.y;
+  if (x >= c || y >= r) return;
+  const int32_t* in = A + (unsigned long long)blockIdx.z * img_stride;
+  int32_t* out = B + (unsigned long long)blockIdx.z * img_stride;
+  const unsigned n = AXIS == 0 ? r : c;            // length of the lifted signal
+  const unsigned p = AXIS == 0 ? y : x;            // position in it
+  auto V = [&](unsigned q) -> int {
+    return AXIS == 0 ? in[(unsigned long long)q * cols + x] : in[(unsigned long long)y * cols + q];
+  };
+  auto even = [&](unsigned q) -> int {             // restored even sample at even position q
+    int dR;
+    if (q + 1 < n) dR = V(q + 1);
+    else dR = q > 0 ? V(q - 1) : 0;
+    const int dL = q > 0 ? V(q - 1) : dR;
+    return V(q) - ((dL + dR + 2) >> 2);
+  };
+  int res;
+  if (n < 2) res = V(p);
+  else if ((p & 1u) == 0) res = even(p);
+  else {
+    const int xl = even(p - 1);
+    const int xr = p + 1 < n ? even(p + 1) : xl;
+    res = V(p) + ((xl + xr) >> 1);
+  }
+  out[(unsigned long long)y * cols + x] = res;
+}
+
 // column pass: A -> B over the top-left r x c region (full row pitch `cols`)
 __global__ void __launch_bounds__(256)
 k_wt53_inv_cols(const int32_t* __restrict__ A, int32_t* __restrict__ B, unsigned r, unsigned c, unsigned cols, unsigned long long img_stride) {
@@ -381,9 +418,27 @@ static bool wavelet_tma_enabled() {
 // copy of the untouched part is not needed: both passes only rewrite the r x c corner and level l+1's
 // corner is inside level l's.
 void launch_wavelet_decode(MicUnit* d_units, const int* d_unit_of_img, int nimg, const uint16_t* d_stream, int* d_flags,
-                           int32_t* d_A, int32_t* d_B, uint16_t* d_px, const WaveletGeom& G, cudaStream_t st) {
+                           int32_t* d_A, int32_t* d_B, uint16_t* d_px, const WaveletGeom& G, cudaStream_t st, int v1_layout) {
   if (nimg <= 0) return;
   const unsigned total = G.rows * G.cols;
+  if (v1_layout) {
+    // coefficients in raster order (G holds ONE segment covering the image), interleaved in-place levels
+    cudaMemsetAsync(d_flags, 0, nimg * sizeof(int), st);
+    const unsigned eb1 = (total + 256 * 16 - 1) / (256 * 16);
+    k_wavelet_has_escape<<<dim3(eb1 < 32 ? 32 : (eb1 > 1024 ? 1024 : eb1), nimg), 256, 0, st>>>(d_units, d_unit_of_img, d_stream, d_flags);
+    const unsigned sb1 = (total / 8 + 255) / 256 + 1;
+    k_wavelet_scatter<false><<<dim3(sb1 < 1024 ? sb1 : 1024, nimg), 256, 0, st>>>(d_units, d_unit_of_img, d_stream, d_flags, d_A, d_B, G);
+    unsigned vr[256], vc[256];
+    unsigned r1 = G.rows, c1 = G.cols;
+    for (int l = 0; l < G.levels; l++) { vr[l] = r1; vc[l] = c1; r1 = (r1 + 1) / 2; c1 = (c1 + 1) / 2; }
+    for (int l = G.levels - 1; l >= 0; l--) {
+      const dim3 grid((vc[l] + 255) / 256, vr[l], nimg);
+      k_wt53_il_inv<0><<<grid, 256, 0, st>>>(d_A, d_B, vr[l], vc[l], G.cols, total);
+      k_wt53_il_inv<1><<<grid, 256, 0, st>>>(d_B, d_A, vr[l], vc[l], G.cols, total);
+    }
+    k_i32_to_u16<<<1024, 256, 0, st>>>(d_A, d_px, (unsigned long long)total * nimg);
+    return;
+  }
   cudaMemsetAsync(d_flags, 0, nimg * sizeof(int), st);
   const unsigned eb = (total + 256 * 16 - 1) / (256 * 16);   // ~16 words per thread
   k_wavelet_has_escape<<<dim3(eb < 32 ? 32 : (eb > 1024 ? 1024 : eb), nimg), 256, 0, st>>>(d_units, d_unit_of_img, d_stream, d_flags);

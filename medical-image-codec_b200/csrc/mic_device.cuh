@@ -100,12 +100,12 @@ void launch_tile_blit(const TileBlitJob* d_jobs, int njobs, const uint16_t* d_pl
 // WaveletV2 decode (k_wavelet.cu)
 struct WaveletGeom {
   unsigned rows, cols;
-  int levels;                 // levels actually applied (header byte 10)
+  int levels;                 // levels actually applied (header byte 10; up to 255 for the V1 layouts, whose geometry is one segment)
   int nseg;                   // 1 + 3*levels subband segments in stream order
   unsigned seg_start[25], seg_y0[25], seg_x0[25], seg_w[25];
 };
 void launch_wavelet_decode(MicUnit* d_units, const int* d_unit_of_img, int nimg, const uint16_t* d_stream, int* d_flags,
-                           int32_t* d_A, int32_t* d_B, uint16_t* d_px, const WaveletGeom& G, cudaStream_t st);
+                           int32_t* d_A, int32_t* d_B, uint16_t* d_px, const WaveletGeom& G, cudaStream_t st, int v1_layout = 0);
 
 // Encode side (k_enc_rle.cu, k_enc_fse.cu)
 void launch_enc_delta_rle(MicEncUnit* d_units, int nunits, const uint16_t* d_src, uint16_t* d_V, uint32_t* d_segs, uint16_t* d_S,

@@ -10,6 +10,7 @@
 enum MicUnitKind {
   MIC_KIND_SPATIAL = 0,  // Delta(avg(top,left),escape)+RLE symbol stream -> w*h pixels
   MIC_KIND_RLE = 1,      // RLE stream with 2-word length prefix (temporal residual / wavelet)
+  MIC_KIND_RAW = 2,      // the FSE symbols are the payload (V1 wavelet without RLE, waveletfsecompressu16.go:124-163)
 };
 
 enum MicStatus {

@@ -2210,8 +2210,27 @@ WaveletGeom wavelet_geom(unsigned rows, unsigned cols, int levels) {
 extern "C" {
 
 // WaveletV2RLEFSEDecompressU16 / WaveletV2SIMDRLEFSEDecompressU16 (waveletfsecompressu16.go:374-421,493-534) for n streams
+// variant 2: WaveletV2 (11-byte header, RLE + FSE-4, subband order, Mallat levels); variant 0: WaveletFSEDecompressU16 (11-byte
+// header, FSE-4 only, raster order, interleaved in-place levels); variant 1: WaveletRLEFSEDecompressU16 (15-byte header, RLE +
+// FSE-4, raster order, interleaved levels) -- waveletfsecompressu16.go:124-163, 374-421, 624-669
+static int wavelet_decompress_batch(int variant, int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
+                                    const size_t* caps, int* rows_out, int* cols_out, int* status);
+
 int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs, const size_t* caps,
                                        int* rows_out, int* cols_out, int* status) {
+  return wavelet_decompress_batch(2, n, blobs, lens, outs, caps, rows_out, cols_out, status);
+}
+
+// WaveletFSEDecompressU16 (with_rle = 0) / WaveletRLEFSEDecompressU16 (with_rle = 1): the V1 layouts
+int micgpu_wavelet_v1_decompress(const uint8_t* blob, size_t len, int with_rle, uint16_t* pixels_out, size_t cap_px, int* rows, int* cols) {
+  if (!blob || !pixels_out) return fail(MICGPU_E_HEADER, "null argument");
+  return wavelet_decompress_batch(with_rle ? 1 : 0, 1, &blob, &len, &pixels_out, &cap_px, rows, cols, nullptr);
+}
+
+static int wavelet_decompress_batch(int variant, int n, const uint8_t* const* blobs, const size_t* lens, uint16_t* const* outs,
+                                    const size_t* caps, int* rows_out, int* cols_out, int* status) {
+  const size_t HDR = variant == 1 ? 15 : 11;
+  const bool v1 = variant != 2;
   if (n <= 0) return 0;
   micgpu_decoder* d = default_decoder(current_device());
   if (!d) return MICGPU_E_CUDA;
@@ -2227,18 +2246,21 @@ int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t* const* blobs, const
     Img& I = im[i];
     I.st = 0; I.unit = -1; I.coff = ctot; I.px_off = ptot; I.rows = I.cols = 0; I.levels = 0;
     ctot += (lens[i] + 63) & ~(size_t)63;
-    if (lens[i] < 11 + 6) { I.st = fail(MICGPU_E_HEADER, "compressed data too short"); continue; }
+    if (lens[i] < HDR + 6) { I.st = fail(MICGPU_E_HEADER, "compressed data too short"); continue; }
     I.rows = rd32(blobs[i]); I.cols = rd32(blobs[i] + 4); I.levels = blobs[i][10];
     if (rows_out) rows_out[i] = (int)I.rows;
     if (cols_out) cols_out[i] = (int)I.cols;
     const uint64_t px = (uint64_t)I.rows * I.cols;
-    if (I.rows == 0 || I.cols == 0 || px > (1ull << 31) || I.levels > 8) { I.st = fail(MICGPU_E_HEADER, "bad wavelet header"); continue; }
-    if (blobs[i][11] != 0xFF || blobs[i][12] != 0x04) { I.st = fail(MICGPU_E_HEADER, "fse4state: missing magic bytes"); continue; }
+    if (I.rows == 0 || I.cols == 0 || px > (1ull << 31) || (!v1 && I.levels > 8)) { I.st = fail(MICGPU_E_HEADER, "bad wavelet header"); continue; }
+    if (v1 && I.rows > 65535) { I.st = fail(MICGPU_E_UNSUPPORTED, "V1 wavelet stream with %u rows", I.rows); continue; }
+    if (blobs[i][HDR] != 0xFF || blobs[i][HDR + 1] != 0x04) { I.st = fail(MICGPU_E_HEADER, "fse4state: missing magic bytes"); continue; }
     if (px > caps[i]) { I.st = fail(MICGPU_E_SIZE, "image %d: output buffer too small", i); continue; }
     // coefficient stream: one u16 per coefficient, three per escaped coefficient; the FSE symbol count bounds it
-    const uint64_t count = rd32(blobs[i] + 13);
-    const uint64_t cap = std::min<uint64_t>(3 * px, std::max<uint64_t>(px, 65535ull * count));
-    I.unit = add_unit_locked(d, blobs[i] + 11, lens[i] - 11, I.coff + 11, MIC_KIND_RLE, (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFFFull), 1, stot);
+    const uint64_t count = rd32(blobs[i] + HDR + 2);
+    const uint64_t cap = variant == 0 ? std::max<uint64_t>(count, 1) : std::min<uint64_t>(3 * px, std::max<uint64_t>(px, 65535ull * count));
+    if (variant == 0 && count > 3 * px) { I.st = fail(MICGPU_E_SIZE, "coefficient stream longer than three words per pixel"); continue; }
+    I.unit = add_unit_locked(d, blobs[i] + HDR, lens[i] - HDR, I.coff + HDR, variant == 0 ? MIC_KIND_RAW : MIC_KIND_RLE,
+                             (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFFFull), 1, stot);
     stot += (cap + 15) & ~15ull;
     ptot += px;
   }
@@ -2269,10 +2291,16 @@ int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t* const* blobs, const
       done[j] = 1;
       j++;
     }
-    const WaveletGeom G = wavelet_geom(im[i].rows, im[i].cols, im[i].levels);
+    WaveletGeom G;
+    if (v1) {   // raster order: one segment that covers the image
+      memset(&G, 0, sizeof G);
+      G.rows = im[i].rows; G.cols = im[i].cols; G.levels = im[i].levels; G.nseg = 1; G.seg_w[0] = im[i].cols;
+    } else {
+      G = wavelet_geom(im[i].rows, im[i].cols, im[i].levels);
+    }
     CUDA_TRY(cudaMemcpyAsync(d_uoi, uoi.data(), cnt * sizeof(int), cudaMemcpyHostToDevice, st));
     launch_wavelet_decode((MicUnit*)d->d_units.p, d_uoi, cnt, (const uint16_t*)d->d_out.p, d_flags, (int32_t*)d->d_wA.p + im[i].px_off,
-                          (int32_t*)d->d_wB.p + im[i].px_off, (uint16_t*)d->d_bytes.p + im[i].px_off, G, st);
+                          (int32_t*)d->d_wB.p + im[i].px_off, (uint16_t*)d->d_bytes.p + im[i].px_off, G, st, v1 ? 1 : 0);
     d->launches += 2 + 2 * std::max(1, G.levels);
     CUDA_TRY(cudaStreamSynchronize(st));   // d_uoi / d_flags are reused by the next group
   }

@@ -1483,6 +1483,108 @@ int orc_wavelet_v2_decompress(const u8 *in, size_t len, u16 **px_out, int *rows_
 }
 
 /* ------------------------------------------------------------------------ */
+/* L3: V1 wavelet layouts (waveletfsecompressu16.go:71-189, 551-669)         */
+/* ------------------------------------------------------------------------ */
+/* WaveletFSECompressU16 (with_rle = 0: 11-byte header) and WaveletRLEFSECompressU16 (with_rle = 1: 15-byte header with the
+ * coefficient-stream length).  The transform is waveletForward2DRegion (:167-177): every row, then every column, IN PLACE
+ * with interleaved low / high coefficients; the next level works on the top-left (r+1)/2 x (c+1)/2 corner of that
+ * interleaved buffer (not on an LL band -- the reason WaveletV2 exists); levels are clamped to [1, 4]; coefficients go
+ * out in raster order. */
+int orc_wavelet_v1_compress(const u16 *px, int rows, int cols, u16 max_value, int levels, int with_rle, u8 **out, size_t *out_len) {
+  *out = NULL; *out_len = 0;
+  if (levels < 1) levels = 1;
+  if (levels > 4) levels = 4;
+  size_t n = (size_t)rows * cols;
+  i32 *data = (i32 *)malloc((n ? n : 1) * sizeof(i32));
+  for (size_t i = 0; i < n; i++) data[i] = (i32)px[i];
+  int r = rows, c = cols;
+  for (int l = 0; l < levels; l++) {
+    if (r < 2 || c < 2) { levels = l; break; }
+    for (int y = 0; y < r; y++) orc_wt53_forward_1d(data, y * cols, c, 1);
+    for (int x = 0; x < c; x++) orc_wt53_forward_1d(data, x, r, cols);
+    r = (r + 1) / 2;
+    c = (c + 1) / 2;
+  }
+  wbuf enc = {0};
+  for (size_t i = 0; i < n; i++) {
+    i32 v = data[i];
+    if (v >= -32767 && v <= 32767) wb_push(&enc, zz_enc16(v));
+    else { wb_push(&enc, 65535); wb_push(&enc, (u16)((u32)v >> 16)); wb_push(&enc, (u16)(u32)v); }
+  }
+  free(data);
+  u16 *sym = enc.p; size_t nsym = enc.n;
+  size_t enc_len = enc.n;
+  int rc = 0;
+  if (with_rle) {
+    u16 zz_max = 0;
+    for (size_t i = 0; i < enc.n; i++) if (enc.p[i] > zz_max) zz_max = enc.p[i];
+    int depth = len16(zz_max);
+    if (depth < 1) depth = 1;
+    rc = orc_rle_compress(enc.p, enc.n, (u16)((1 << depth) - 1), &sym, &nsym);
+    free(enc.p);
+    if (rc) return rc;
+  }
+  u8 *fse; size_t nfse;
+  rc = orc_fse_compress(sym, nsym, ORC_FSE4, &fse, &nfse);
+  free(sym);
+  if (rc) return rc;
+  bbuf o = {0};
+  bb_u32(&o, (u32)rows); bb_u32(&o, (u32)cols);
+  bb_push(&o, (u8)max_value); bb_push(&o, (u8)(max_value >> 8));
+  bb_push(&o, (u8)levels);
+  if (with_rle) bb_u32(&o, (u32)enc_len);
+  bb_append(&o, fse, nfse);
+  free(fse);
+  *out = o.p; *out_len = o.n;
+  return 0;
+}
+
+/* WaveletFSEDecompressU16 (:124-163) / WaveletRLEFSEDecompressU16 (:624-669) */
+int orc_wavelet_v1_decompress(const u8 *in, size_t len, int with_rle, u16 **px_out, int *rows_o, int *cols_o) {
+  *px_out = NULL;
+  const size_t hdr = with_rle ? 15 : 11;
+  if (len < hdr) return ORC_ERR_CORRUPT;
+  int rows = (int)rd32(in), cols = (int)rd32(in + 4);
+  int levels = in[10];
+  if (len - hdr < 6 || in[hdr] != 0xFF || in[hdr + 1] != 0x04) return ORC_ERR_CORRUPT; /* FSEDecompressU16FourState magic */
+  u16 *enc; size_t nenc;
+  int rc = orc_fse_decompress_auto(in + hdr, len - hdr, &enc, &nenc);
+  if (rc) return rc;
+  if (with_rle) {
+    u16 *e2; size_t n2;
+    rc = orc_rle_decompress(enc, nenc, &e2, &n2);
+    free(enc);
+    if (rc) return rc;
+    enc = e2; nenc = n2;
+  }
+  size_t n = (size_t)rows * cols;
+  i32 *data = (i32 *)calloc(n ? n : 1, sizeof(i32));
+  size_t i = 0, k = 0;
+  while (i < nenc && k < n) { /* u16ToWaveletCoeffs :45-58 */
+    if (enc[i] != 65535) { data[k++] = zz_dec16(enc[i]); i++; }
+    else {
+      if (i + 2 >= nenc) { free(enc); free(data); return ORC_ERR_CORRUPT; } /* Go: index out of range */
+      data[k++] = (i32)(((u32)enc[i + 1] << 16) | (u32)enc[i + 2]);
+      i += 3;
+    }
+  }
+  free(enc);
+  if (k != n) { free(data); return ORC_ERR_CORRUPT; } /* Go: the inverse transform indexes past the short slice */
+  int dr[256], dc[256];
+  int r = rows, c = cols;
+  for (int l = 0; l < levels; l++) { dr[l] = r; dc[l] = c; r = (r + 1) / 2; c = (c + 1) / 2; }
+  for (int l = levels - 1; l >= 0; l--) { /* waveletInverse2DRegion :180-189: columns, then rows */
+    for (int x = 0; x < dc[l]; x++) orc_wt53_inverse_1d(data, x, dr[l], cols);
+    for (int y = 0; y < dr[l]; y++) orc_wt53_inverse_1d(data, y * cols, dc[l], 1);
+  }
+  u16 *px = (u16 *)malloc((n ? n : 1) * sizeof(u16));
+  for (size_t j = 0; j < n; j++) px[j] = (u16)data[j];
+  free(data);
+  *px_out = px; *rows_o = rows; *cols_o = cols;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* L4: PICS (parallelstrips.go:55-330)                                       */
 /* ------------------------------------------------------------------------ */
 int orc_pics_compress(const u16 *px, int width, int height, u16 max_value, int num_strips, int nstates, u8 **out, size_t *out_len) {

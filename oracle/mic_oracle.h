@@ -97,6 +97,10 @@ int orc_decompress_residual_frame(const uint8_t *in, size_t len, uint16_t **out,
 int orc_wavelet_v2_compress(const uint16_t *px, int rows, int cols, uint16_t max_value, int levels, uint8_t **out, size_t *out_len);
 int orc_wavelet_v2_decompress(const uint8_t *in, size_t len, uint16_t **px_out, int *rows, int *cols);
 
+/* WaveletFSECompressU16 / WaveletRLEFSECompressU16 and their decoders (V1 layouts, waveletfsecompressu16.go:71-189,551-669) */
+int orc_wavelet_v1_compress(const uint16_t *px, int rows, int cols, uint16_t max_value, int levels, int with_rle, uint8_t **out, size_t *out_len);
+int orc_wavelet_v1_decompress(const uint8_t *in, size_t len, int with_rle, uint16_t **px_out, int *rows, int *cols);
+
 /* ---- L4: containers ------------------------------------------------------ */
 /* CompressParallelStrips[4State/8State] / DecompressParallelStrips (parallelstrips.go:55-330) */
 int orc_pics_compress(const uint16_t *px, int width, int height, uint16_t max_value, int num_strips, int nstates, uint8_t **out, size_t *out_len);

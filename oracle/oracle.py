@@ -239,6 +239,19 @@ class Oracle:
         n = C.c_size_t(r.value * c.value)
         return self._take_u16(p, n), r.value, c.value
 
+    def wavelet_v1_compress(self, px, rows, cols, max_value, levels, with_rle) -> bytes:
+        a = _as_u16(px)
+        p, n = _u8p(), C.c_size_t()
+        self._chk(self.lib.orc_wavelet_v1_compress(_ptr(a, _u16p), rows, cols, C.c_uint16(max_value), levels, int(bool(with_rle)), C.byref(p), C.byref(n)), "wavelet_v1_compress")
+        return self._take_u8(p, n)
+
+    def wavelet_v1_decompress(self, blob, with_rle):
+        a = _as_u8(blob)
+        p = _u16p()
+        r, c = C.c_int(), C.c_int()
+        self._chk(self.lib.orc_wavelet_v1_decompress(_ptr(a, _u8p), C.c_size_t(a.size), int(bool(with_rle)), C.byref(p), C.byref(r), C.byref(c)), "wavelet_v1_decompress")
+        return self._take_u16(p, C.c_size_t(r.value * c.value)), r.value, c.value
+
     # -- L4 ----------------------------------------------------------------
     def pics_compress(self, px, width, height, max_value, num_strips, nstates=2) -> bytes:
         a = _as_u16(px)

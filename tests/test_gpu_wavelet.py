@@ -71,3 +71,35 @@ def test_wavelet_bad_magic(mic, oracle):
     blob[12] = 0x02
     with pytest.raises(mic.MicGpuError):
         mic.WaveletV2RLEFSEDecompressU16(bytes(blob))
+
+
+# ---- SURVEY 8(f).4 (wavelet half): the V1 layouts, decode only ------------------------------------------------------------
+@pytest.mark.parametrize("with_rle", [0, 1])
+@pytest.mark.parametrize("rows,cols,levels", [(64, 40, 1), (65, 33, 2), (128, 96, 3), (257, 129, 4), (300, 517, 4), (40, 1000, 9), (9, 4000, 3), (4000, 9, 4)])
+def test_wavelet_v1_layouts_decode(mic, oracle, synth, with_rle, rows, cols, levels):
+    """WaveletFSEDecompressU16 / WaveletRLEFSEDecompressU16 (waveletfsecompressu16.go:124-163, 624-669): raster-order
+    coefficients, interleaved in-place lifting on the top-left corner per level (waveletInverse2DRegion :180-189), levels
+    clamped to 4 by the encoder, early stop below 2 rows / columns."""
+    px, mx = _field(rows, cols, 5), 4095
+    blob = oracle.wavelet_v1_compress(px, rows, cols, mx, levels, with_rle)
+    ref, r, c = oracle.wavelet_v1_decompress(blob, with_rle)
+    assert (r, c) == (rows, cols) and np.array_equal(ref, px)
+    got, gr, gc = (mic.WaveletRLEFSEDecompressU16 if with_rle else mic.WaveletFSEDecompressU16)(blob)
+    assert (gr, gc) == (rows, cols) and np.array_equal(got, px)
+
+
+def test_wavelet_v1_reference_images_and_escapes(mic, oracle):
+    import os
+    from conftest import GOLDEN
+
+    for name, w, h in (("MR_256_256", 256, 256), ("CT_512_512", 512, 512)):   # CT: full 16-bit range -> escape triples
+        px = np.fromfile(os.path.join(GOLDEN, f"{name}_image.bin"), dtype="<u2")
+        for with_rle in (0, 1):
+            blob = oracle.wavelet_v1_compress(px, h, w, int(px.max()), 3, with_rle)
+            got, r, c = (mic.WaveletRLEFSEDecompressU16 if with_rle else mic.WaveletFSEDecompressU16)(blob)
+            assert (r, c) == (h, w) and np.array_equal(got, px), (name, with_rle)
+    # damaged streams: no hang, an error or the oracle's verdict
+    blob = bytearray(oracle.wavelet_v1_compress(px, 512, 512, int(px.max()), 2, 1))
+    for bad in (bytes(blob[:14]), bytes(blob[:15]) + b"\x00" * 8, bytes(blob[:40])):
+        with pytest.raises(mic.MicGpuError):
+            mic.WaveletRLEFSEDecompressU16(bad)

@@ -468,3 +468,23 @@ def test_published_ratios_wavelet_and_strip_counts(oracle, name, w, h, wav5, pic
     assert (rows, cols) == (h, w) and np.array_equal(got, px)
     for n, want in zip((1, 2, 4, 8), pics):
         assert abs(raw / len(oracle.pics_compress(px, w, h, mx, n, 2)) - want) < 0.006   # published to two decimals, some rounded twice (2.1446 -> 2.145 -> 2.15)
+
+
+@pytest.mark.parametrize("with_rle", [0, 1])
+def test_wavelet_v1_layouts_roundtrip(oracle, with_rle):
+    """WaveletFSECompressU16 / WaveletRLEFSECompressU16 (waveletfsecompressu16.go:71-189, 551-669): header layout (11 / 15
+    bytes, the RLE variant stores the coefficient-stream length), level clamp to 4 and pixel-exact round trips on the
+    reference's own images (TestWaveletFSECompress / TestWaveletRLEFSECompress shapes, waveletu16_test.go)."""
+    for name, w, h in (("MR_256_256", 256, 256), ("CT_512_512", 512, 512)):
+        px = np.fromfile(os.path.join(GOLDEN, f"{name}_image.bin"), dtype="<u2")
+        mx = int(px.max())
+        for levels in (1, 3, 9):
+            blob = oracle.wavelet_v1_compress(px, h, w, mx, levels, with_rle)
+            assert int.from_bytes(blob[0:4], "little") == h and int.from_bytes(blob[4:8], "little") == w
+            assert int.from_bytes(blob[8:10], "little") == mx and blob[10] == min(levels, 4)
+            hdr = 15 if with_rle else 11
+            assert blob[hdr] == 0xFF and blob[hdr + 1] == 0x04          # FSECompressU16FourState magic
+            if with_rle:
+                assert int.from_bytes(blob[11:15], "little") >= w * h   # one word per coefficient, three per escape
+            got, r, c = oracle.wavelet_v1_decompress(blob, with_rle)
+            assert (r, c) == (h, w) and np.array_equal(got, px)

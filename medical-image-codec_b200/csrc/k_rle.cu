@@ -57,9 +57,23 @@ struct WalkState {
   int nout;        // elements produced by the last walk
   int nruns;       // runs listed by the last walk
   int done, err;
+  int mdirty;      // PW: the speculative masks are fresh, the true header mask has not been stitched yet
+  int hcount, hidx; // PW: headers on the list, index of the next one (the header at ipos)
+  int pwmode;      // PW: 1 = this window is walked in parallel (chosen at every predicted restage from the header density)
+  int hseen;       // headers consumed since the last restage
 };
 
-template <int THREADS, int CHUNK>
+// PW: parallel header walk.  The run headers of a stream form a chain (the position of a header follows from the one
+// before it), which one warp used to follow run by run while the other warps waited: the bound of run-heavy streams
+// (temporal residual frames, wavelet coefficient streams: a run every ~5 symbols; 8-bit tile planes).  The chain
+// re-synchronises: followed from a wrong position it falls onto the true chain within a few runs (every diff-run of even
+// length and every symbol above midCount re-aligns it).  So at every restage each warp follows the chain of its own
+// 1/K3_WARPS of the window speculatively from the first symbol of that part (one shuffle per run, 32 symbols per
+// shared-memory load) and leaves a bit mask of its headers; warp 0 then stitches the true chain: where the true entry
+// of a part lies on the part's speculative chain, the rest of that part is adopted, else the chain is followed by hand
+// until it meets the speculative one.  With the header bit mask of the window, the headers of a chunk are taken 32 at a
+// time, one per lane: run lengths by a warp scan, short runs expanded by their lane, long ones listed for phase B2.
+template <int THREADS, int CHUNK, bool PW>
 __global__ void __launch_bounds__(THREADS, K3Shape<THREADS, CHUNK>::MINB)
 k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict__ states,
              const uint16_t* __restrict__ tabS, uint16_t* __restrict__ D, uint32_t* __restrict__ M,
@@ -77,6 +91,11 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
   __shared__ uint16_t s_run_o[MAXR], s_run_n[MAXR];   // run list of the current chunk: output start, length
   __shared__ int s_run_src[MAXR];                     // >= 0: first literal in s_in (diff-run); < 0: -(value+1) (same-run)
   __shared__ WalkState ws;
+  constexpr int SW = IN_N / K3_WARPS;                 // symbols of the window each warp follows speculatively (multiple of 32)
+  __shared__ uint32_t s_spec[PW ? IN_N / 32 : 1];     // speculative header bits, one word per 32 window symbols
+  __shared__ uint32_t s_hdr[PW ? IN_N / 32 : 1];      // true header bits of the window (valid from the entry of the last restage on)
+  __shared__ int s_exit[PW ? K3_WARPS : 1];           // first position of each part's speculative chain beyond the part
+  __shared__ uint16_t s_hpos[PW ? IN_N / 2 : 1];      // the true headers of the window in order (window-relative positions)
   extern __shared__ __align__(16) uint16_t s_tab[];   // tabS of the current unit (when it fits: tab_smem_log >= tableLog)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,6 +112,8 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     const uint16_t* st = states + U->sym_off;
     const uint16_t* Sy = tabS + U->tab_off;
     const bool spatial = U->kind == MIC_KIND_SPATIAL;
+    // strips of 12-bit and deeper pixels have a few runs per chunk (diff-runs of thousands): the one-warp walk is cheaper there
+    const bool use_pw = PW && (!spatial || U->table_log <= 12);
     const unsigned W = U->width, H = U->height, wp = U->wp, align0 = U->align0;
     const unsigned long long npx = (unsigned long long)W * H;
 
@@ -140,7 +161,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     if (tid == 0) {
       ws.ipos = spatial ? 1 : 3;
       ws.wbase = 0; ws.wend = 0;
-      ws.c_rem = 0; ws.kind = 0; ws.value = 0; ws.nout = 0; ws.done = 0; ws.err = 0;
+      ws.c_rem = 0; ws.kind = 0; ws.value = 0; ws.nout = 0; ws.done = 0; ws.err = 0; ws.mdirty = 0; ws.hcount = 0; ws.hidx = 0; ws.pwmode = 0; ws.hseen = 0;
     }
     unsigned thr = 0, delim = 0;
     unsigned long long pix = 0;        // pixels (spatial) or elements (RLE) emitted so far
@@ -152,6 +173,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
     while (true) {
       // ---------------- A: (re)stage the symbol window ----------------------
       const int ipos = ws.ipos, wend0 = ws.wend;
+      const bool pwm = PW && use_pw && ws.pwmode;      // walk this window in parallel (uniform: written before the last barrier)
       const bool restage = first || window_clobbered || (wend0 < nsym && wend0 - ipos < IN_N / 2);
       window_clobbered = false;
       __syncthreads();
@@ -179,9 +201,27 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
           const unsigned sv = __ldg(st + a0 + i);
           s_in[i] = tab_in_smem ? s_tab[sv] : __ldg(Sy + sv);
         }
-        if (tid == 0) { ws.wbase = a0; ws.wend = a0 + nb; }
+        if (tid == 0) { ws.wbase = a0; ws.wend = a0 + nb; ws.mdirty = 1; }
       }
       __syncthreads();
+      if (pwm && restage) {
+        // ---- speculative header chains, one part of the window per warp ----
+        const int wlen = ws.wend - ws.wbase;
+        const int pbase = warp * SW, pend = min(pbase + SW, wlen);
+        int p = pbase;
+        for (int blk = pbase; blk < pbase + SW; blk += 32) {
+          const unsigned cl = blk + lane < wlen ? (unsigned)s_in[blk + lane] : 1u;
+          unsigned mbits = 0;
+          while (p < blk + 32 && p < pend) {
+            const unsigned c = __shfl_sync(0xffffffffu, cl, p - blk);
+            mbits |= 1u << (p - blk);
+            p += (c == 0u || c <= mid) ? 2 : 1 + (int)(c - mid);
+          }
+          if (lane == 0) s_spec[blk >> 5] = mbits;
+        }
+        if (lane == 0) s_exit[warp] = p;
+        __syncthreads();
+      }
       // Destination-aligned layout: element o of the chunk sits at se[o] = s_e_raw[ph + o]; for spatial units ph makes
       // (index in s_e_raw) == (pixel index + align0) mod 8, so aligned groups of eight are aligned 16 B stores in D.
       const int skip = (spatial && first) ? 1 : 0;   // element 0 of the stream is maxValue, not a pixel
@@ -204,6 +244,166 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         }
         int nr = 0;
         bool slow_once = false;
+        int hseen = ws.hseen;
+        if (pwm) {
+          const int wlen = we - wb;
+          int hidx = ws.hidx, hcount = ws.hcount;
+          // ---- stitch the true header chain of the window (once per restage) ----
+          if (ws.mdirty) {
+            for (int i = lane; i < IN_N / 32; i += 32) s_hdr[i] = 0;
+            __syncwarp();
+            int cur = ip + ((c_rem > 0 && kind == 1) ? (int)c_rem : 0) - wb;    // the next header (after a carried diff-run)
+            while (cur < wlen) {
+              if ((s_spec[cur >> 5] >> (cur & 31)) & 1u) {
+                const int k = cur / SW;
+                const int w0 = cur >> 5, w1 = (k + 1) * SW / 32;
+                for (int wi = w0 + lane; wi < w1; wi += 32) {
+                  unsigned wv = s_spec[wi];
+                  if (wi == w0) wv &= ~0u << (cur & 31);
+                  s_hdr[wi] |= wv;
+                }
+                __syncwarp();
+                cur = s_exit[k];
+              } else {
+                if (lane == 0) s_hdr[cur >> 5] |= 1u << (cur & 31);
+                __syncwarp();
+                const unsigned c = s_in[cur];
+                cur += (c == 0u || c <= mid) ? 2 : 1 + (int)(c - mid);
+              }
+            }
+            __syncwarp();
+            // the headers in order: lane = mask word, positions by a scan over the word populations
+            int total = 0;
+            for (int wb32 = 0; wb32 < IN_N / 32; wb32 += 32) {
+              unsigned mw = s_hdr[wb32 + lane];
+              const int cnt = __popc(mw);
+              int inc2 = cnt;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc2, d);
+                if (lane >= d) inc2 += t;
+              }
+              int o2 = total + inc2 - cnt;
+              while (mw) {
+                s_hpos[o2++] = (uint16_t)((wb32 + lane) * 32 + (__ffs(mw) - 1));
+                mw &= mw - 1u;
+              }
+              total += __shfl_sync(0xffffffffu, inc2, 31);
+            }
+            __syncwarp();
+            hcount = total;
+            hidx = 0;
+            if (lane == 0) ws.mdirty = 0;
+          }
+          // ---- the carried run (a chunk ended inside it) ----
+          if (c_rem > 0 && o < budget) {
+            int take = (int)min(c_rem, (unsigned)(budget - o));
+            int src = -(int)(value + 1u);
+            bool ok = true;
+            if (kind == 1) {
+              const int avail = we - ip;
+              if (avail <= 0) {
+                if (ip >= nsym) { err = 1; done = 1; }
+                ok = false;
+              } else {
+                take = min(take, avail);
+                src = ip - wb;
+                ip += take;
+              }
+            }
+            if (ok) {
+              if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = src; }
+              nr++;
+              o += take;
+              c_rem -= (unsigned)take;
+            }
+          }
+          // ---- headers, 32 at a time ----
+          while (!done && c_rem == 0 && o < budget && nr + 32 <= MAXR) {
+            if (ip >= nsym) { done = 1; break; }
+            const int hp = ip - wb;
+            if (hp >= wlen) break;                                        // the next header lies beyond the window: restage
+            if (hidx >= hcount || (int)s_hpos[hidx] != hp) { err = 1; done = 1; break; }   // cannot happen: ip is on the listed chain
+            const int n = min(32, hcount - hidx);
+            const bool valid = lane < n;
+            const int pos = valid ? (int)s_hpos[hidx + lane] : 0;
+            const unsigned c = valid ? (unsigned)s_in[pos] : 1u;
+            const bool same = c <= mid;
+            const int len = same ? (int)c : (int)(c - mid);
+            const int apos = wb + pos;
+            const bool bad = valid && (c == 0u || apos + 1 >= nsym);      // zero count, or a header that ends the stream
+            const bool needre = valid && !bad && pos + 1 >= wlen;         // its value / payload starts beyond the window
+            const int avail = same ? len : min(len, max(wlen - (pos + 1), 0));
+            const unsigned v = (valid && same && pos + 1 < wlen) ? (unsigned)s_in[pos + 1] : 0u;
+            int inc = valid ? avail : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, inc, d);
+              if (lane >= d) inc += t;
+            }
+            const int excl = inc - (valid ? avail : 0);
+            const int room = budget - o;
+            const bool cut = valid && !same && len > avail;               // payload cut by the end of the window
+            const bool over = valid && inc > room;
+            const unsigned stopm = __ballot_sync(0xffffffffu, bad || needre || cut || over);
+            const int f = stopm ? __ffs(stopm) - 1 : n;                   // lanes below f are emitted whole
+            int take = lane < f ? avail : 0;
+            // the stopping header: what the reference decoder would do with it at this point
+            const int f_s = f < 32 ? f : 31;
+            const int fbad = __shfl_sync(0xffffffffu, (int)bad, f_s), fneed = __shfl_sync(0xffffffffu, (int)needre, f_s);
+            const int fexcl = __shfl_sync(0xffffffffu, excl, f_s), favail = __shfl_sync(0xffffffffu, avail, f_s);
+            const int flen = __shfl_sync(0xffffffffu, len, f_s), fsame = __shfl_sync(0xffffffffu, (int)same, f_s);
+            const int fpos = __shfl_sync(0xffffffffu, pos, f_s);
+            const unsigned fv = __shfl_sync(0xffffffffu, v, f_s);
+            bool stop = f < n;
+            int ftake = 0;
+            if (stop && !fbad && !fneed) ftake = min(favail, room - fexcl);      // partial run: the budget or the window cut it
+            if (lane == f && ftake > 0) take = ftake;
+            // ---- emit: short runs by their lane, long ones on the run list ----
+            const int olane = o + excl;
+            const bool emit = take > 0;
+            const bool longr = emit && take > 16;
+            const unsigned longm = __ballot_sync(0xffffffffu, longr);
+            if (longr) {
+              const int slot = nr + __popc(longm & ((1u << lane) - 1u));
+              s_run_o[slot] = (uint16_t)olane; s_run_n[slot] = (uint16_t)take;
+              s_run_src[slot] = same ? -(int)(v + 1u) : pos + 1;
+            } else if (emit) {
+              if (same) {
+                for (int j = 0; j < take; j++) se[olane + j] = (uint16_t)v;
+              } else {
+                for (int j = 0; j < take; j++) se[olane + j] = s_in[pos + 1 + j];
+              }
+            }
+            nr += __popc(longm);
+            // totals and the position after the last whole run
+            const int nwhole = f;
+            int tot = 0, ipn = ip;
+            if (nwhole > 0) {
+              tot = __shfl_sync(0xffffffffu, inc, nwhole - 1);
+              const int lpos = __shfl_sync(0xffffffffu, pos, nwhole - 1), llen = __shfl_sync(0xffffffffu, len, nwhole - 1);
+              const int lsame = __shfl_sync(0xffffffffu, (int)same, nwhole - 1);
+              ipn = wb + lpos + (lsame ? 2 : 1 + llen);
+            }
+            o += tot;
+            ip = ipn;
+            hidx += nwhole;
+            if (stop) {
+              if (fbad) { err = 1; done = 1; break; }
+              if (fneed) break;                                            // ip is that header: the restage brings its payload
+              hidx++;                                                      // the partial run's header is consumed
+              // partial (possibly empty) piece of run f
+              o += ftake;
+              c_rem = (unsigned)(flen - ftake);
+              kind = fsame ? 0 : 1;
+              value = fv;
+              ip = wb + fpos + (fsame ? 2 : 1 + ftake);
+              break;
+            }
+          }
+          hseen = hidx;
+          if (lane == 0) { ws.hidx = hidx; ws.hcount = hcount; }
+        } else
         while (o < budget && nr < MAXR) {
           // Long-run path: headers whose run is longer than 32 elements are followed one by one with uniform (broadcast)
           // loads -- one shared-memory load and a dozen instructions per header, ~70 cycles against ~200 for the
@@ -218,7 +418,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
               const unsigned v = s_in[ip + 1 - wb];
               const int take = min((int)c, room);
               if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = -(int)(v + 1u); }
-              nr++; o += take; ip += 2;
+              nr++; o += take; ip += 2; hseen++;
               if (take < (int)c) { c_rem = c - (unsigned)take; kind = 0; value = v; }
             } else {
               const int len = (int)(c - mid);
@@ -226,7 +426,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
               const int first = ip + 1;
               const int take = min(min(len, room), we - first);   // we - first >= 1 here
               if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = first - wb; }
-              nr++; o += take;
+              nr++; o += take; hseen++;
               if (take < len) { c_rem = (unsigned)(len - take); kind = 1; ip += 1 + take; }
               else ip += 1 + len;
             }
@@ -255,7 +455,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
                   if (lane == 0) { s_run_o[nr] = (uint16_t)o; s_run_n[nr] = (uint16_t)take; s_run_src[nr] = -(int)(v + 1u); }
                   nr++;
                 }
-                o += take; p += 2;
+                o += take; p += 2; hseen++;
                 if (take < (int)c) { c_rem = c - (unsigned)take; kind = 0; value = v; stop = true; }
               } else {
                 const int len = (int)(c - mid);
@@ -268,6 +468,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
                   nr++;
                 }
                 o += take;
+                hseen++;
                 if (take < len) { c_rem = (unsigned)(len - take); kind = 1; p += 1 + take; stop = true; }
                 else p += 1 + len;
               }
@@ -285,9 +486,9 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
               if (c == 0 || ip + 1 >= nsym) { err = 1; done = 1; break; }
               if (ip + 1 >= we) break;
               value = s_in[ip + 1 - wb];
-              kind = 0; c_rem = c; ip += 2;
+              kind = 0; c_rem = c; ip += 2; hseen++;
             } else {
-              kind = 1; c_rem = c - mid; ip += 1;
+              kind = 1; c_rem = c - mid; ip += 1; hseen++;
             }
           }
           int take = (int)min(c_rem, (unsigned)(budget - o));
@@ -313,6 +514,13 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
         if (lane == 0) {
           ws.ipos = ip; ws.c_rem = c_rem; ws.kind = kind; ws.value = value;
           ws.nout = o; ws.nruns = nr; ws.done = done; ws.err = err;
+          if (PW && use_pw) {
+            // the next iteration restages (same predicate as at its top): choose how the new window is walked from the
+            // header density of the stretch just consumed -- a header every <= 16 symbols pays for the parallel walk
+            // (residual frames: one every ~5), fewer do not (wavelet streams, tile planes, strips)
+            if (we < nsym && we - ip < IN_N / 2) { ws.pwmode = hseen >= IN_N / 32 ? 1 : 0; ws.hseen = 0; }
+            else ws.hseen = hseen;
+          }
         }
       }
       __syncthreads();
@@ -588,12 +796,12 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
   }
 }
 
-template <int THREADS, int CHUNK>
+template <int THREADS, int CHUNK, bool PW = false>
 static void launch_rle_expand_t(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS, uint16_t* d_D,
                                 uint32_t* d_M, uint16_t* d_out, int tab_log, int grid, unsigned int* d_queue, cudaStream_t st) {
   const size_t smem = (size_t)2 << tab_log;
-  cudaFuncSetAttribute(k_rle_expand<THREADS, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_rle_expand<THREADS, CHUNK><<<grid, THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue, ubase);
+  cudaFuncSetAttribute(k_rle_expand<THREADS, CHUNK, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_rle_expand<THREADS, CHUNK, PW><<<grid, THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue, ubase);
 }
 
 void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,
@@ -611,6 +819,9 @@ void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* 
     case 2: launch_rle_expand_t<128, 2048>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 2), d_queue, st); break;
     case 3: launch_rle_expand_t<64, 2048>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 4), d_queue, st); break;
     case 4: launch_rle_expand_t<64, 1024>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 4), d_queue, st); break;
+    // parallel header walk (run-heavy streams)
+    case 5: launch_rle_expand_t<256, 4096, true>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, grid, d_queue, st); break;
+    case 6: launch_rle_expand_t<128, 2048, true>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, std::min(nunits, grid * 2), d_queue, st); break;
     default: launch_rle_expand_t<256, 4096>(d_units, ubase, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, grid, d_queue, st); break;
   }
 }

@@ -70,6 +70,7 @@ struct micgpu_decoder {
   unsigned long long sym_total = 0, tab_total = 0, d_total = 0, m_total = 0, out_need = 0;
   int max_log_all = 5, max_w = 1, max_h = 1;
   int n_grad = 0;             // spatial units coded with the gradient-adaptive predictor
+  int n_rle = 0;              // RLE-kind units (temporal residual frames, wavelet coefficient streams)
   int k1_grid = 1;
   unsigned long long k1_stride = 0;
   bool committed = false;
@@ -143,6 +144,7 @@ int plan_commit(micgpu_decoder* d) {
   d->max_log_all = 5;
   d->max_w = d->max_h = 1;
   d->n_grad = 0;
+  d->n_rle = 0;
   for (auto& l : d->lists) l.clear();
   d->spatial.clear();
   for (size_t i = 0; i < d->units.size(); i++) {
@@ -171,6 +173,7 @@ int plan_commit(micgpu_decoder* d) {
       d->max_h = std::max(d->max_h, (int)u.height);
     } else {
       u.wp = 0; u.d_off = 0; u.m_off = 0;
+      if (u.kind == MIC_KIND_RLE) d->n_rle++;
     }
     d->lists[nstates_index(u.nstates)].push_back((int)i);
     d->out_need = std::max(d->out_need, u.out_off + px);
@@ -412,7 +415,11 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
   // K3 launch shape (k_rle.cu): small tables mean 8-bit planes (MIC3 tiles), whose run headers come every <= 124 symbols:
   // the header walk of one warp is the bound there, and CTAs of 128 threads / 2048-element chunks put 2.4x the walkers
   // on an SM (measured on 4096 tiles: K3 1.86 -> 1.45 ms; strips lose 10 % with it, profiles/README.md)
-  const int k3_shape = d->max_log_all <= 12 ? 2 : 0;
+  // Plans with RLE-kind units (residual frames, wavelet streams) take the kernel that can walk a window's run headers in
+  // parallel (shape 5; chosen per window from the header density: residual frames have a header every ~5 symbols and
+  // their K3 time falls from 224 to 44 ms per stack, wavelet streams and spatial frames stay on the one-warp walk).
+  // Tile planes measured slightly slower with it (1.53 against 1.44 ms per 4096 tiles) and keep shape 2.
+  const int k3_shape = d->max_log_all <= 12 ? 2 : (d->n_rle ? 5 : 0);
   // CTAs of K3 per SM when unit ranges overlap on their own streams: K3 is a persistent queue kernel, so fewer CTAs leave
   // registers for the K4 CTAs of the previous range to co-reside (MICGPU_K3_CPS for A/B runs)
   static const bool k3_chain = [] { const char* e = getenv("MICGPU_K3_CHAIN"); return e && e[0] == '1'; }();

@@ -77,7 +77,7 @@ template <int THREADS, int CHUNK, bool PW>
 __global__ void __launch_bounds__(THREADS, K3Shape<THREADS, CHUNK>::MINB)
 k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict__ states,
              const uint16_t* __restrict__ tabS, uint16_t* __restrict__ D, uint32_t* __restrict__ M,
-             uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue, int ubase) {
+             uint16_t* __restrict__ out, int tab_smem_log, unsigned int* __restrict__ queue, int ubase, int pw_min_headers) {
   using SH = K3Shape<THREADS, CHUNK>;
   constexpr int K3_THREADS = SH::K3_THREADS, K3_WARPS = SH::K3_WARPS, IN_N = SH::IN_N, OUT_CH = SH::OUT_CH, NWIN = SH::NWIN,
                 WPL = SH::WPL, MAXR = SH::MAXR;
@@ -518,7 +518,7 @@ k_rle_expand(MicUnit* __restrict__ units, int nunits, const uint16_t* __restrict
             // the next iteration restages (same predicate as at its top): choose how the new window is walked from the
             // header density of the stretch just consumed -- a header every <= 16 symbols pays for the parallel walk
             // (residual frames: one every ~5), fewer do not (wavelet streams, tile planes, strips)
-            if (we < nsym && we - ip < IN_N / 2) { ws.pwmode = hseen >= IN_N / 32 ? 1 : 0; ws.hseen = 0; }
+            if (we < nsym && we - ip < IN_N / 2) { ws.pwmode = hseen >= pw_min_headers ? 1 : 0; ws.hseen = 0; }
             else ws.hseen = hseen;
           }
         }
@@ -801,7 +801,10 @@ static void launch_rle_expand_t(MicUnit* d_units, int ubase, int nunits, const u
                                 uint32_t* d_M, uint16_t* d_out, int tab_log, int grid, unsigned int* d_queue, cudaStream_t st) {
   const size_t smem = (size_t)2 << tab_log;
   cudaFuncSetAttribute(k_rle_expand<THREADS, CHUNK, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_rle_expand<THREADS, CHUNK, PW><<<grid, THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue, ubase);
+  // headers per consumed stretch (about half a window) from which a window is walked in parallel: one per 16 symbols
+  static const int pw_div = [] { const char* e = getenv("MICGPU_PW_DIV"); int v = e ? atoi(e) : 32; return v < 1 ? 1 : v; }();
+  k_rle_expand<THREADS, CHUNK, PW><<<grid, THREADS, smem, st>>>(d_units, nunits, d_states, d_tabS, d_D, d_M, d_out, tab_log, d_queue, ubase,
+                                                                  CHUNK / pw_div);
 }
 
 void launch_rle_expand(MicUnit* d_units, int ubase, int nunits, const uint16_t* d_states, const uint16_t* d_tabS,

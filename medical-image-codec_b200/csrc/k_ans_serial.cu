@@ -60,7 +60,8 @@ __device__ __forceinline__ void serial_refill(int P, int& cross, uint32_t& ra, u
       : "memory");
 }
 
-// FMT: 0 = 4-byte cells, 1 = 2-byte nextState cells (+ bit 16 in a bit array when L16), 2 = 2-byte direct cells
+// FMT: 0 = 4-byte cells, 1 = 2-byte nextState cells (+ bit 16 in a bit array when L16), 2 = 2-byte direct cells,
+// 3 = split cells (u16 newState array + u8 nbBits array: 3 bytes per cell)
 template <int FMT, bool L16>
 struct Cells {
   const uint8_t* tab;
@@ -75,9 +76,15 @@ struct Cells {
       if (L16) nx |= ((flags[st >> 5] >> (st & 31u)) & 1u) << 16;
       nb = L - (31u - __clz(nx));   // nextState >= 1 (K1)
       ns = (nx << nb) - S;
-    } else {
+    } else if (FMT == 2) {
       const uint32_t e = reinterpret_cast<const uint16_t*>(tab)[st];
       nb = e & 15u; ns = (e >> 4) << nb;
+    } else {
+      // split cells: newState (< 2^16 even for tableLog 16) in a u16 array, nbBits in a u8 array behind it -- two
+      // independent loads and nothing to compute, where the 2-byte nextState format needs a flag word, a shift and a
+      // find-leading-one on the state chain (157 against 112 cycles per round on tableLog-16 residual frames)
+      ns = reinterpret_cast<const uint16_t*>(tab)[st];
+      nb = (tab + ((size_t)2 << L))[st];
     }
   }
 };
@@ -260,7 +267,7 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
 
 }  // namespace
 
-// mode: 0 = 4-byte cells, 1 = 2-byte cells.  The host cuts the unit list into SEGMENTS (first index, count) whose tables
+// mode: 0 = 4-byte cells, 1 = 2-byte cells, 3 = split cells.  The host cuts the unit list into SEGMENTS (first index, count) whose tables
 // and rings fit one CTA together; slot_off[i] is the byte offset of list entry i inside its segment's shared memory
 // (table, then -- tableLog 16 in 2-byte cells -- the bit array, then the ring).  Tables of different sizes share a
 // CTA, so a batch of 4 KB and 8 KB tables (MIC3 luma / chroma planes) fills shared memory instead of paying the
@@ -289,6 +296,14 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, c
       if (mode == 0) {
         uint4* T4 = reinterpret_cast<uint4*>(T);
         for (uint32_t i = tid; i < S / 4; i += blockDim.x) T4[i] = __ldg(A4 + i);
+      } else if (mode == 3) {
+        uint2* T2 = reinterpret_cast<uint2*>(T);
+        uint32_t* T1 = reinterpret_cast<uint32_t*>(T + ((size_t)2 << L));
+        for (uint32_t i = tid; i < S / 4; i += blockDim.x) {
+          const uint4 e = __ldg(A4 + i);
+          T2[i] = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
+          T1[i] = (e.x >> 16) | ((e.y >> 16) << 8) | ((e.z >> 16) << 16) | ((e.w >> 16) << 24);
+        }
       } else {
         // direct cells (k_ans.cu:469-472): valid while newState >> nbBits < 4096 and tableLog <= 15
         uint2* T2 = reinterpret_cast<uint2*>(T);
@@ -342,11 +357,12 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, c
       if (U->status == MIC_OK) {
         const uint32_t L = U->table_log;
         const uint8_t* mytab = smem + slot_off[base + slot];
-        const size_t cells = (size_t)(mode == 0 ? 4 : 2) << L;
+        const size_t cells = mode == 3 ? (size_t)3 << L : (size_t)(mode == 0 ? 4 : 2) << L;
         const uint32_t* myflags = reinterpret_cast<const uint32_t*>(mytab + cells);
         const size_t fl = (mode == 1 && L > 15) ? (1u << 16) / 8 : 0;
         uint32_t* ring = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(mytab) + cells + fl);
         if (mode == 0) decode_unit<N, 0, false>(U, comp, states_out, mytab, myflags, ring);
+        else if (mode == 3) decode_unit<N, 3, false>(U, comp, states_out, mytab, myflags, ring);
         else if (d16) decode_unit<N, 2, false>(U, comp, states_out, mytab, myflags, ring);
         else if (l16 && L > 15) decode_unit<N, 1, true>(U, comp, states_out, mytab, myflags, ring);
         else decode_unit<N, 1, false>(U, comp, states_out, mytab, myflags, ring);
@@ -357,6 +373,7 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, c
 
 // shared-memory bytes of one unit: cells, the bit array for bit 16 of nextState (tableLog 16 in 2-byte cells), the ring
 size_t ans_serial_unit_bytes(int table_log, int mode) {
+  if (mode == 3) return ((size_t)3 << table_log) + SRING_STRIDE * 4;
   size_t t = (size_t)(1u << table_log) * (mode == 0 ? 4 : 2);
   if (mode == 1 && table_log == 16) t += (1u << 16) / 8;
   return t + SRING_STRIDE * 4;

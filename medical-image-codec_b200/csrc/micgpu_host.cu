@@ -211,7 +211,11 @@ int plan_commit(micgpu_decoder* d) {
         return s;
       };
       const int want = std::min(need_per_sm, 128);
-      const int smode = fit_s(0) >= want ? 0 : 1;   // 2-byte cells hold twice the units per SM
+      // 2-byte cells hold twice the units per SM; tableLog 16 does not fit 4-byte cells at all (256 KB) and its 2-byte
+      // form needs a flag word and a find-leading-one per lookup: one unit per SM either way, so it takes the split
+      // cells (192 KB) -- MICGPU_K2S_SPLITCELLS=0 keeps the 2-byte form
+      static const bool split_ok = [] { const char* e = getenv("MICGPU_K2S_SPLITCELLS"); return !(e && e[0] == '0'); }();
+      const int smode = fit_s(0) >= want ? 0 : ((ml == 16 && split_ok && fit_s(3) >= 1) ? 3 : 1);
       const int f = fit_s(smode);
       if (f >= 1) {
         a.serial = true;

@@ -67,23 +67,25 @@ struct Cells {
   const uint8_t* tab;
   const uint32_t* flags;
   uint32_t L, S;
-  __device__ __forceinline__ void get(uint32_t st, uint32_t& nb, uint32_t& ns) const {
+  // -> nbBits and h = newState >> nbBits (newState is a multiple of 2^nbBits): the next state is (h << nb) | field, which
+  // one funnel shift forms from h and the 32 stream bits that end where the field ends (decode_unit)
+  __device__ __forceinline__ void get(uint32_t st, uint32_t& nb, uint32_t& h) const {
     if (FMT == 0) {
       const uint32_t e = reinterpret_cast<const uint32_t*>(tab)[st];
-      nb = e >> 16; ns = e & 0xFFFFu;
+      nb = e >> 16; h = (e & 0xFFFFu) >> nb;
     } else if (FMT == 1) {
       uint32_t nx = reinterpret_cast<const uint16_t*>(tab)[st];
       if (L16) nx |= ((flags[st >> 5] >> (st & 31u)) & 1u) << 16;
       nb = L - (31u - __clz(nx));   // nextState >= 1 (K1)
-      ns = (nx << nb) - S;
+      h = nx - (S >> nb);           // ((nx << nb) - S) >> nb
     } else if (FMT == 2) {
       const uint32_t e = reinterpret_cast<const uint16_t*>(tab)[st];
-      nb = e & 15u; ns = (e >> 4) << nb;
+      nb = e & 15u; h = e >> 4;
     } else {
-      // split cells: newState (< 2^16 even for tableLog 16) in a u16 array, nbBits in a u8 array behind it -- two
-      // independent loads and nothing to compute, where the 2-byte nextState format needs a flag word, a shift and a
+      // split cells: h (< 2^16 even for tableLog 16) in a u16 array, nbBits in a u8 array behind it -- two independent
+      // loads and nothing to compute, where the 2-byte nextState format needs a flag word, a shift and a
       // find-leading-one on the state chain (157 against 112 cycles per round on tableLog-16 residual frames)
-      ns = reinterpret_cast<const uint16_t*>(tab)[st];
+      h = reinterpret_cast<const uint16_t*>(tab)[st];
       nb = (tab + ((size_t)2 << L))[st];
     }
   }
@@ -144,27 +146,44 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
   uint16_t* out = states_out + U->sym_off;
   uint32_t nsym = 0;
 
-  // Window of NW registers loaded once per group of symbols that consume at most 32 * (NW - 1) bits: the top word
-  // holds bit P-1, so P sits at Pb in (32 (NW-1), 32 NW] and every field of the group lies inside the window.
-  constexpr int NW = N == 4 ? 3 : 2;
-  uint32_t W0 = 0, W1 = 0, W2 = 0, Pb = 0;
+  // Sliding two-word window in registers: W1 holds bit P-1, so P sits at Pb in (32, 64] and the fields of a step of at
+  // most 32 bits lie inside it.  After a step the window moves down by one word if the top word is used up; the word
+  // below it (WN) was loaded a step earlier, so no shared-memory load sits between the bit position of one step and the
+  // fields of the next (reloading the window from the ring at every round put an address computation and a load --
+  // ~45 cycles -- on exactly that chain).
+  constexpr int NW = 2;
+  uint32_t W0 = 0, W1 = 0, W2 = 0, WN = 0, Pb = 0, wlw = 0;
+  const uint32_t* ringw = reinterpret_cast<const uint32_t*>(ringb);
   auto load_window = [&]() {
-    const uint32_t wl = (((uint32_t)(P - 1)) >> 5) - (uint32_t)(NW - 1);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + ((wl & 31u) << 2));
-    W0 = w[0]; W1 = w[1];
-    if (NW == 3) W2 = w[2];
-    Pb = (uint32_t)P - (wl << 5);
+    wlw = (((uint32_t)(P - 1)) >> 5) - 1u;
+    W0 = ringw[wlw & 31u]; W1 = ringw[(wlw + 1u) & 31u];
+    WN = ringw[(wlw - 1u) & 31u];
+    Pb = (uint32_t)P - (wlw << 5);
   };
-  auto field = [&](uint32_t lo, uint32_t nb) -> uint32_t {
-    uint32_t a, b;
+  auto slide = [&]() {
+    const bool sl = Pb <= 32u;
+    W1 = sl ? W0 : W1;
+    W0 = sl ? WN : W0;
+    wlw -= sl ? 1u : 0u;
+    Pb += sl ? 32u : 0u;
+    WN = ringw[(wlw - 1u) & 31u];
+  };
+  // The 32 stream bits that end at window position `prev` (exclusive): a field of nb bits read there is the top nb bits of
+  // this word, so it does not depend on nb -- it is formed while the table lookup is still in flight, and the next state
+  // is ONE funnel shift away from the cell: (h : word) << nb, high half.  (The state chain used to run
+  // lookup -> nb -> position -> select -> shift -> mask -> add.)
+  auto top_word = [&](uint32_t prev) -> uint32_t {
+    const uint32_t t = prev - 1u;
+    uint32_t hi_w, lo_w;
     if (NW == 2) {
-      a = (lo & 32u) ? W1 : W0; b = W1;
+      hi_w = (t & 32u) ? W1 : W0; lo_w = (t & 32u) ? W0 : 0u;
     } else {
-      a = (lo & 64u) ? W2 : ((lo & 32u) ? W1 : W0);
-      b = (lo & 32u) ? W2 : W1;
+      hi_w = (t & 64u) ? W2 : ((t & 32u) ? W1 : W0);
+      lo_w = (t & 64u) ? W1 : ((t & 32u) ? W0 : 0u);
     }
-    return __funnelshift_r(a, b, lo) & ((1u << nb) - 1u);
+    return __funnelshift_l(lo_w, hi_w, 0u - prev);   // (hi : lo) << ((32 - prev mod 32) mod 32), high half
   };
+  auto next_state = [&](uint32_t word, uint32_t h, uint32_t nb) -> uint32_t { return __funnelshift_l(word, h, nb); };
 
   if (N == 1) {
     // 1-state: no symbol count; the stream ends when the bits do (fsedecompressu16.go:351-376)
@@ -172,27 +191,32 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
     uint32_t s0 = st[0];
     // 16 symbols (<= 256 bits) per ring check, two per window; cannot reach the end of the bits inside the group
     while (!err && P - shift > 256 && nsym + 16 <= cap) {
+      load_window();
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        load_window();
-        uint32_t nb, ns;
-        cells.get(s0, nb, ns);
+        uint32_t nb, h;
+        uint32_t prev = Pb;
+        uint32_t word = top_word(prev);
+        cells.get(s0, nb, h);
         const uint32_t e0 = s0;
-        uint32_t lo = Pb - nb;
-        s0 = ns + field(lo, nb);
-        cells.get(s0, nb, ns);
+        s0 = next_state(word, h, nb);
+        prev -= nb;
+        word = top_word(prev);
+        cells.get(s0, nb, h);
         const uint32_t e1 = s0;
-        lo -= nb;
-        s0 = ns + field(lo, nb);
+        s0 = next_state(word, h, nb);
+        prev -= nb;
         *reinterpret_cast<uint32_t*>(out + nsym) = e0 | (e1 << 16);
         nsym += 2;
-        P -= (int)(Pb - lo);
+        P -= (int)(Pb - prev);
+        Pb = prev;
+        slide();
       }
       refill();
     }
     while (!err) {
-      uint32_t nb, ns;
-      cells.get(s0, nb, ns);
+      uint32_t nb, h;
+      cells.get(s0, nb, h);
       if (P == shift && nb > 0) {        // decoderU16.finished()
         if (s0 != 0) {
           if (nsym >= cap) { err = 2; break; }
@@ -203,7 +227,7 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
       if (nsym >= cap) { err = 2; break; }
       out[nsym++] = (uint16_t)s0;
       if ((uint32_t)(P - shift) < nb) { err = 1; break; }   // partial over-read -> io.ErrUnexpectedEOF
-      s0 = ns + extract(P - (int)nb, nb);
+      s0 = (h << nb) + extract(P - (int)nb, nb);
       P -= (int)nb;
       refill();
     }
@@ -213,26 +237,31 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
     const uint32_t full = err ? 0u : count / N;
     // one round = N symbols in stream order A, B, ...: emit the current states, then move each one
     auto round_win = [&](uint16_t* op) {
-      load_window();
-      uint32_t nb[N], ns[N];
+      uint32_t nb[N], h[N];
 #pragma unroll
-      for (int k = 0; k < N; k++) cells.get(st[k], nb[k], ns[k]);
+      for (int k = 0; k < N; k++) cells.get(st[k], nb[k], h[k]);
       if (N == 2) {
         *reinterpret_cast<uint32_t*>(op) = st[0] | (st[1] << 16);
       } else {
         *reinterpret_cast<uint2*>(op) = make_uint2(st[0] | (st[1] << 16), st[2] | (st[3] << 16));
       }
-      uint32_t lo = Pb;
+      uint32_t prev = Pb;
 #pragma unroll
       for (int k = 0; k < N; k++) {
-        lo -= nb[k];
-        st[k] = ns[k] + field(lo, nb[k]);
+        st[k] = next_state(top_word(prev), h[k], nb[k]);
+        prev -= nb[k];
+        if ((k & 1) == 1 || k == N - 1) {      // at most 32 bits since the last slide
+          P -= (int)(Pb - prev);
+          Pb = prev;
+          slide();
+          prev = Pb;
+        }
       }
-      P -= (int)(Pb - lo);
     };
     constexpr uint32_t RPC = 16 / N;    // rounds per ring check: RPC * N * 16 = 256 bits
     uint32_t r = 0;
     uint16_t* op = out;
+    load_window();
     for (; r + RPC <= full; r += RPC) {
 #pragma unroll
       for (uint32_t j = 0; j < RPC; j++) round_win(op + j * N);
@@ -250,8 +279,8 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
 #pragma unroll
       for (int k = 0; k < N; k++) {
         if ((uint32_t)k < tail) {
-          uint32_t nb, ns;
-          cells.get(st[k], nb, ns);
+          uint32_t nb, h;
+          cells.get(st[k], nb, h);
           op[k] = (uint16_t)st[k];
           P -= (int)nb;
         }
@@ -301,7 +330,9 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, c
         uint32_t* T1 = reinterpret_cast<uint32_t*>(T + ((size_t)2 << L));
         for (uint32_t i = tid; i < S / 4; i += blockDim.x) {
           const uint4 e = __ldg(A4 + i);
-          T2[i] = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
+          const uint32_t h0 = (e.x & 0xFFFFu) >> (e.x >> 16), h1 = (e.y & 0xFFFFu) >> (e.y >> 16);
+          const uint32_t h2 = (e.z & 0xFFFFu) >> (e.z >> 16), h3 = (e.w & 0xFFFFu) >> (e.w >> 16);
+          T2[i] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
           T1[i] = (e.x >> 16) | ((e.y >> 16) << 8) | ((e.z >> 16) << 16) | ((e.w >> 16) << 24);
         }
       } else {

@@ -146,44 +146,45 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
   uint16_t* out = states_out + U->sym_off;
   uint32_t nsym = 0;
 
-  // Sliding two-word window in registers: W1 holds bit P-1, so P sits at Pb in (32, 64] and the fields of a step of at
-  // most 32 bits lie inside it.  After a step the window moves down by one word if the top word is used up; the word
-  // below it (WN) was loaded a step earlier, so no shared-memory load sits between the bit position of one step and the
-  // fields of the next (reloading the window from the ring at every round put an address computation and a load --
-  // ~45 cycles -- on exactly that chain).
-  constexpr int NW = 2;
-  uint32_t W0 = 0, W1 = 0, W2 = 0, WN = 0, Pb = 0, wlw = 0;
+  // Bit buffer in registers, top aligned: the next unread stream bit is bit 31 of BH, `cnt` bits of BH:BL are valid
+  // (kept in (32, 64] between steps of at most 32 bits), the word below the buffer (WN, stream word `wn`) is loaded a step
+  // before it is appended.  A field of nb bits is then simply the top nb bits of BH, so
+  //   * the next state is ONE funnel shift away from the table cell: (h : BH) << nb, high half, with h = newState >> nb
+  //     (the chain used to run lookup -> nb -> position -> select -> shift -> mask -> add);
+  //   * consuming a field is one funnel shift and one shift; no position arithmetic, no word select;
+  //   * no shared-memory load sits between the fields of one step and those of the next (reloading a window from the
+  //     ring at every round put an address computation and a load on exactly that chain).
+  // The bit position is implicit: P = 32 (wn + 1) + cnt; it is materialised for the ring checks only.
+  uint32_t BH = 0, BL = 0, WN = 0, cnt = 0, wn = 0;
   const uint32_t* ringw = reinterpret_cast<const uint32_t*>(ringb);
-  auto load_window = [&]() {
-    wlw = (((uint32_t)(P - 1)) >> 5) - 1u;
-    W0 = ringw[wlw & 31u]; W1 = ringw[(wlw + 1u) & 31u];
-    WN = ringw[(wlw - 1u) & 31u];
-    Pb = (uint32_t)P - (wlw << 5);
+  auto buf_load = [&]() {                       // from P
+    const uint32_t wtop = ((uint32_t)(P - 1)) >> 5;
+    const uint32_t r = (uint32_t)P - (wtop << 5);                 // valid bits of the top word, 1..32
+    const uint32_t wt = ringw[wtop & 31u], wb = ringw[(wtop - 1u) & 31u];
+    BH = __funnelshift_l(wb, wt, 32u - r);                         // (wt : wb) << (32 - r), high half
+    BL = wb << ((32u - r) & 31u);
+    if (r == 32u) BL = wb;
+    cnt = r + 32u;
+    wn = wtop - 2u;
+    WN = ringw[wn & 31u];
   };
-  auto slide = [&]() {
-    const bool sl = Pb <= 32u;
-    W1 = sl ? W0 : W1;
-    W0 = sl ? WN : W0;
-    wlw -= sl ? 1u : 0u;
-    Pb += sl ? 32u : 0u;
-    WN = ringw[(wlw - 1u) & 31u];
+  auto buf_sync = [&]() { P = (int)(((wn + 1u) << 5) + cnt); };   // the bit position the buffer stands for
+  auto take = [&](uint32_t nb) {                                   // consume nb <= 16 bits
+    BH = __funnelshift_l(BL, BH, nb);
+    BL <<= nb;
+    cnt -= nb;
   };
-  // The 32 stream bits that end at window position `prev` (exclusive): a field of nb bits read there is the top nb bits of
-  // this word, so it does not depend on nb -- it is formed while the table lookup is still in flight, and the next state
-  // is ONE funnel shift away from the cell: (h : word) << nb, high half.  (The state chain used to run
-  // lookup -> nb -> position -> select -> shift -> mask -> add.)
-  auto top_word = [&](uint32_t prev) -> uint32_t {
-    const uint32_t t = prev - 1u;
-    uint32_t hi_w, lo_w;
-    if (NW == 2) {
-      hi_w = (t & 32u) ? W1 : W0; lo_w = (t & 32u) ? W0 : 0u;
-    } else {
-      hi_w = (t & 64u) ? W2 : ((t & 32u) ? W1 : W0);
-      lo_w = (t & 64u) ? W1 : ((t & 32u) ? W0 : 0u);
+  auto top_up = [&]() {                                            // after a step of <= 32 bits: append the word below
+    if (cnt <= 32u) {                                              // BL holds no valid bit any more (and is zero)
+      const unsigned long long add = ((unsigned long long)WN << 32) >> cnt;
+      BH |= (uint32_t)(add >> 32);
+      BL = (uint32_t)add;
+      cnt += 32u;
+      wn -= 1u;
     }
-    return __funnelshift_l(lo_w, hi_w, 0u - prev);   // (hi : lo) << ((32 - prev mod 32) mod 32), high half
+    WN = ringw[wn & 31u];
   };
-  auto next_state = [&](uint32_t word, uint32_t h, uint32_t nb) -> uint32_t { return __funnelshift_l(word, h, nb); };
+  auto next_state = [&](uint32_t h, uint32_t nb) -> uint32_t { return __funnelshift_l(BH, h, nb); };
 
   if (N == 1) {
     // 1-state: no symbol count; the stream ends when the bits do (fsedecompressu16.go:351-376)
@@ -191,27 +192,23 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
     uint32_t s0 = st[0];
     // 16 symbols (<= 256 bits) per ring check, two per window; cannot reach the end of the bits inside the group
     while (!err && P - shift > 256 && nsym + 16 <= cap) {
-      load_window();
+      buf_load();
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         uint32_t nb, h;
-        uint32_t prev = Pb;
-        uint32_t word = top_word(prev);
         cells.get(s0, nb, h);
         const uint32_t e0 = s0;
-        s0 = next_state(word, h, nb);
-        prev -= nb;
-        word = top_word(prev);
+        s0 = next_state(h, nb);
+        take(nb);
         cells.get(s0, nb, h);
         const uint32_t e1 = s0;
-        s0 = next_state(word, h, nb);
-        prev -= nb;
+        s0 = next_state(h, nb);
+        take(nb);
+        top_up();
         *reinterpret_cast<uint32_t*>(out + nsym) = e0 | (e1 << 16);
         nsym += 2;
-        P -= (int)(Pb - prev);
-        Pb = prev;
-        slide();
       }
+      buf_sync();
       refill();
     }
     while (!err) {
@@ -245,27 +242,22 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
       } else {
         *reinterpret_cast<uint2*>(op) = make_uint2(st[0] | (st[1] << 16), st[2] | (st[3] << 16));
       }
-      uint32_t prev = Pb;
 #pragma unroll
       for (int k = 0; k < N; k++) {
-        st[k] = next_state(top_word(prev), h[k], nb[k]);
-        prev -= nb[k];
-        if ((k & 1) == 1 || k == N - 1) {      // at most 32 bits since the last slide
-          P -= (int)(Pb - prev);
-          Pb = prev;
-          slide();
-          prev = Pb;
-        }
+        st[k] = next_state(h[k], nb[k]);
+        take(nb[k]);
+        if ((k & 1) == 1 || k == N - 1) top_up();      // at most 32 bits since the last one
       }
     };
     constexpr uint32_t RPC = 16 / N;    // rounds per ring check: RPC * N * 16 = 256 bits
     uint32_t r = 0;
     uint16_t* op = out;
-    load_window();
+    buf_load();
     for (; r + RPC <= full; r += RPC) {
 #pragma unroll
       for (uint32_t j = 0; j < RPC; j++) round_win(op + j * N);
       op += RPC * N;
+      buf_sync();
       refill();
       if (P < shift) break;             // over-read (corrupt stream): reads stayed inside the ring, writes inside sym_cap
     }
@@ -273,6 +265,7 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
       for (; r < full; r++) {
         round_win(op);
         op += N;
+        buf_sync();
         refill();
       }
       const uint32_t tail = err ? 0u : count - full * N;

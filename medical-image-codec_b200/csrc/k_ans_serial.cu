@@ -1,7 +1,7 @@
-// k_ans_serial.cu -- K2s: tANS decode of 1-, 2- and 4-state streams with ONE THREAD PER UNIT.
+// k_ans_serial.cu -- K2s: tANS decode of 1-, 2-, 4- and 8-state streams with ONE THREAD PER UNIT.
 //
 // Replaces decompress (fsedecompressu16.go:267-377), decompress2State (fse2state.go:203-308) and
-// decompress4State (fse4state.go:195-353) for the streams the Go API emits by default:
+// decompress4State (fse4state.go:195-353), and decompress8State (fse8state.go:230-380) for the streams the Go API emits by default:
 // CompressParallelStrips, CompressSingleFrame (MIC2 frames, MIC3 tile planes) and compressResidualFrame all
 // try the two-state coder first and fall back to the single-state one (multiframecompress.go:15-35,145-162).
 //
@@ -239,8 +239,12 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
       for (int k = 0; k < N; k++) cells.get(st[k], nb[k], h[k]);
       if (N == 2) {
         *reinterpret_cast<uint32_t*>(op) = st[0] | (st[1] << 16);
-      } else {
+      } else if (N == 4) {
         *reinterpret_cast<uint2*>(op) = make_uint2(st[0] | (st[1] << 16), st[2] | (st[3] << 16));
+      } else {
+        // sym_off is a multiple of 16 elements and op advances by whole rounds: 16 B aligned
+        *reinterpret_cast<uint4*>(op) = make_uint4(st[0] | (st[1] << 16), st[2] | (st[3] << 16), st[4 % N] | (st[5 % N] << 16),
+                                                   st[6 % N] | (st[7 % N] << 16));
       }
 #pragma unroll
       for (int k = 0; k < N; k++) {
@@ -422,7 +426,8 @@ void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, const int2* d
   };
   if (nstates == 1) go(k_ans_decode_serial<1>);
   else if (nstates == 2) go(k_ans_decode_serial<2>);
-  else go(k_ans_decode_serial<4>);
+  else if (nstates == 4) go(k_ans_decode_serial<4>);
+  else go(k_ans_decode_serial<8>);
 }
 
 }  // namespace micgpu

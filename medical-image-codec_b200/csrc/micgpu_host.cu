@@ -42,9 +42,12 @@ struct AnsPlan {
   size_t dev_off = 0;                 // byte offset of [segs | slot_off] in d_segs
 };
 
-// Streams with at most this many states go through the thread-per-unit kernel (MICGPU_K2_SERIAL_MAXN: 0 = never, 1, 2, 4).
+// Streams with at most this many states go through the thread-per-unit kernel (MICGPU_K2_SERIAL_MAXN: 0 = never, 1, 2, 4, 8).
+// The kernel costs ~35 cycles per SYMBOL whatever N is (issue slots of its one warp per scheduler), the lane-parallel
+// kernel ~177 cycles per ROUND of N symbols: measured on the bench batch (tools/k2s_maxn.sh) 2-state 11.3 ms, 4-state
+// 10.1 against 12.9 ms, 8-state 10.2 against 7.2 ms -- so N <= 4 goes here and 8-state (and rANS-8) stays lane-parallel.
 int serial_max_n() {
-  static const int v = [] { const char* e = getenv("MICGPU_K2_SERIAL_MAXN"); return e ? atoi(e) : 2; }();
+  static const int v = [] { const char* e = getenv("MICGPU_K2_SERIAL_MAXN"); return e ? atoi(e) : 4; }();
   return v;
 }
 
@@ -204,7 +207,9 @@ int plan_commit(micgpu_decoder* d) {
       return s;
     };
     a.serial = false;
-    if (a.nstates <= serial_max_n()) {
+    bool list_rans = false;   // rANS-8 frames share the 8-state list; only the lane-parallel kernel decodes them
+    for (int i : d->lists[g]) list_rans |= d->units[i].rans != 0;
+    if (a.nstates <= serial_max_n() && !list_rans) {
       auto fit_s = [&](int mode) {
         int s = 0;
         while (s < 128 && ans_serial_smem_bytes(ml, mode, s + 1) <= budget) s++;

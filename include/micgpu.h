@@ -225,6 +225,19 @@ int micgpu_wavelet_v2_decompress(const uint8_t *blob, size_t len, uint16_t *pixe
  * WaveletRLEFSEDecompressU16 (with_rle = 1, :624-669): coefficients in raster order, interleaved in-place lifting
  * (waveletInverse2DRegion :180-189).  Decode only: the reference replaced these encoders by WaveletV2. */
 int micgpu_wavelet_v1_decompress(const uint8_t *blob, size_t len, int with_rle, uint16_t *pixels_out, size_t cap_px, int *rows, int *cols);
+/* The canonical-Huffman back end of the legacy streams.  A Huffman stream has no magic byte, so these are
+ * explicit entry points.  micgpu_huff_decompress = CanHuffmanDecompressU16.Init + ReadTable + Decompress
+ * (canhuffmandecompressu16.go:31-108): *n_out receives the symbol count of the header (also when cap is too small:
+ * MICGPU_E_SIZE).  micgpu_delta_rle_huff_decompress = DeltaRleHuffDecompressU16.Decompress
+ * (deltarlehuffdecompressu16.go:19-39): Huffman -> RLE -> inverse avg(top,left) predictor.
+ * micgpu_decoder_add_huff_unit queues such a stream in a plan beside FSE units (kind as for micgpu_decoder_add_unit:
+ * SPATIAL = Delta+RLE symbols of a width x height image, RLE = an RLE stream of up to `width` words).
+ * Limits: maxCodeLength <= 16 (the reference's encoder stops at 14 before it adds the delimiter); a stream that asks for
+ * bits past its end returns MICGPU_E_BITSTREAM (Go reads stale window bits or panics on the slice). */
+int micgpu_huff_decompress(const uint8_t *stream, size_t len, uint16_t *symbols_out, size_t cap, size_t *n_out);
+int micgpu_delta_rle_huff_decompress(const uint8_t *stream, size_t len, uint16_t *pixels_out, int width, int height);
+int micgpu_decoder_add_huff_unit(micgpu_decoder *d, const uint8_t *stream, size_t len, uint64_t comp_off, int kind,
+                                 uint32_t width, uint32_t height, uint64_t out_off);
 int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t *const *blobs, const size_t *lens, uint16_t *const *outs, const size_t *caps,
                                        int *rows, int *cols, int *status);
 

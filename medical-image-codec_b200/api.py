@@ -120,6 +120,9 @@ lib.micgpu_wsi_decompress_tiles.argtypes = [C.c_void_p, C.c_size_t, C.c_int, _ip
 lib.micgpu_wsi_decompress_region.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_rgb_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
 lib.micgpu_wavelet_v2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_huff_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+lib.micgpu_delta_rle_huff_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+lib.micgpu_decoder_add_huff_unit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64]
 lib.micgpu_wavelet_v1_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_wavelet_v2_decompress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _ip, _ip, _ip]
 _szp = C.POINTER(C.c_size_t)
@@ -490,6 +493,26 @@ def WaveletV2RLEFSEDecompressU16(compressed):
 WaveletV2SIMDRLEFSEDecompressU16 = WaveletV2RLEFSEDecompressU16
 
 
+def CanHuffmanDecompressU16(compressed) -> np.ndarray:
+    """canhuffmandecompressu16.go:31-108 (Init + ReadTable + Decompress) -> the symbols of one canonical-Huffman stream."""
+    a = _bytes_view(compressed)
+    if a.size < 9:
+        raise MicGpuError(E_HEADER, "compressed data too short")
+    n = (int(a[0]) << 24) | (int(a[1]) << 16) | (int(a[2]) << 8) | int(a[3])
+    out = np.empty(max(n, 1), np.uint16)
+    got = C.c_size_t()
+    _check(lib.micgpu_huff_decompress(a.ctypes.data, a.size, out.ctypes.data, n, C.byref(got)))
+    return out[: got.value]
+
+
+def DeltaRleHuffDecompressU16(compressed, width: int, height: int) -> np.ndarray:
+    """deltarlehuffdecompressu16.go:19 (Huffman -> RLE -> inverse avg(top,left) predictor) -> pixels."""
+    a = _bytes_view(compressed)
+    out = np.empty(width * height, np.uint16)
+    _check(lib.micgpu_delta_rle_huff_decompress(a.ctypes.data, a.size, out.ctypes.data, width, height))
+    return out
+
+
 def _wavelet_v1(compressed, with_rle: int):
     a = _bytes_view(compressed)
     if a.size < (15 if with_rle else 11):
@@ -759,6 +782,14 @@ class Decoder:
         a = _bytes_view(frame)
         self._keep.append(a)
         rc = lib.micgpu_decoder_add_unit(self._h, a.ctypes.data, a.size, comp_off, kind, width, height, out_off)
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def add_huff_unit(self, stream, comp_off: int, kind: int, width: int, height: int, out_off: int) -> int:
+        a = _bytes_view(stream)
+        self._keep.append(a)
+        rc = lib.micgpu_decoder_add_huff_unit(self._h, a.ctypes.data, a.size, comp_off, kind, width, height, out_off)
         if rc < 0:
             _check(rc)
         return rc

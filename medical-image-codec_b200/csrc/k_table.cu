@@ -93,7 +93,7 @@ k_build_tables(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
   for (int ui = blockIdx.x; ui < nunits; ui += gridDim.x) {
     MicUnit* U = &units[ui];
     __syncthreads();
-    if (U->status != MIC_OK) continue;
+    if (U->status != MIC_OK || U->rans == MIC_CODER_HUFF) continue;   // Huffman units bring no ncount header (k_huff.cu)
     if (only_flagged && U->npres != K1_FALLBACK) continue;   // the split kernels below already built this unit's tables
     const uint8_t* frame = comp + U->comp_off;
     const int flen = (int)U->comp_len;
@@ -342,7 +342,7 @@ k_parse_ncount(MicUnit* __restrict__ units, int nunits, const uint8_t* __restric
   const int ui = blockIdx.x * K1A_WARPS + warp;
   if (ui >= nunits) return;
   MicUnit* U = &units[ui];
-  if (U->status != MIC_OK) return;
+  if (U->status != MIC_OK || U->rans == MIC_CODER_HUFF) return;
   uint32_t* win = s_win_all[warp];
   const uint8_t* frame = comp + U->comp_off;
   const int flen = (int)U->comp_len;
@@ -595,7 +595,7 @@ k_build_dtable(MicUnit* __restrict__ units, int nunits, const int32_t* __restric
     const int ui = s_ui;
     if (ui >= nunits) break;
     MicUnit* U = &units[ui];
-    if (U->status != MIC_OK || U->npres == K1_FALLBACK) continue;
+    if (U->status != MIC_OK || U->npres == K1_FALLBACK || U->rans == MIC_CODER_HUFF) continue;
     const uint32_t L = U->table_log, S = 1u << L, np = U->npres;
     const int32_t* gn = g_norm + U->tab_off;
     const uint16_t* gs = g_sym + U->tab_off;

@@ -38,6 +38,12 @@ void launch_ans_decode_serial(MicUnit* d_units, const int* d_list, const int2* d
 size_t ans_serial_unit_bytes(int table_log, int mode);
 size_t ans_serial_smem_bytes(int max_log, int mode, int slots);
 
+// Canonical-Huffman streams (k_huff.cu): one CTA per listed unit parses the header, builds the code table in the unit's
+// tabA region, writes an identity tabS and decodes the symbols to the unit's place in the state stream (self-synchronising
+// subsequences, one per thread; serial != 0: one thread walks the chain, for A/B runs).
+void launch_huff_decode(MicUnit* d_units, const int* d_list, int nlist, const uint8_t* d_comp, uint32_t* d_tabA, uint16_t* d_tabS,
+                        uint16_t* d_states, int serial, int sm_count, cudaStream_t st);
+
 // RLE expand (+ escape split for spatial units).  Spatial units produce the
 // residual plane D (pitch wp) and the literal bit mask M; RLE units write
 // their expanded stream straight to d_out.

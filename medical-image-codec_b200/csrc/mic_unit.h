@@ -13,6 +13,13 @@ enum MicUnitKind {
   MIC_KIND_RAW = 2,      // the FSE symbols are the payload (V1 wavelet without RLE, waveletfsecompressu16.go:124-163)
 };
 
+// MicUnit::rans (the entropy coder of the unit)
+enum MicCoder {
+  MIC_CODER_TANS = 0,    // FSE, 1/2/4/8 states
+  MIC_CODER_RANS = 1,    // rANS-8 (magic [0xFF,0x08])
+  MIC_CODER_HUFF = 2,    // canonical Huffman (canhuffmandecompressu16.go; no magic: chosen by the caller, k_huff.cu decodes it)
+};
+
 enum MicStatus {
   MIC_OK = 0,
   MIC_E_HEADER = -1,     // bad magic / truncated frame          (C twin: -1)
@@ -38,7 +45,7 @@ struct MicUnit {
   unsigned int width, height;   // spatial: image geometry; RLE: width = expected outlen, height = 1
   unsigned int wp;              // padded pitch (multiple of 32 elements, >= width + 8)
   unsigned int nstates;         // 1,2,4,8 (from the magic prefix, fse2state.go:102-116)
-  unsigned int rans;            // 1 when magic is [0xFF,0x08]
+  unsigned int rans;            // MicCoder: 1 when magic is [0xFF,0x08], 2 for a canonical-Huffman stream
   unsigned int table_log;       // peeked from the ncount header (fsedecompressu16.go:61)
   unsigned int count;           // symbol count from the 6-byte prefix (0: 1-state, unknown)
   unsigned int sym_cap;         // capacity (elements) reserved at sym_off

@@ -66,6 +66,7 @@ struct micgpu_decoder {
   std::mutex mu;
   std::vector<MicUnit> units;
   std::vector<int> lists[4];
+  std::vector<int> huff;              // canonical-Huffman units (k_huff.cu); they are in none of the ANS lists
   std::vector<int> spatial;
   std::vector<TemporalGroup> temporal;
   std::vector<std::pair<unsigned long long, unsigned long long>> zero_ranges;   // output elements no unit covers (offset, count)
@@ -149,21 +150,24 @@ int plan_commit(micgpu_decoder* d) {
   d->n_grad = 0;
   d->n_rle = 0;
   for (auto& l : d->lists) l.clear();
+  d->huff.clear();
   d->spatial.clear();
   for (size_t i = 0; i < d->units.size(); i++) {
     MicUnit& u = d->units[i];
     const unsigned long long px = (unsigned long long)u.width * u.height;
     // symbol capacity: exact for N-state streams; for 1-state the stream is bounded by the
     // RLE worst case (every pixel escaped, plus run headers)
-    unsigned long long cap = u.nstates > 1 ? u.count : 3 * px + 4096;
+    const bool counted = u.nstates > 1 || u.rans == MIC_CODER_HUFF;   // the frame states its symbol count
+    unsigned long long cap = counted ? u.count : 3 * px + 4096;
     if (cap > 0xFFFFFFF0ull) { u.status = MIC_E_UNSUPPORTED; cap = 0; }
-    if (u.nstates > 1 && cap > 3 * px + 4096) { u.status = MIC_E_SIZE; cap = 0; }   // count cannot exceed the RLE worst case
+    if (counted && cap > 3 * px + 4096) { u.status = MIC_E_SIZE; cap = 0; }   // count cannot exceed the RLE worst case
     u.sym_cap = (unsigned)cap;
     u.sym_off = d->sym_total;
     d->sym_total += (cap + 15) & ~15ull;
     u.tab_off = d->tab_total;
     d->tab_total += 1ull << u.table_log;
-    d->max_log_all = std::max(d->max_log_all, (int)u.table_log);
+    // a Huffman unit reserves tableLog-16 regions (code table in tabA, identity in tabS) but takes no part in K1
+    if (u.rans != MIC_CODER_HUFF) d->max_log_all = std::max(d->max_log_all, (int)u.table_log);
     if (u.kind == MIC_KIND_SPATIAL) {
       u.wp = (u.width + 8 + 63) & ~63u;   // rows start on 128 B lines;   // room for the 0..7 pixel row phase (mic_unit.h align0)
       u.d_off = d->d_total;
@@ -178,7 +182,8 @@ int plan_commit(micgpu_decoder* d) {
       u.wp = 0; u.d_off = 0; u.m_off = 0;
       if (u.kind == MIC_KIND_RLE) d->n_rle++;
     }
-    d->lists[nstates_index(u.nstates)].push_back((int)i);
+    if (u.rans == MIC_CODER_HUFF) d->huff.push_back((int)i);
+    else d->lists[nstates_index(u.nstates)].push_back((int)i);
     d->out_need = std::max(d->out_need, u.out_off + px);
   }
   // slots of one warp run in lockstep to the longest unit: keep similar lengths together
@@ -208,7 +213,7 @@ int plan_commit(micgpu_decoder* d) {
     };
     a.serial = false;
     bool list_rans = false;   // rANS-8 frames share the 8-state list; only the lane-parallel kernel decodes them
-    for (int i : d->lists[g]) list_rans |= d->units[i].rans != 0;
+    for (int i : d->lists[g]) list_rans |= d->units[i].rans == MIC_CODER_RANS;
     if (a.nstates <= serial_max_n() && !list_rans) {
       auto fit_s = [&](int mode) {
         int s = 0;
@@ -295,7 +300,7 @@ int plan_commit(micgpu_decoder* d) {
   static const bool split_cfg = [] { const char* e = getenv("MICGPU_K1_SPLIT"); return !(e && e[0] == '0'); }();
   d->k1_split = split_cfg;
   bool any_rans = false;
-  for (const MicUnit& u : d->units) any_rans |= u.rans != 0;
+  for (const MicUnit& u : d->units) any_rans |= u.rans == MIC_CODER_RANS;
   d->k1_fallback = !d->k1_split || any_rans || d->max_log_all >= 12;
   if (d->k1_fallback && (rc = d->d_k1.ensure((size_t)d->k1_grid * d->k1_stride))) return rc;
   if (d->k1_split) {
@@ -309,11 +314,13 @@ int plan_commit(micgpu_decoder* d) {
     CUDA_TRY(cudaMallocHost(&d->h_units, (nu + nu / 4 + 16) * sizeof(MicUnit)));
     d->h_units_cap = nu + nu / 4 + 16;
   }
-  // unit index lists: [N=1 | N=2 | N=4 | N=8] then the spatial list
+  // unit index lists: [N=1 | N=2 | N=4 | N=8] then the spatial list, then the Huffman units (each unit is in exactly one
+  // of the coder lists, so 2 * nu entries hold everything)
   std::vector<int> flat;
   flat.reserve(2 * nu);
   for (auto& l : d->lists) flat.insert(flat.end(), l.begin(), l.end());
   flat.insert(flat.end(), d->spatial.begin(), d->spatial.end());
+  flat.insert(flat.end(), d->huff.begin(), d->huff.end());
   if (!flat.empty()) CUDA_TRY(cudaMemcpy(d->d_list.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
   // segment tables of the thread-per-unit ANS kernel: [segs | slot offsets] per state-count group
   {
@@ -425,6 +432,13 @@ int run_device_locked(micgpu_decoder* d, const void* d_comp, size_t comp_bytes, 
     }
     loff += n;
   }
+  if (!d->huff.empty()) {
+    static const int huff_serial = [] { const char* e = getenv("MICGPU_HUFF_SERIAL"); return e ? atoi(e) : 0; }();
+    prof_mark(d, "k_huff_decode", st);
+    launch_huff_decode(du, dl + loff + d->spatial.size(), (int)d->huff.size(), comp, (uint32_t*)d->d_tabA.p, (uint16_t*)d->d_tabS.p,
+                       (uint16_t*)d->d_states.p, huff_serial, d->sm_count, st);
+    d->launches++;
+  }
   // K3 launch shape (k_rle.cu): small tables mean 8-bit planes (MIC3 tiles), whose run headers come every <= 124 symbols:
   // the header walk of one warp is the bound there, and CTAs of 128 threads / 2048-element chunks put 2.4x the walkers
   // on an SM (measured on 4096 tiles: K3 1.86 -> 1.45 ms; strips lose 10 % with it, profiles/README.md)
@@ -517,6 +531,40 @@ int add_unit_locked(micgpu_decoder* d, const uint8_t* frame, size_t len, uint64_
   u.out_off = out_off;
   peek_frame(frame, len, u);
   if (w == 0 || h == 0) u.status = MIC_E_HEADER;
+  d->units.push_back(u);
+  d->committed = false;
+  return (int)d->units.size() - 1;
+}
+
+// The fixed head of a canonical-Huffman stream (canhuffmancompressu16.go:119-128, MSB first): u32 symbol count, u16
+// maxValue, u8 maxCodeLength, u16 list size.  There is no magic: the caller says that the stream is Huffman-coded.
+int add_huff_unit_locked(micgpu_decoder* d, const uint8_t* s, size_t len, uint64_t comp_off, int kind, uint32_t w, uint32_t h,
+                         uint64_t out_off) {
+  MicUnit u;
+  memset(&u, 0, sizeof u);
+  u.comp_off = comp_off;
+  u.comp_len = (unsigned)len;
+  u.kind = (unsigned)kind;
+  u.width = w;
+  u.height = h;
+  u.out_off = out_off;
+  u.nstates = 1;
+  u.rans = MIC_CODER_HUFF;
+  u.table_log = 16;
+  u.status = MIC_OK;
+  if (len < 9 || w == 0 || h == 0) u.status = MIC_E_HEADER;
+  else if (len >= (1u << 28)) u.status = MIC_E_UNSUPPORTED;
+  else {
+    u.count = ((uint32_t)s[0] << 24) | ((uint32_t)s[1] << 16) | ((uint32_t)s[2] << 8) | s[3];
+    const unsigned max_value = ((unsigned)s[4] << 8) | s[5], max_len = s[6], nl = ((unsigned)s[7] << 8) | s[8];
+    unsigned depth = 0, len_bits = 0;
+    while (depth < 16 && (max_value >> depth)) depth++;
+    while (len_bits < 8 && (max_len >> len_bits)) len_bits++;
+    // 2^maxCodeLength table cells live in the unit's tabA region (2^16): the reference's own encoder stops at 14 bits
+    // before it adds the delimiter (canhuffmancompressu16.go:168-186)
+    if (max_len > 16) u.status = MIC_E_UNSUPPORTED;
+    else if (72ull + (unsigned long long)nl * (depth + len_bits) > (unsigned long long)len * 8) u.status = MIC_E_HEADER;
+  }
   d->units.push_back(u);
   d->committed = false;
   return (int)d->units.size() - 1;
@@ -832,6 +880,14 @@ int micgpu_decoder_add_unit(micgpu_decoder* d, const uint8_t* frame, size_t fram
   if (kind != MICGPU_KIND_SPATIAL && kind != MICGPU_KIND_RLE) return fail(MICGPU_E_HEADER, "unknown unit kind %d", kind);
   std::lock_guard<std::mutex> lk(d->mu);
   return add_unit_locked(d, frame, frame_len, comp_off, kind, width, height, out_off);
+}
+
+int micgpu_decoder_add_huff_unit(micgpu_decoder* d, const uint8_t* stream, size_t len, uint64_t comp_off, int kind,
+                                 uint32_t width, uint32_t height, uint64_t out_off) {
+  if (!d || !stream) return fail(MICGPU_E_HEADER, "null argument");
+  if (kind != MICGPU_KIND_SPATIAL && kind != MICGPU_KIND_RLE) return fail(MICGPU_E_HEADER, "unknown unit kind %d", kind);
+  std::lock_guard<std::mutex> lk(d->mu);
+  return add_huff_unit_locked(d, stream, len, comp_off, kind, width, height, out_off);
 }
 
 int micgpu_decoder_add_pics(micgpu_decoder* d, const uint8_t* pics, size_t len, uint64_t comp_off, uint64_t out_off,
@@ -1286,6 +1342,43 @@ int micgpu_decompress_single_frame_grad(const uint8_t* frame, size_t len, uint16
   int rc = plan_commit(d);
   if (rc) return rc;
   return run_host_locked(d, frame, len, pixels_out, (size_t)width * height);
+}
+
+// CanHuffmanDecompressU16.Init + ReadTable + Decompress (canhuffmandecompressu16.go:31-108): the symbols of one stream
+int micgpu_huff_decompress(const uint8_t* stream, size_t len, uint16_t* symbols_out, size_t cap, size_t* n_out) {
+  if (!stream || !symbols_out || !n_out) return fail(MICGPU_E_HEADER, "null argument");
+  if (len < 9) return fail(MICGPU_E_HEADER, "huffman: stream shorter than its fixed header");
+  const size_t n = ((size_t)stream[0] << 24) | ((size_t)stream[1] << 16) | ((size_t)stream[2] << 8) | stream[3];
+  *n_out = n;
+  if (n > cap) return fail(MICGPU_E_SIZE, "output buffer holds %zu symbols, stream has %zu", cap, n);
+  if (n == 0) return 0;
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  d->units.clear();
+  d->temporal.clear();
+  d->zero_ranges.clear();
+  d->out_need = 0;
+  add_huff_unit_locked(d, stream, len, 0, MIC_KIND_RAW, (uint32_t)n, 1, 0);
+  int rc = plan_commit(d);
+  if (rc) return rc;
+  return run_host_locked(d, stream, len, symbols_out, n);
+}
+
+// DeltaRleHuffDecompressU16.Decompress (deltarlehuffdecompressu16.go:19-39): Huffman -> RLE -> avg(top,left) predictor
+int micgpu_delta_rle_huff_decompress(const uint8_t* stream, size_t len, uint16_t* pixels_out, int width, int height) {
+  if (!stream || !pixels_out || width <= 0 || height <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_decoder* d = default_decoder(current_device());
+  if (!d) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(d->mu);
+  d->units.clear();
+  d->temporal.clear();
+  d->zero_ranges.clear();
+  d->out_need = 0;
+  add_huff_unit_locked(d, stream, len, 0, MIC_KIND_SPATIAL, (uint32_t)width, (uint32_t)height, 0);
+  int rc = plan_commit(d);
+  if (rc) return rc;
+  return run_host_locked(d, stream, len, pixels_out, (size_t)width * height);
 }
 
 static int mic2_decode(const uint8_t* mic2, size_t len, int last_frame, bool only_last, uint16_t* out, size_t cap_px, int* width,

@@ -57,6 +57,15 @@ int orc_fse_decompress_auto(const uint8_t *in, size_t len, uint16_t **out, size_
 /* diagnostics: tableLog / symbolLen / norm[] chosen for an input */
 int orc_fse_table_info(const uint16_t *in, size_t n, int *table_log, int *symbol_len, int32_t *norm_out /* 65536 or NULL */);
 
+/* CanHuffmanCompressU16.Init+Compress / CanHuffmanDecompressU16.Init+ReadTable+Decompress (canhuffmancompressu16.go:46-81,
+ * canhuffmandecompressu16.go:31-108; mic_oracle_huff.c).  Encoder bytes: ties between equal frequencies are ordered by a
+ * stable sort here, by Go's unstable sort.Slice there (parity unpinned); the decoder is fully determined by the stream. */
+int orc_huff_compress(const uint16_t *in, size_t n, uint8_t **out, size_t *out_len);
+int orc_huff_decompress(const uint8_t *in, size_t len, uint16_t **out, size_t *out_len);
+/* DeltaRleCompressU16 -> CanHuffman (fseu16_test.go:881-889) / DeltaRleHuffDecompressU16.Decompress (deltarlehuffdecompressu16.go:19-39) */
+int orc_delta_rle_huff_compress(const uint16_t *px, int width, int height, uint16_t max_value, uint8_t **out, size_t *out_len);
+int orc_delta_rle_huff_decompress(const uint8_t *in, size_t len, int width, int height, uint16_t *px_out);
+
 /* ---- L2: transforms ----------------------------------------------------- */
 /* RleCompressU16.Init(len,1,maxValue)+Compress (rlecompressu16.go:15-93) */
 int orc_rle_compress(const uint16_t *in, size_t n, uint16_t max_value, uint16_t **out, size_t *out_len);

@@ -35,8 +35,8 @@ class OracleError(RuntimeError):
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference tree is present)."""
     so = os.path.join(_HERE, "libmicoracle.so")
-    src = os.path.join(_HERE, "mic_oracle.c")
-    need = force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
+    srcs = [os.path.join(_HERE, f) for f in ("mic_oracle.c", "mic_oracle_huff.c", "mic_oracle.h")]
+    need = force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs)
     need_ref = os.path.isdir("/root/reference/ojph") and not os.path.exists(os.path.join(_HERE, "_ref", "libmicref.so"))
     if need or need_ref:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
@@ -99,6 +99,32 @@ class Oracle:
         p, n = _u16p(), C.c_size_t()
         self._chk(self.lib.orc_fse_decompress_auto(_ptr(a, _u8p), C.c_size_t(a.size), C.byref(p), C.byref(n)), "fse_decompress")
         return self._take_u16(p, n)
+
+    def huff_compress(self, sym) -> bytes:
+        a = _as_u16(sym)
+        p, n = _u8p(), C.c_size_t()
+        self._chk(self.lib.orc_huff_compress(_ptr(a, _u16p), C.c_size_t(a.size), C.byref(p), C.byref(n)), "huff_compress")
+        return self._take_u8(p, n)
+
+    def huff_decompress(self, blob) -> np.ndarray:
+        a = _as_u8(blob)
+        p, n = _u16p(), C.c_size_t()
+        self._chk(self.lib.orc_huff_decompress(_ptr(a, _u8p), C.c_size_t(a.size), C.byref(p), C.byref(n)), "huff_decompress")
+        return self._take_u16(p, n)
+
+    def delta_rle_huff_compress(self, px, width, height, max_value) -> bytes:
+        a = _as_u16(px)
+        p, n = _u8p(), C.c_size_t()
+        self._chk(self.lib.orc_delta_rle_huff_compress(_ptr(a, _u16p), width, height, C.c_uint16(max_value), C.byref(p), C.byref(n)),
+                  "delta_rle_huff_compress")
+        return self._take_u8(p, n)
+
+    def delta_rle_huff_decompress(self, blob, width, height) -> np.ndarray:
+        a = _as_u8(blob)
+        o = np.empty(width * height, dtype=np.uint16)
+        self._chk(self.lib.orc_delta_rle_huff_decompress(_ptr(a, _u8p), C.c_size_t(a.size), width, height, _ptr(o, _u16p)),
+                  "delta_rle_huff_decompress")
+        return o.reshape(height, width)
 
     def fse_table_info(self, sym):
         a = _as_u16(sym)

@@ -28,12 +28,21 @@ namespace micgpu {
 
 namespace {
 
-constexpr int SRING_STRIDE = 36;   // words per unit: 32 ring words + mirror of words 0..3
 constexpr int SERIAL_THREADS = 128;
+// Ring of RQ quarters of 32 B (+ mirror of words 0..3).  Four quarters cover every table up to tableLog 13; wider tables
+// take eight.  Why: the register bit buffer reads up to 96 bits below the bit position, so the rounds after a ring check
+// touch [P - C - 96, P) with C <= 256 bits consumed per check.  With four quarters and the two youngest copies possibly
+// still in flight (wait_group 2), what is guaranteed to have landed reaches down to the start of the quarter below the
+// one P is in -- enough unless three consecutive checks consume more than 673 bits (48 symbols of > 14 bits: only
+// tableLog >= 14 can do that, and near-incompressible 16-bit data does).  With eight quarters the landed part reaches
+// 1280 bits below the top quarter.  The extra 128 B do not cost residency: such a table is 32 KB or more.
+__host__ __device__ constexpr int serial_ring_quarters(int table_log) { return table_log >= 14 ? 8 : 4; }
+__host__ __device__ constexpr int serial_ring_words(int table_log) { return serial_ring_quarters(table_log) * 8 + 4; }
 
 // Branch-free ring maintenance of one thread's unit (see ring_refill_async in k_ans.cu for the coverage proof; the
 // cadence is the same: at most 256 bits are consumed between two calls).  When the top unread bit has left quarter
 // qtop, the slot of that quarter receives quarter qtop - 4: two 16 B cp.async, plus the mirror copy for ring slot 0.
+template <int RQ>
 __device__ __forceinline__ void serial_refill(int P, int& cross, uint32_t& ra, uint32_t& qo, int& hidx, const uint8_t*& srcp,
                                               uint32_t ring_sa) {
   asm volatile(
@@ -43,7 +52,7 @@ __device__ __forceinline__ void serial_refill(int P, int& cross, uint32_t& ra, u
       "setp.eq.and.u32 q, %2, 0, pl;\n\t"
       "@pl cp.async.ca.shared.global [%1], [%4], 16;\n\t"
       "@pl cp.async.ca.shared.global [%1+16], [%4+16], 16;\n\t"
-      "@q cp.async.ca.shared.global [%1+128], [%4], 16;\n\t"
+      "@q cp.async.ca.shared.global [%1+%7], [%4], 16;\n\t"
       "cp.async.commit_group;\n\t"
       "cp.async.wait_group 2;\n\t"
       "setp.ge.and.s32 pp, %3, 8, p;\n\t"
@@ -52,11 +61,11 @@ __device__ __forceinline__ void serial_refill(int P, int& cross, uint32_t& ra, u
       "@p add.s32 %3, %3, -1;\n\t"
       "@p add.s64 %4, %4, -32;\n\t"
       "@p add.s32 %2, %2, -32;\n\t"
-      "@p and.b32 %2, %2, 96;\n\t"
+      "@p and.b32 %2, %2, %8;\n\t"
       "add.s32 %1, %6, %2;\n\t"
       "}\n"
       : "+r"(cross), "+r"(ra), "+r"(qo), "+r"(hidx), "+l"(srcp)
-      : "r"(P), "r"(ring_sa)
+      : "r"(P), "r"(ring_sa), "n"(RQ * 32), "n"((RQ - 1) * 32)
       : "memory");
 }
 
@@ -91,7 +100,7 @@ struct Cells {
   }
 };
 
-template <int N, int FMT, bool L16>
+template <int N, int FMT, bool L16, int RQ>
 __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restrict__ comp, uint16_t* __restrict__ states_out,
                                             const uint8_t* mytab, const uint32_t* myflags, uint32_t* ring) {
   const Cells<FMT, L16> cells{mytab, myflags, U->table_log, 1u << U->table_log};
@@ -107,28 +116,29 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
   const uint8_t* ringb = reinterpret_cast<const uint8_t*>(ring);
   const int qtop = (P - 1) >> 8;
   int cross = qtop << 8;                             // P <= cross  <=>  the top unread bit left quarter qtop
+  constexpr uint32_t WMASK = RQ * 8 - 1;   // ring words
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
+  for (int j = 0; j < RQ; j++) {
     const int q = qtop - j;
     if (q >= 0) {
-      const uint32_t dst = ring_sa + (uint32_t)((q & 3) << 5);
+      const uint32_t dst = ring_sa + (uint32_t)((q & (RQ - 1)) << 5);
       const uint8_t* src = wbase + (size_t)q * 32;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 16) : "memory");
-      if ((q & 3) == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 128u), "l"(src) : "memory");
+      if ((q & (RQ - 1)) == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(RQ * 32)), "l"(src) : "memory");
     }
   }
-  int hidx = qtop - 4;
+  int hidx = qtop - RQ;
   const uint8_t* srcp = wbase + (ptrdiff_t)hidx * 32;
-  uint32_t qo = (uint32_t)((hidx & 3) << 5), ra = ring_sa + qo;
+  uint32_t qo = (uint32_t)((hidx & (RQ - 1)) << 5), ra = ring_sa + qo;
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 
   // bits [lo, lo+nb) straight from the ring (start-up and tails; the hot loops use a register window)
   auto extract = [&](int lo, uint32_t nb) -> uint32_t {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + (((uint32_t)lo >> 3) & 0x7Cu));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(ringb + (((uint32_t)lo >> 3) & (WMASK * 4u)));
     return __funnelshift_r(w[0], w[1], (uint32_t)lo & 31u) & ((1u << nb) - 1u);
   };
-  auto refill = [&]() { serial_refill(P, cross, ra, qo, hidx, srcp, ring_sa); };
+  auto refill = [&]() { serial_refill<RQ>(P, cross, ra, qo, hidx, srcp, ring_sa); };
 
   int err = 0;
   uint32_t st[N];
@@ -160,13 +170,13 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
   auto buf_load = [&]() {                       // from P
     const uint32_t wtop = ((uint32_t)(P - 1)) >> 5;
     const uint32_t r = (uint32_t)P - (wtop << 5);                 // valid bits of the top word, 1..32
-    const uint32_t wt = ringw[wtop & 31u], wb = ringw[(wtop - 1u) & 31u];
+    const uint32_t wt = ringw[wtop & WMASK], wb = ringw[(wtop - 1u) & WMASK];
     BH = __funnelshift_l(wb, wt, 32u - r);                         // (wt : wb) << (32 - r), high half
     BL = wb << ((32u - r) & 31u);
     if (r == 32u) BL = wb;
     cnt = r + 32u;
     wn = wtop - 2u;
-    WN = ringw[wn & 31u];
+    WN = ringw[wn & WMASK];
   };
   auto buf_sync = [&]() { P = (int)(((wn + 1u) << 5) + cnt); };   // the bit position the buffer stands for
   auto take = [&](uint32_t nb) {                                   // consume nb <= 16 bits
@@ -182,7 +192,7 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
       cnt += 32u;
       wn -= 1u;
     }
-    WN = ringw[wn & 31u];
+    WN = ringw[wn & WMASK];
   };
   auto next_state = [&](uint32_t h, uint32_t nb) -> uint32_t { return __funnelshift_l(BH, h, nb); };
 
@@ -389,11 +399,18 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, c
         const uint32_t* myflags = reinterpret_cast<const uint32_t*>(mytab + cells);
         const size_t fl = (mode == 1 && L > 15) ? (1u << 16) / 8 : 0;
         uint32_t* ring = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(mytab) + cells + fl);
-        if (mode == 0) decode_unit<N, 0, false>(U, comp, states_out, mytab, myflags, ring);
-        else if (mode == 3) decode_unit<N, 3, false>(U, comp, states_out, mytab, myflags, ring);
-        else if (d16) decode_unit<N, 2, false>(U, comp, states_out, mytab, myflags, ring);
-        else if (l16 && L > 15) decode_unit<N, 1, true>(U, comp, states_out, mytab, myflags, ring);
-        else decode_unit<N, 1, false>(U, comp, states_out, mytab, myflags, ring);
+        if (L < 14) {   // four ring quarters (see serial_ring_quarters)
+          if (mode == 0) decode_unit<N, 0, false, 4>(U, comp, states_out, mytab, myflags, ring);
+          else if (mode == 3) decode_unit<N, 3, false, 4>(U, comp, states_out, mytab, myflags, ring);
+          else if (d16) decode_unit<N, 2, false, 4>(U, comp, states_out, mytab, myflags, ring);
+          else decode_unit<N, 1, false, 4>(U, comp, states_out, mytab, myflags, ring);
+        } else {        // eight
+          if (mode == 0) decode_unit<N, 0, false, 8>(U, comp, states_out, mytab, myflags, ring);
+          else if (mode == 3) decode_unit<N, 3, false, 8>(U, comp, states_out, mytab, myflags, ring);
+          else if (d16) decode_unit<N, 2, false, 8>(U, comp, states_out, mytab, myflags, ring);
+          else if (l16 && L > 15) decode_unit<N, 1, true, 8>(U, comp, states_out, mytab, myflags, ring);
+          else decode_unit<N, 1, false, 8>(U, comp, states_out, mytab, myflags, ring);
+        }
       }
     }
   }
@@ -401,10 +418,11 @@ k_ans_decode_serial(MicUnit* __restrict__ units, const int* __restrict__ list, c
 
 // shared-memory bytes of one unit: cells, the bit array for bit 16 of nextState (tableLog 16 in 2-byte cells), the ring
 size_t ans_serial_unit_bytes(int table_log, int mode) {
-  if (mode == 3) return ((size_t)3 << table_log) + SRING_STRIDE * 4;
+  const size_t ring = (size_t)serial_ring_words(table_log) * 4;
+  if (mode == 3) return ((size_t)3 << table_log) + ring;
   size_t t = (size_t)(1u << table_log) * (mode == 0 ? 4 : 2);
   if (mode == 1 && table_log == 16) t += (1u << 16) / 8;
-  return t + SRING_STRIDE * 4;
+  return t + ring;
 }
 
 size_t ans_serial_smem_bytes(int max_log, int mode, int slots) { return (size_t)slots * ans_serial_unit_bytes(max_log, mode); }

@@ -342,3 +342,26 @@ def test_predictor_uint16_wrap_follows_the_reference(mic, oracle, w, h):
         got = mic.DecompressSingleFrame(blob, w, h)
         assert np.array_equal(got, want), coder
     assert not np.array_equal(want, img)
+
+
+@pytest.mark.parametrize("coder", [1, 2, 4, 8])
+def test_dense_streams_on_wide_tables(mic, oracle, coder):
+    # near-incompressible 15-bit data at tableLog 16: every symbol costs 14-15 bits, so the thread-per-unit kernel consumes
+    # its bitstream ring at the highest rate the format allows (three ring checks in a row take > 673 bits: the case that
+    # needs the eight-quarter ring of k_ans_serial.cu); RLE-kind unit = the layout of a temporal residual frame
+    rng = np.random.default_rng(coder)
+    res = rng.integers(0, 24000, 300_000).astype(np.uint16)
+    sym = oracle.rle_compress(res, 23999)
+    blob = np.frombuffer(oracle.fse_compress(sym, coder), np.uint8)
+    hdr = 0 if coder == 1 else 6
+    assert (int(blob[hdr]) & 0xF) + 5 == 16 and blob.size * 8 / sym.size > 14.0      # tableLog 16, > 14 bits per symbol
+    dec = mic.Decoder(0)
+    dec.begin()
+    dec.add_unit(blob, 0, 1, res.size, 1, 0)
+    dec.commit()
+    comp = np.zeros(blob.size + 256, np.uint8)
+    comp[: blob.size] = blob
+    out = np.zeros(res.size, np.uint16)
+    dec.run_host(comp, out)
+    assert np.array_equal(out, res)
+    dec.close()

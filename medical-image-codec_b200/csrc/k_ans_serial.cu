@@ -203,6 +203,7 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
     // 16 symbols (<= 256 bits) per ring check, two per window; cannot reach the end of the bits inside the group
     while (!err && P - shift > 256 && nsym + 16 <= cap) {
       buf_load();
+      uint32_t pk[8];                    // states are < 2^16: two per word, the 16 of a check leave as two 16 B stores
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         uint32_t nb, h;
@@ -211,13 +212,14 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
         s0 = next_state(h, nb);
         take(nb);
         cells.get(s0, nb, h);
-        const uint32_t e1 = s0;
+        pk[j] = __byte_perm(e0, s0, 0x5410);
         s0 = next_state(h, nb);
         take(nb);
         top_up();
-        *reinterpret_cast<uint32_t*>(out + nsym) = e0 | (e1 << 16);
-        nsym += 2;
       }
+      *reinterpret_cast<uint4*>(out + nsym) = make_uint4(pk[0], pk[1], pk[2], pk[3]);       // nsym is a multiple of 16 here
+      *reinterpret_cast<uint4*>(out + nsym + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      nsym += 16;
       buf_sync();
       refill();
     }
@@ -263,13 +265,33 @@ __device__ __forceinline__ void decode_unit(MicUnit* U, const uint8_t* __restric
         if ((k & 1) == 1 || k == N - 1) top_up();      // at most 32 bits since the last one
       }
     };
+    // the same round with the emitted states packed two per word into pw[N / 2]: the hot loop stores the 16 symbols of a
+    // ring check as two 16 B words (one PRMT per two symbols and two stores, against shift + or + store per round; a unit
+    // alone on its SM -- a MIC2 frame -- runs 15 % faster with it, full warps the same: tools/k2s_variants.sh)
+    auto round_pack = [&](uint32_t* pw) {
+      uint32_t nb[N], h[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) cells.get(st[k], nb[k], h[k]);
+#pragma unroll
+      for (int k = 0; k < N; k += 2) pw[k / 2] = __byte_perm(st[k], st[k + 1], 0x5410);
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        st[k] = next_state(h[k], nb[k]);
+        take(nb[k]);
+        if ((k & 1) == 1 || k == N - 1) top_up();
+      }
+    };
     constexpr uint32_t RPC = 16 / N;    // rounds per ring check: RPC * N * 16 = 256 bits
     uint32_t r = 0;
     uint16_t* op = out;
     buf_load();
     for (; r + RPC <= full; r += RPC) {
+      uint32_t pk[8];
 #pragma unroll
-      for (uint32_t j = 0; j < RPC; j++) round_win(op + j * N);
+      for (uint32_t j = 0; j < RPC; j++) round_pack(pk + j * (N / 2));
+      // sym_off is a multiple of 16 elements and op advances by 16: both stores are 16 B aligned
+      *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       op += RPC * N;
       buf_sync();
       refill();

@@ -238,6 +238,14 @@ int micgpu_huff_decompress(const uint8_t *stream, size_t len, uint16_t *symbols_
 int micgpu_delta_rle_huff_decompress(const uint8_t *stream, size_t len, uint16_t *pixels_out, int width, int height);
 int micgpu_decoder_add_huff_unit(micgpu_decoder *d, const uint8_t *stream, size_t len, uint64_t comp_off, int kind,
                                  uint32_t width, uint32_t height, uint64_t out_off);
+/* The encoder: CanHuffmanCompressU16.Init + Compress (canhuffmancompressu16.go:46-81) and the test composition
+ * DeltaRleCompressU16 -> CanHuffman (fseu16_test.go:881-889).  Histogram and bit emission on the device, the code
+ * construction (<= 65536 list entries) on the host between them.  *out_len receives the stream size (also with
+ * MICGPU_E_SIZE).  Symbols of equal frequency are ordered by a stable sort (ascending symbol, the delimiter last) where
+ * the reference's sort.Slice is unstable: the bytes can differ from Go's there; either decoder reads either stream. */
+int micgpu_huff_compress(const uint16_t *symbols, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+int micgpu_delta_rle_huff_compress(const uint16_t *pixels, int width, int height, uint16_t max_value, uint8_t *out, size_t cap,
+                                   size_t *out_len);
 int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t *const *blobs, const size_t *lens, uint16_t *const *outs, const size_t *caps,
                                        int *rows, int *cols, int *status);
 

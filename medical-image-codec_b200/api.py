@@ -120,6 +120,8 @@ lib.micgpu_wsi_decompress_tiles.argtypes = [C.c_void_p, C.c_size_t, C.c_int, _ip
 lib.micgpu_wsi_decompress_region.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _ip, _ip]
 lib.micgpu_rgb_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
 lib.micgpu_wavelet_v2_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _ip, _ip]
+lib.micgpu_huff_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+lib.micgpu_delta_rle_huff_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
 lib.micgpu_huff_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
 lib.micgpu_delta_rle_huff_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
 lib.micgpu_decoder_add_huff_unit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64]
@@ -491,6 +493,26 @@ def WaveletV2RLEFSEDecompressU16(compressed):
 
 
 WaveletV2SIMDRLEFSEDecompressU16 = WaveletV2RLEFSEDecompressU16
+
+
+def CanHuffmanCompressU16(symbols) -> bytes:
+    """canhuffmancompressu16.go:46-81 (Init + Compress) -> one canonical-Huffman stream."""
+    a = np.ascontiguousarray(symbols, dtype=np.uint16).ravel()
+    cap = 9 + 5 * 65536 + 4 * a.size + 16      # header + symbol list + every symbol escaped (<= 32 bits each)
+    out = np.empty(cap, np.uint8)
+    got = C.c_size_t()
+    _check(lib.micgpu_huff_compress(a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(got)))
+    return out[: got.value].tobytes()
+
+
+def DeltaRleHuffCompressU16(pixels, width: int, height: int, max_value: int) -> bytes:
+    """DeltaRleCompressU16.Compress -> CanHuffmanCompressU16 (fseu16_test.go:881-889)."""
+    a = np.ascontiguousarray(pixels, dtype=np.uint16).ravel()
+    cap = 9 + 5 * 65536 + 4 * (3 * a.size + 4096) + 16
+    out = np.empty(cap, np.uint8)
+    got = C.c_size_t()
+    _check(lib.micgpu_delta_rle_huff_compress(a.ctypes.data, width, height, max_value, out.ctypes.data, out.size, C.byref(got)))
+    return out[: got.value].tobytes()
 
 
 def CanHuffmanDecompressU16(compressed) -> np.ndarray:

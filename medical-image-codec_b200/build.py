@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmicgpu.so")
-SOURCES = ["k_table.cu", "k_ans.cu", "k_ans_serial.cu", "k_huff.cu", "k_rle.cu", "k_delta.cu", "k_delta_scan.cu", "k_grad.cu", "k_misc.cu", "k_wavelet.cu", "k_enc_rle.cu", "k_enc_fse.cu", "k_enc_front.cu", "micgpu_host.cu", "micgpu_enc_host.cu"]
+SOURCES = ["k_table.cu", "k_ans.cu", "k_ans_serial.cu", "k_huff.cu", "k_rle.cu", "k_delta.cu", "k_delta_scan.cu", "k_grad.cu", "k_misc.cu", "k_wavelet.cu", "k_enc_rle.cu", "k_enc_fse.cu", "k_enc_front.cu", "micgpu_host.cu", "micgpu_enc_host.cu", "micgpu_huff_host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--shared", "-t", "0",

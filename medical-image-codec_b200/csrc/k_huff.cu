@@ -21,6 +21,7 @@
 // The symbols go where K2 puts ANS states; K3 maps states through tabS, so this kernel also writes an identity tabS for
 // the unit (the host reserves tableLog-16 regions for it: 65536 code-table cells in tabA, 65536 identity cells in tabS).
 // A read past the end of the stream, which Go answers with stale window bits or a slice panic, is MIC_E_BITSTREAM here.
+// The encode direction (histogram, bit emission) is at the end of the file.
 #include "mic_device.cuh"
 
 namespace micgpu {
@@ -266,6 +267,150 @@ void launch_huff_decode(MicUnit* d_units, const int* d_list, int nlist, const ui
   if (nlist <= 0) return;
   const int grid = nlist < sm_count * 4 ? nlist : sm_count * 4;
   k_huff_decode<<<grid, HUFF_THREADS, 0, st>>>(d_units, d_list, nlist, d_comp, d_tabA, d_tabS, d_states, serial);
+}
+
+}  // namespace micgpu
+
+// ---- encode direction (CanHuffmanCompressU16.Compress, canhuffmancompressu16.go:52-81) ------------------------------
+// The code itself (frequencies -> code lengths -> canonical codes) is a few thousand operations on at most 65536 list
+// entries and stays on the host (micgpu_huff_host.cu); what scales with the input is the histogram and the bit
+// emission.  enc[s] = code | codeLen << 24 | delimiter << 31 (GenerateAllSymbolTable, :83-106); a symbol outside the list
+// is the delimiter's code followed by the symbol in pixelDepth bits, i.e. one field of codeLen + pixelDepth <= 32 bits.
+namespace micgpu {
+
+namespace {
+constexpr int HENC_THREADS = 256;
+constexpr int HENC_PER_THREAD = 16;
+constexpr int HENC_CHUNK = HENC_THREADS * HENC_PER_THREAD;
+
+__device__ __forceinline__ void huff_field(uint32_t e, uint32_t sym, int depth, uint32_t& v, uint32_t& nb) {
+  nb = (e >> 24) & 0x7Fu;
+  v = e & 0xFFFFFFu;
+  if (e >> 31) {
+    v = depth ? (v << depth) | sym : v;
+    nb += (uint32_t)depth;
+  }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(256) k_huff_hist(const uint16_t* __restrict__ sym, unsigned long long n, uint32_t* __restrict__ hist) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+    atomicAdd(&hist[sym[i]], 1u);
+}
+
+// bits of every chunk of HENC_CHUNK symbols
+__global__ void __launch_bounds__(HENC_THREADS)
+k_huff_chunk_bits(const uint16_t* __restrict__ sym, unsigned long long n, const uint32_t* __restrict__ enc, int depth,
+                  unsigned long long* __restrict__ chunk_bits) {
+  __shared__ uint32_t s_w[HENC_THREADS / 32];
+  const unsigned long long base = (unsigned long long)blockIdx.x * HENC_CHUNK;
+  uint32_t bits = 0;
+  for (int k = 0; k < HENC_PER_THREAD; k++) {
+    const unsigned long long i = base + (unsigned long long)k * HENC_THREADS + threadIdx.x;
+    if (i < n) {
+      uint32_t v, nb;
+      huff_field(enc[sym[i]], sym[i], depth, v, nb);
+      bits += nb;
+    }
+  }
+  for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = bits;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < HENC_THREADS / 32; w++) t += s_w[w];
+    chunk_bits[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the chunk totals in place (one CTA; a 5 M-symbol stream has 1228 chunks); total[0] = sum
+__global__ void __launch_bounds__(256) k_huff_scan(unsigned long long* __restrict__ chunk_bits, int nchunks, unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long s_part[256];
+  const int per = (nchunks + 255) / 256;
+  const int lo = threadIdx.x * per, hi = min(lo + per, nchunks);
+  unsigned long long sum = 0;
+  for (int i = lo; i < hi; i++) sum += chunk_bits[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  unsigned long long before = 0;
+  for (int t = 0; t < (int)threadIdx.x; t++) before += s_part[t];
+  for (int i = lo; i < hi; i++) {
+    const unsigned long long v = chunk_bits[i];
+    chunk_bits[i] = before;
+    before += v;
+  }
+  if (threadIdx.x == 255) total[0] = before;
+}
+
+// every symbol's field to its place in the MSB-first bit string that starts `first_bit` bits into out (zeroed but for the
+// header the host wrote).  Thread t of a chunk owns symbols [16 t, 16 t + 16): consecutive fields, so whole words are
+// assembled in a register; the first and last word of a thread's run are shared with its neighbours, hence atomicOr.
+__global__ void __launch_bounds__(HENC_THREADS)
+k_huff_emit(const uint16_t* __restrict__ sym, unsigned long long n, const uint32_t* __restrict__ enc, int depth,
+            const unsigned long long* __restrict__ chunk_off, unsigned long long first_bit, uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_w[HENC_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long base = (unsigned long long)blockIdx.x * HENC_CHUNK + (unsigned long long)tid * HENC_PER_THREAD;
+  uint32_t v[HENC_PER_THREAD], nb[HENC_PER_THREAD], mine = 0;
+#pragma unroll
+  for (int k = 0; k < HENC_PER_THREAD; k++) {
+    v[k] = 0; nb[k] = 0;
+    if (base + k < n) huff_field(enc[sym[base + k]], sym[base + k], depth, v[k], nb[k]);
+    mine += nb[k];
+  }
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  uint32_t before = inc - mine;
+  for (int w = 0; w < warp; w++) before += s_w[w];
+  unsigned long long p = first_bit + chunk_off[blockIdx.x] + before;     // bit position of this thread's first field
+  // 64-bit accumulator holding the bits of word `w` (top-aligned) and what spills into the next one
+  unsigned long long w = p >> 5;
+  uint32_t fill = (uint32_t)(p & 31);          // bits of word w that belong to earlier threads (or the header)
+  unsigned long long acc = 0;                  // bits [fill, ...) of word w, top-aligned at bit 63 - fill
+  auto flush = [&](uint32_t word) {            // word w is complete (or the run ends): big-endian bytes in memory
+    atomicOr(&out[w], __byte_perm(word, 0, 0x0123));
+  };
+#pragma unroll
+  for (int k = 0; k < HENC_PER_THREAD; k++) {
+    if (nb[k]) {
+      acc |= (unsigned long long)v[k] << (64 - fill - nb[k]);      // fill < 32, nb <= 32
+      fill += nb[k];
+      if (fill >= 32) {
+        flush((uint32_t)(acc >> 32));
+        acc <<= 32;
+        fill -= 32;
+        w++;
+      }
+    }
+  }
+  if (fill && (uint32_t)(acc >> 32)) flush((uint32_t)(acc >> 32));
+}
+
+void launch_huff_hist(const uint16_t* d_sym, unsigned long long n, uint32_t* d_hist, int sm_count, cudaStream_t st) {
+  if (!n) return;
+  const unsigned long long want = (n + 255) / 256;
+  const int grid = (int)(want < (unsigned long long)sm_count * 8 ? want : (unsigned long long)sm_count * 8);
+  k_huff_hist<<<grid, 256, 0, st>>>(d_sym, n, d_hist);
+}
+
+int huff_enc_chunks(unsigned long long n) { return (int)((n + HENC_CHUNK - 1) / HENC_CHUNK); }
+
+void launch_huff_emit(const uint16_t* d_sym, unsigned long long n, const uint32_t* d_enc, int depth, unsigned long long* d_chunk,
+                      unsigned long long* d_total, unsigned long long first_bit, uint32_t* d_out, int phase, cudaStream_t st) {
+  const int nchunks = huff_enc_chunks(n);
+  if (!nchunks) return;
+  if (phase == 0) {
+    k_huff_chunk_bits<<<nchunks, HENC_THREADS, 0, st>>>(d_sym, n, d_enc, depth, d_chunk);
+    k_huff_scan<<<1, 256, 0, st>>>(d_chunk, nchunks, d_total);
+  } else {
+    k_huff_emit<<<nchunks, HENC_THREADS, 0, st>>>(d_sym, n, d_enc, depth, d_chunk, first_bit, d_out);
+  }
 }
 
 }  // namespace micgpu

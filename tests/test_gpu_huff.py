@@ -38,6 +38,37 @@ def test_huffman_symbols(mic, oracle, name, sym, monkeypatch):
     assert got.size == sym.size and np.array_equal(got, sym)
 
 
+@pytest.mark.parametrize("name,sym", list(_streams()), ids=[n for n, _ in _streams()])
+def test_huffman_encoder_bytes(mic, oracle, name, sym):
+    # the device encoder (histogram + bit emission on the GPU, code construction on the host) against the restatement:
+    # same stream byte for byte, and the stream decodes on the device
+    want = oracle.huff_compress(sym)
+    got = mic.CanHuffmanCompressU16(sym)
+    assert got == want
+    assert np.array_equal(mic.CanHuffmanDecompressU16(got), sym)
+
+
+def test_delta_rle_huff_encoder_bytes(mic, oracle, synth):
+    for (w, h, img) in [(5, 2, REF_INPUT), (333, 217, synth.xr_image(9, 333, 217).ravel()),
+                        (256, 256, np.fromfile(os.path.join(GOLDEN, "MR_256_256_image.bin"), dtype="<u2"))]:
+        mx = int(img.max())
+        got = mic.DeltaRleHuffCompressU16(img, w, h, mx)
+        assert got == oracle.delta_rle_huff_compress(img, w, h, mx)
+        assert np.array_equal(mic.DeltaRleHuffDecompressU16(got, w, h), img)
+
+
+def test_huffman_encoder_large_and_small_buffers(mic, oracle):
+    rng = np.random.default_rng(17)
+    sym = np.minimum(rng.geometric(0.05, 3_000_000), 1023).astype(np.uint16)      # 733 chunks: the chunk scan and word seams
+    blob = mic.CanHuffmanCompressU16(sym)
+    assert blob == oracle.huff_compress(sym)
+    out = np.empty(16, np.uint8)
+    import ctypes as C
+    got = C.c_size_t()
+    rc = mic.lib.micgpu_huff_compress(sym.ctypes.data, sym.size, out.ctypes.data, out.size, C.byref(got))
+    assert rc == mic.api.E_SIZE and got.value == len(blob)
+
+
 def test_huffman_multi_tile_stream(mic, oracle):
     # 4 M symbols: ~250 tiles of 256 subsequences; the carried start of every tile and the running output offset are exercised
     rng = np.random.default_rng(3)

@@ -223,7 +223,7 @@ int micgpu_rgb_decompress(const uint8_t *blob, size_t len, int width, int height
 int micgpu_wavelet_v2_decompress(const uint8_t *blob, size_t len, uint16_t *pixels_out, size_t cap_px, int *rows, int *cols);
 /* The V1 wavelet layouts: WaveletFSEDecompressU16 (with_rle = 0, waveletfsecompressu16.go:124-163) and
  * WaveletRLEFSEDecompressU16 (with_rle = 1, :624-669): coefficients in raster order, interleaved in-place lifting
- * (waveletInverse2DRegion :180-189).  Decode only: the reference replaced these encoders by WaveletV2. */
+ * (waveletInverse2DRegion :180-189).  (The reference replaced these layouts by WaveletV2.) */
 int micgpu_wavelet_v1_decompress(const uint8_t *blob, size_t len, int with_rle, uint16_t *pixels_out, size_t cap_px, int *rows, int *cols);
 /* The canonical-Huffman back end of the legacy streams.  A Huffman stream has no magic byte, so these are
  * explicit entry points.  micgpu_huff_decompress = CanHuffmanDecompressU16.Init + ReadTable + Decompress
@@ -246,6 +246,10 @@ int micgpu_decoder_add_huff_unit(micgpu_decoder *d, const uint8_t *stream, size_
 int micgpu_huff_compress(const uint16_t *symbols, size_t n, uint8_t *out, size_t cap, size_t *out_len);
 int micgpu_delta_rle_huff_compress(const uint16_t *pixels, int width, int height, uint16_t max_value, uint8_t *out, size_t cap,
                                    size_t *out_len);
+/* ... and their encoders, WaveletFSECompressU16 (with_rle = 0, :71-123) / WaveletRLEFSECompressU16 (with_rle = 1, :551-623):
+ * levels are clamped to [1, 4] as the reference does. */
+int micgpu_wavelet_v1_compress(const uint16_t *pixels, int rows, int cols, uint16_t max_value, int levels, int with_rle,
+                               uint8_t *out, size_t cap, size_t *out_len);
 int micgpu_wavelet_v2_decompress_batch(int n, const uint8_t *const *blobs, const size_t *lens, uint16_t *const *outs, const size_t *caps,
                                        int *rows, int *cols, int *status);
 

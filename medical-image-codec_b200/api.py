@@ -138,6 +138,7 @@ lib.micgpu_pica_boundaries.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i
 lib.micgpu_pics_compress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, C.c_int,
                                            C.POINTER(C.c_void_p), _szp, _szp, _ip]
 lib.micgpu_mic2_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
+lib.micgpu_wavelet_v1_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_int, C.c_void_p, C.c_size_t, _szp]
 lib.micgpu_wavelet_v2_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t, _szp]
 lib.micgpu_wavelet_v2_compress_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int,
                                                  C.POINTER(C.c_void_p), _szp, _szp, _ip]
@@ -688,6 +689,24 @@ def WaveletV2RLEFSECompressU16(pixels, rows: int, cols: int, max_value: int, lev
 
 
 WaveletV2SIMDRLEFSECompressU16 = WaveletV2RLEFSECompressU16
+
+
+def _wavelet_v1_compress(pixels, rows, cols, max_value, levels, with_rle) -> bytes:
+    a = _u16(pixels)
+    out = np.empty(8 * a.size + 8192, np.uint8)
+    ol = C.c_size_t()
+    _check(lib.micgpu_wavelet_v1_compress(a.ctypes.data, rows, cols, max_value, levels, with_rle, out.ctypes.data, out.size, C.byref(ol)))
+    return out[: ol.value].tobytes()
+
+
+def WaveletFSECompressU16(pixels, rows: int, cols: int, max_value: int, levels: int) -> bytes:
+    """waveletfsecompressu16.go:71 (V1 layout: interleaved lifting, raster order, 4-state FSE)."""
+    return _wavelet_v1_compress(pixels, rows, cols, max_value, levels, 0)
+
+
+def WaveletRLEFSECompressU16(pixels, rows: int, cols: int, max_value: int, levels: int) -> bytes:
+    """waveletfsecompressu16.go:551 (V1 layout behind the RLE layer)."""
+    return _wavelet_v1_compress(pixels, rows, cols, max_value, levels, 1)
 
 
 def WaveletV2CompressBatch(images, rows: int, cols: int, max_values, levels: int):

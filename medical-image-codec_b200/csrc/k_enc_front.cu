@@ -335,6 +335,55 @@ void launch_wavelet_forward(const uint16_t* d_px, int32_t* d_A, int32_t* d_B, in
     c = (c + 1) / 2;
   }
 }
+// V1 layouts (waveletForward2DRegion, waveletfsecompressu16.go:167-177): wt53Forward1D (waveletu16.go:26-73) IN PLACE on
+// interleaved samples (even = low, odd = high), every row of the r x c corner, then every column; the next level takes the
+// top-left (r+1)/2 x (c+1)/2 corner of that interleaved buffer.  Out of place here, one output sample per thread:
+//   d[2i+1] = x[2i+1] - ((x[2i] + x[2i+2]) >> 1)            (x[2i] again at the right edge)
+//   s[2i]   = x[2i]   + ((dL + dR + 2) >> 2)                dR = d[2i+1] (d[2i-1] at the end of an odd-length signal, 0 if alone), dL = d[2i-1] (dR at i == 0)
+// AXIS 0: along columns (stride = row pitch), AXIS 1: along rows.
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+k_wt53_il_fwd(const int32_t* __restrict__ A, int32_t* __restrict__ B, unsigned r, unsigned c, unsigned cols, unsigned long long img_stride) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned y = blockIdx.y;
+  if (x >= c || y >= r) return;
+  const int32_t* in = A + (unsigned long long)blockIdx.z * img_stride;
+  int32_t* out = B + (unsigned long long)blockIdx.z * img_stride;
+  const unsigned n = AXIS == 0 ? r : c;
+  const unsigned p = AXIS == 0 ? y : x;
+  auto X = [&](unsigned q) -> int {
+    return AXIS == 0 ? in[(unsigned long long)q * cols + x] : in[(unsigned long long)y * cols + q];
+  };
+  auto odd = [&](unsigned q) -> int {              // high-pass sample at odd position q
+    const int l = X(q - 1), rr = q + 1 < n ? X(q + 1) : l;
+    return X(q) - ((l + rr) >> 1);
+  };
+  int res;
+  if (n < 2) res = X(p);
+  else if (p & 1u) res = odd(p);
+  else {
+    int dR;
+    if (p + 1 < n) dR = odd(p + 1);
+    else dR = p > 0 ? odd(p - 1) : 0;
+    const int dL = p > 0 ? odd(p - 1) : dR;
+    res = X(p) + ((dL + dR + 2) >> 2);
+  }
+  out[(unsigned long long)y * cols + x] = res;
+}
+
+void launch_wavelet_forward_v1(const uint16_t* d_px, int32_t* d_A, int32_t* d_B, int nimg, unsigned rows, unsigned cols, int levels, int sm_count,
+                               cudaStream_t st) {
+  const unsigned total = rows * cols;
+  k_u16_to_i32<<<sm_count * 8, 256, 0, st>>>(d_px, d_A, (unsigned long long)total * nimg);
+  unsigned r = rows, c = cols;
+  for (int l = 0; l < levels; l++) {
+    const dim3 grid((c + 255) / 256, r, nimg);
+    k_wt53_il_fwd<1><<<grid, 256, 0, st>>>(d_A, d_B, r, c, cols, total);     // rows: A -> B (the corner only)
+    k_wt53_il_fwd<0><<<grid, 256, 0, st>>>(d_B, d_A, r, c, cols, total);     // columns: B -> A
+    r = (r + 1) / 2;
+    c = (c + 1) / 2;
+  }
+}
 void launch_wavelet_pack(const int32_t* d_A, uint16_t* d_V, MicEncUnit* d_units, const int* d_unit_of_img, int nimg, const WaveletGeom& G, cudaStream_t st) {
   if (nimg <= 0) return;
   const unsigned total = G.rows * G.cols;

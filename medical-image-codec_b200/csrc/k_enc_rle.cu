@@ -138,6 +138,10 @@ k_enc_rle_segments(MicEncUnit* __restrict__ units, int nunits, const uint16_t* _
     MicEncUnit* U = &units[ui];
     __syncthreads();
     if (U->status != MIC_ENC_OK) continue;
+    if (U->kind == MIC_ENC_RAW) {          // no RLE layer: S = V (k_enc_rle_emit copies it)
+      if (threadIdx.x == 0) { U->v_len = U->width; U->nseg = 0; U->mid = 0; }
+      continue;
+    }
     if (U->kind == MIC_ENC_RLE) {
       if (threadIdx.x == 0) U->v_len = U->width;
       // rleMaxVal / resMax = max over V when the caller asks for it (multiframecompress.go:194-199)
@@ -232,6 +236,13 @@ k_enc_rle_offsets(MicEncUnit* __restrict__ units, int nunits, uint32_t* __restri
     MicEncUnit* U = &units[ui];
     __syncthreads();
     if (U->status != MIC_ENC_OK) continue;
+    if (U->kind == MIC_ENC_RAW) {
+      if (threadIdx.x == 0) {
+        if (U->width > U->s_cap) U->status = MIC_ENC_CAPACITY;
+        U->s_len = U->width;
+      }
+      continue;
+    }
     const unsigned n = U->v_len, nseg = U->nseg, mid = U->mid, P = mid - 3;
     uint32_t* sg = segs + U->seg_off * 2;
     unsigned out = U->kind == MIC_ENC_SPATIAL ? 1u : 3u;   // word 0 (+ the 2 length words of Compress, rlecompressu16.go:85-87)
@@ -274,6 +285,10 @@ k_enc_rle_emit(MicEncUnit* __restrict__ units, int nunits, const uint16_t* __res
     const uint16_t* V = enc_stream(U, src, Vbuf);
     const uint32_t* sg = segs + U->seg_off * 2;
     uint16_t* S = Sbuf + U->s_off;
+    if (U->kind == MIC_ENC_RAW) {
+      for (unsigned i = threadIdx.x; i < U->width; i += E_THREADS) S[i] = V[i];
+      continue;
+    }
     if (threadIdx.x == 0) {
       if (U->kind == MIC_ENC_SPATIAL) {
         S[0] = (uint16_t)((1u << (32 - __clz(U->max_value))) - 1u);          // Init(width,height,delimiter)

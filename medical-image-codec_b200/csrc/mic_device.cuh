@@ -137,6 +137,9 @@ void launch_downsample2x(const uint8_t* d_src, uint8_t* d_dst, unsigned w, unsig
 void launch_tile_planes(const TilePlaneJob* d_jobs, int njobs, const uint8_t* d_images, uint16_t* d_planes, cudaStream_t st);
 void launch_plane_stats(const uint16_t* d_planes, const unsigned long long* d_offs, unsigned long long npx, int nplanes, unsigned* d_stats, cudaStream_t st);
 void launch_wavelet_forward(const uint16_t* d_px, int32_t* d_A, int32_t* d_B, int nimg, const WaveletGeom& G, int sm_count, cudaStream_t st);
+// V1 layouts: interleaved in-place lifting on the top-left corner per level (result in d_A)
+void launch_wavelet_forward_v1(const uint16_t* d_px, int32_t* d_A, int32_t* d_B, int nimg, unsigned rows, unsigned cols, int levels, int sm_count,
+                               cudaStream_t st);
 void launch_wavelet_pack(const int32_t* d_A, uint16_t* d_V, MicEncUnit* d_units, const int* d_unit_of_img, int nimg, const WaveletGeom& G, cudaStream_t st);
 void launch_gather_bytes(const GatherJob* d_jobs, int njobs, const uint8_t* d_src, uint8_t* d_dst, cudaStream_t st);
 void launch_plane_raw(const GatherJob* d_jobs, int njobs, const uint16_t* d_planes, uint8_t* d_dst, cudaStream_t st);

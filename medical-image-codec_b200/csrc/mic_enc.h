@@ -9,6 +9,7 @@
 enum MicEncKind {
   MIC_ENC_SPATIAL = 0,   // source = pixels (w x h); V = [maxValue, delta symbols / escapes]
   MIC_ENC_RLE = 1,       // source = ready-made symbol stream V (residuals / wavelet coefficients); RleCompressU16.Compress
+  MIC_ENC_RAW = 2,       // source = ready-made symbol stream that goes to FSE as it is (WaveletFSECompressU16, waveletfsecompressu16.go:71-123)
 };
 
 enum MicEncStatus {

@@ -760,6 +760,66 @@ int micgpu_wavelet_v2_compress_batch(int n, const uint16_t* const* pixels, int r
   return first;
 }
 
+// WaveletFSECompressU16 (with_rle = 0, waveletfsecompressu16.go:71-123) and WaveletRLEFSECompressU16 (with_rle = 1, :551-623):
+// the V1 layouts -- interleaved in-place lifting, levels clamped to [1, 4], coefficients in raster order, then 4-state FSE
+// directly or behind the RLE layer (whose header also carries the length of the coefficient stream)
+int micgpu_wavelet_v1_compress(const uint16_t* pixels, int rows, int cols, uint16_t max_value, int levels, int with_rle, uint8_t* out, size_t cap,
+                               size_t* out_len) {
+  if (!pixels || !out || rows <= 0 || cols <= 0) return fail(MICGPU_E_HEADER, "bad argument");
+  micgpu_encoder* e = default_encoder(current_device());
+  if (!e) return MICGPU_E_CUDA;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (levels < 1) levels = 1;
+  if (levels > 4) levels = 4;
+  int applied = levels;
+  {
+    int r = rows, c = cols;
+    for (int l = 0; l < levels; l++) {
+      if (r < 2 || c < 2) { applied = l; break; }
+      r = (r + 1) / 2; c = (c + 1) / 2;
+    }
+  }
+  const unsigned long long px = (unsigned long long)rows * cols;
+  if (px > 0x7FFFFFFFull / 3) return fail(MICGPU_E_UNSUPPORTED, "image too large for one coefficient stream");
+  WaveletGeom G;                       // raster order = one segment that covers the image
+  memset(&G, 0, sizeof G);
+  G.rows = (unsigned)rows; G.cols = (unsigned)cols; G.levels = applied; G.nseg = 1;
+  G.seg_start[0] = 0; G.seg_y0[0] = 0; G.seg_x0[0] = 0; G.seg_w[0] = (unsigned)cols;
+  e->units.clear();
+  // V holds one word per coefficient, three per escaped coefficient; rleMaxVal as for WaveletV2 (:595-601)
+  const int u = enc_add_unit(e, with_rle ? MIC_ENC_RLE : MIC_ENC_RAW, 0, (unsigned)(3 * px), 1, 0xFFFFFFFEu, 4);
+  e->units[u].no_ladder = 1;           // FSECompressU16FourState, no fallback
+  int rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  if ((rc = e->d_img.ensure((size_t)px * 2 + 64))) return rc;
+  if ((rc = e->d_wA.ensure((size_t)px * 4 + 64))) return rc;
+  if ((rc = e->d_wB.ensure((size_t)px * 4 + 64))) return rc;
+  if ((rc = e->d_src.ensure((size_t)3 * px * 2 + 64))) return rc;
+  if ((rc = e->d_stats.ensure(sizeof(int) + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->d_img.p, pixels, (size_t)px * 2, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_stats.p, &u, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  launch_wavelet_forward_v1((const uint16_t*)e->d_img.p, (int32_t*)e->d_wA.p, (int32_t*)e->d_wB.p, 1, (unsigned)rows, (unsigned)cols, applied,
+                            e->sm_count, e->stream);
+  rc = enc_run(e, (const uint16_t*)e->d_src.p, [&](MicEncUnit* du, cudaStream_t st) {
+    launch_wavelet_pack((const int32_t*)e->d_wA.p, (uint16_t*)e->d_src.p, du, (const int*)e->d_stats.p, 1, G, st);
+  });
+  if (rc) return rc;
+  const MicEncUnit& r = e->h_units[0];
+  if (r.status != MIC_ENC_OK) return enc_status_to_rc(r.status);
+  std::vector<std::vector<uint8_t>> blobs;
+  if ((rc = fetch_frames(e, 0, 1, blobs))) return rc;
+  const size_t hdr = with_rle ? 15 : 11;
+  if (out_len) *out_len = hdr + blobs[0].size();
+  if (hdr + blobs[0].size() > cap) return fail(MICGPU_E_SIZE, "output buffer too small");
+  const uint32_t r32 = (uint32_t)rows, c32 = (uint32_t)cols, n32 = r.v_len;   // v_len: words of the coefficient stream
+  for (int k = 0; k < 4; k++) { out[k] = (uint8_t)(r32 >> (8 * k)); out[4 + k] = (uint8_t)(c32 >> (8 * k)); }
+  out[8] = (uint8_t)max_value; out[9] = (uint8_t)(max_value >> 8);
+  out[10] = (uint8_t)applied;
+  if (with_rle) for (int k = 0; k < 4; k++) out[11 + k] = (uint8_t)(n32 >> (8 * k));
+  memcpy(out + hdr, blobs[0].data(), blobs[0].size());
+  return 0;
+}
+
 int micgpu_wavelet_v2_compress(const uint16_t* pixels, int rows, int cols, uint16_t max_value, int levels, uint8_t* out, size_t cap, size_t* out_len) {
   return micgpu_wavelet_v2_compress_batch(1, &pixels, rows, cols, &max_value, levels, &out, &cap, out_len, nullptr);
 }

@@ -73,7 +73,7 @@ def test_wavelet_bad_magic(mic, oracle):
         mic.WaveletV2RLEFSEDecompressU16(bytes(blob))
 
 
-# ---- SURVEY 8(f).4 (wavelet half): the V1 layouts, decode only ------------------------------------------------------------
+# ---- SURVEY 8(f).4 (wavelet half): the V1 layouts ---------------------------------------------------------------------------
 @pytest.mark.parametrize("with_rle", [0, 1])
 @pytest.mark.parametrize("rows,cols,levels", [(64, 40, 1), (65, 33, 2), (128, 96, 3), (257, 129, 4), (300, 517, 4), (40, 1000, 9), (9, 4000, 3), (4000, 9, 4)])
 def test_wavelet_v1_layouts_decode(mic, oracle, synth, with_rle, rows, cols, levels):
@@ -103,3 +103,35 @@ def test_wavelet_v1_reference_images_and_escapes(mic, oracle):
     for bad in (bytes(blob[:14]), bytes(blob[:15]) + b"\x00" * 8, bytes(blob[:40])):
         with pytest.raises(mic.MicGpuError):
             mic.WaveletRLEFSEDecompressU16(bad)
+
+
+@pytest.mark.parametrize("with_rle", [0, 1])
+@pytest.mark.parametrize("rows,cols,levels", [(64, 40, 1), (65, 33, 2), (128, 96, 3), (257, 129, 4), (300, 517, 4), (40, 1000, 9), (9, 4000, 3), (4000, 9, 4),
+                                               (2, 2, 3), (3, 1, 2)])
+def test_wavelet_v1_layouts_encode_bytes(mic, oracle, with_rle, rows, cols, levels):
+    """WaveletFSECompressU16 / WaveletRLEFSECompressU16 (waveletfsecompressu16.go:71-123, 551-623): the device encoder
+    (interleaved forward lifting, raster-order pack, FSE-4 directly or behind RLE) emits the oracle's bytes, and they decode."""
+    px, mx = _field(rows, cols, 7), 4095
+    enc = mic.WaveletRLEFSECompressU16 if with_rle else mic.WaveletFSECompressU16
+    dec = mic.WaveletRLEFSEDecompressU16 if with_rle else mic.WaveletFSEDecompressU16
+    try:
+        want = oracle.wavelet_v1_compress(px, rows, cols, mx, levels, with_rle)
+    except Exception:
+        with pytest.raises(mic.MicGpuError):          # e.g. a 3 x 1 image: the FSE stage rejects the tiny stream in both
+            enc(px, rows, cols, mx, levels)
+        return
+    got = enc(px, rows, cols, mx, levels)
+    assert got == want
+    out, r, c = dec(got)
+    assert (r, c) == (rows, cols) and np.array_equal(out, px)
+
+
+def test_wavelet_v1_encode_reference_images_and_escapes(mic, oracle):
+    import os
+    from conftest import GOLDEN
+
+    for name, w, h in (("MR_256_256", 256, 256), ("CT_512_512", 512, 512)):   # CT: full 16-bit range -> escape triples
+        px = np.fromfile(os.path.join(GOLDEN, f"{name}_image.bin"), dtype="<u2")
+        for with_rle in (0, 1):
+            enc = mic.WaveletRLEFSECompressU16 if with_rle else mic.WaveletFSECompressU16
+            assert enc(px, h, w, int(px.max()), 3) == oracle.wavelet_v1_compress(px, h, w, int(px.max()), 3, with_rle), (name, with_rle)

@@ -15,6 +15,9 @@
 // concatenation of those fields in descending symbol order, i.e. a suffix sum of nbBits gives every field its bit
 // position; a CTA packs them through a shared-memory word buffer and appends the final states (N-1 .. 0,
 // tableLog bits each) and the 1-bit end mark (bitwriter.go:162-168).
+#include <algorithm>
+#include <cstdlib>
+
 #include "mic_device.cuh"
 #include "mic_enc.h"
 
@@ -431,16 +434,18 @@ k_enc_ans(MicEncUnit* __restrict__ units, const int* __restrict__ list, int nlis
       unsigned x = 0;
       if ((unsigned)k < n) {
         long long i = (long long)(n - 1) - (long long)((n - 1 - (unsigned)k) % N);
-        unsigned sym = S[i];
+        unsigned sym1 = i >= N ? S[i - N] : 0u;
+        uint2 tt = __ldg(TT + S[i]);
         for (; i >= 0; i -= N) {
-          const unsigned nsym = i >= N ? S[i - N] : 0u;
-          const uint2 tt = __ldg(TT + sym);
+          const unsigned sym2 = i >= 2 * N ? S[i - 2 * N] : 0u;   // symbols two steps ahead, table entries one step ahead
+          const uint2 tt1 = __ldg(TT + sym1);
           const unsigned freq = tt.x & 0xFFFFFu, k0 = tt.x >> 20;
           const unsigned xL = x + Sz;
           const unsigned kk = k0 - (xL < (freq << k0) ? 1u : 0u);
           T[i] = (xL & ((1u << kk) - 1u)) | (kk << 16);
           x = tt.y + (xL >> kk) - freq;
-          sym = nsym;
+          tt = tt1;
+          sym1 = sym2;
         }
       }
       T[n + k] = x & (Sz - 1u);
@@ -451,15 +456,97 @@ k_enc_ans(MicEncUnit* __restrict__ units, const int* __restrict__ list, int nlis
     // from the histogram of this very stream, so every symbol has cells whenever the unit's status is still OK here.
     if ((unsigned)k < n) {
       long long i = (long long)(n - 1) - (long long)((n - 1 - (unsigned)k) % N);   // last index congruent to k mod N
-      unsigned sym = S[i];
+      // The chain is state -> nbBits -> cell -> stateTable[cell] -> state.  The symbolTT entry of a step depends on the symbol
+      // only, so it is loaded one step ahead (and the symbol two steps ahead): on a wide alphabet that entry comes from L2,
+      // and fetched inside its own step it sat on the chain (WaveletV2 x16: k_enc_ans<4> 471 ms per call with it there).
+      unsigned sym1 = i >= N ? S[i - N] : 0u;
+      uint2 tt = __ldg(TT + S[i]);
       for (; i >= 0; i -= N) {
-        const unsigned nsym = i >= N ? S[i - N] : 0u;      // prefetch the next symbol of this chain
-        const uint2 tt = __ldg(TT + sym);
+        const unsigned sym2 = i >= 2 * N ? S[i - 2 * N] : 0u;
+        const uint2 tt1 = __ldg(TT + sym1);                // index 0 past the first symbol: a valid entry, never used
         const unsigned nb = (state + tt.x) >> 16;
         const int cell = (int)(state >> nb) + (int)tt.y;
         T[i] = (state & ((1u << nb) - 1u)) | (nb << 16);
         state = Sz + __ldg(ST + cell);
-        sym = nsym;
+        tt = tt1;
+        sym1 = sym2;
+      }
+    }
+    T[n + k] = state & (Sz - 1u);
+  }
+}
+
+// The same chains with the unit's stateTable in SHARED memory: one warp per CTA, the 32 lanes copy the table (2 B per cell,
+// 16 KB for a 12-bit strip, 128 KB at tableLog 16), then lane k < N runs state k.  stateTable[cell] is the one load on the
+// state -> state chain; through L2 it costs several hundred cycles per symbol (WaveletV2 x16: 400 ms per call for sixteen
+// 5 M-symbol streams), from shared memory ~30.  Taken when every listed unit is resident at once (the latency-bound
+// regime: wavelet streams, MIC2 frames, a PICS batch: at most four waves of resident units); many short units (MIC3 planes)
+// keep the kernel above, whose 64 warps per SM hide the latency by numbers.
+template <int N, int D>
+__global__ void __launch_bounds__(32)
+k_enc_ans_smem(MicEncUnit* __restrict__ units, const int* __restrict__ list, int nlist, const uint16_t* __restrict__ Sbuf,
+               const uint16_t* __restrict__ state_tab, const uint2* __restrict__ sym_tt, uint32_t* __restrict__ Tbuf) {
+  extern __shared__ __align__(16) uint16_t s_st[];
+  const int k = threadIdx.x;
+  for (int li = blockIdx.x; li < nlist; li += gridDim.x) {
+    MicEncUnit* U = &units[list[li]];
+    __syncwarp();                                          // the previous unit's chains are done with the table
+    if (U->status != MIC_ENC_OK) continue;
+    const unsigned n = U->s_len, tl = U->table_log, Sz = 1u << tl;
+    const uint16_t* S = Sbuf + U->s_off;
+    const uint2* TT = sym_tt + U->tt_off;
+    uint32_t* T = Tbuf + U->t_off;
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(state_tab + U->tab_off);   // tab_off is a multiple of 8192 entries
+      uint4* dst = reinterpret_cast<uint4*>(s_st);
+      for (unsigned j = (unsigned)k; j < Sz / 8u; j += 32u) dst[j] = __ldg(src + j);
+    }
+    __syncwarp();
+    if (k >= N) continue;
+    unsigned state = Sz;
+    if ((unsigned)k < n) {
+      long long i = (long long)(n - 1) - (long long)((n - 1 - (unsigned)k) % N);
+      auto step = [&](long long at, uint2 tt) {
+        const unsigned nb = (state + tt.x) >> 16;
+        const int cell = (int)(state >> nb) + (int)tt.y;
+        T[at] = (state & ((1u << nb) - 1u)) | (nb << 16);
+        state = Sz + s_st[cell];
+      };
+      if (D > 1) {
+        // symbolTT entries D steps ahead, symbols 2 D steps ahead, in register queues indexed by step mod D: on a wide
+        // alphabet (wavelet coefficients, residuals) an entry comes from L2, several hundred cycles away from a chain
+        // whose step is now ~60
+        uint2 tq[D];
+        unsigned sq[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+          const long long a = i - (long long)j * N, b = i - (long long)(D + j) * N;
+          tq[j] = __ldg(TT + (a >= 0 ? S[a] : 0u));
+          sq[j] = b >= 0 ? S[b] : 0u;
+        }
+        while (i - (long long)(D - 1) * N >= 0) {
+#pragma unroll
+          for (int j = 0; j < D; j++) {
+            const uint2 tt = tq[j];
+            tq[j] = __ldg(TT + sq[j]);                         // the entry of step i - D N
+            const long long c = i - (long long)2 * D * N;
+            sq[j] = c >= 0 ? S[c] : 0u;                        // the symbol of the refill after that
+            step(i, tt);
+            i -= N;
+          }
+        }
+      }
+      // D == 1, and the last steps of a queued chain: symbol two steps ahead, entry one step ahead
+      if (i >= 0) {
+        unsigned sym1 = i >= N ? S[i - N] : 0u;
+        uint2 tt = __ldg(TT + S[i]);
+        for (; i >= 0; i -= N) {
+          const unsigned sym2 = i >= 2 * N ? S[i - 2 * N] : 0u;
+          const uint2 tt1 = __ldg(TT + sym1);
+          step(i, tt);
+          tt = tt1;
+          sym1 = sym2;
+        }
       }
     }
     T[n + k] = state & (Sz - 1u);
@@ -578,8 +665,41 @@ void launch_enc_tables(MicEncUnit* d_units, int nunits, const uint16_t* d_S, uin
 unsigned long long enc_tables_scratch_per_cta() { return K6_SCRATCH + 256; }
 
 void launch_enc_ans(MicEncUnit* d_units, const int* d_list, int nlist, int nstates, const uint16_t* d_S, const uint16_t* d_state_tab,
-                    const uint2* d_sym_tt, uint32_t* d_T, int sm_count, cudaStream_t st) {
+                    const uint2* d_sym_tt, uint32_t* d_T, int sm_count, cudaStream_t st, int max_table_log, bool any_rans) {
   if (nlist <= 0) return;
+  // stateTable in shared memory when every listed unit can be resident at once (k_enc_ans_smem); max_table_log bounds the
+  // tables of the list (the host's reservation, enc_plan), 0 = unknown.  rANS units use no stateTable.
+  static const int smem_cfg = [] { const char* e = getenv("MICGPU_K7_SMEM"); return e ? atoi(e) : 1; }();
+  if (smem_cfg && max_table_log >= 5 && max_table_log <= 16 && !any_rans) {
+    const size_t bytes = (size_t)2 << max_table_log;
+    const int per_sm = (int)std::min<size_t>((227 * 1024) / (bytes + 1024), 16);
+    if (per_sm >= 1 && nlist <= 4 * sm_count * per_sm) {   // at most four waves of resident units
+      auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        kern<<<nlist, 32, bytes, st>>>(d_units, d_list, nlist, d_S, d_state_tab, d_sym_tt, d_T);
+      };
+      // MICGPU_K7_DEPTH: how many steps ahead the symbolTT entries are fetched (8, or 1 for A/B runs).  WaveletV2 x16 encode per
+      // call: 724 ms with the tables read through L1/L2, 663 with the entry one step ahead, 505 with the state table in shared
+      // memory, 406 with the entries eight steps ahead.
+      static const int depth_cfg = [] { const char* e = getenv("MICGPU_K7_DEPTH"); return e ? atoi(e) : 8; }();
+      if (depth_cfg > 1) {
+        switch (nstates) {
+          case 1: go(k_enc_ans_smem<1, 8>); break;
+          case 2: go(k_enc_ans_smem<2, 8>); break;
+          case 4: go(k_enc_ans_smem<4, 8>); break;
+          default: go(k_enc_ans_smem<8, 8>); break;
+        }
+      } else {
+        switch (nstates) {
+          case 1: go(k_enc_ans_smem<1, 1>); break;
+          case 2: go(k_enc_ans_smem<2, 1>); break;
+          case 4: go(k_enc_ans_smem<4, 1>); break;
+          default: go(k_enc_ans_smem<8, 1>); break;
+        }
+      }
+      return;
+    }
+  }
   const int warps_per_cta = 4;
   int grid = (nlist + warps_per_cta - 1) / warps_per_cta;
   if (grid > sm_count * 16) grid = sm_count * 16;

@@ -120,7 +120,7 @@ void launch_enc_tables(MicEncUnit* d_units, int nunits, const uint16_t* d_S, uin
                        uint8_t* d_hdrs, int grid, cudaStream_t st);
 unsigned long long enc_tables_scratch_per_cta();
 void launch_enc_ans(MicEncUnit* d_units, const int* d_list, int nlist, int nstates, const uint16_t* d_S, const uint16_t* d_state_tab,
-                    const uint2* d_sym_tt, uint32_t* d_T, int sm_count, cudaStream_t st);
+                    const uint2* d_sym_tt, uint32_t* d_T, int sm_count, cudaStream_t st, int max_table_log = 0, bool any_rans = false);
 void launch_enc_pack(MicEncUnit* d_units, int nunits, const uint32_t* d_T, const uint8_t* d_hdrs, uint8_t* d_frames, int grid, cudaStream_t st);
 
 // Encode front ends (k_enc_front.cu)

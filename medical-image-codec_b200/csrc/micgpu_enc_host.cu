@@ -187,8 +187,18 @@ int enc_run(micgpu_encoder* e, const uint16_t* d_src, const EncHook& after_uploa
     size_t off = 0;
     for (int g = 0; g < 4; g++) {
       if (!lists[g].empty()) {
+        // the largest table a unit of this list can have (the reservation of enc_plan) decides whether the state tables
+        // go to shared memory (k_enc_ans_smem)
+        int max_log = 0;
+        bool any_rans = false;
+        for (int i : lists[g]) {
+          const MicEncUnit& u = e->units[i];
+          const int depth = u.kind == MIC_ENC_SPATIAL ? bit_len(u.max_value) : 16;
+          max_log = std::max(max_log, std::min(16, std::max(13, depth + 1)));
+          any_rans |= u.rans != 0;
+        }
         launch_enc_ans(du, (const int*)e->d_list.p + off, (int)lists[g].size(), NS[g], (const uint16_t*)e->d_S.p, (const uint16_t*)e->d_tab.p,
-                       (const uint2*)e->d_tt.p, (uint32_t*)e->d_T.p, e->sm_count, st);
+                       (const uint2*)e->d_tt.p, (uint32_t*)e->d_T.p, e->sm_count, st, max_log, any_rans);
         e->launches++;
       }
       off += lists[g].size();

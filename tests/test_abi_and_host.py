@@ -205,3 +205,18 @@ def test_partition_twin_matches_python(tmp_path):
             want = shard.partition_by_bytes([int(x) for x in sizes], parts)
             got = [(int(cuts[i]), int(cuts[i + 1])) for i in range(parts)]
             assert got == want, (sizes[:8], parts, got, want)
+
+
+def test_integration_doc_names_only_exported_symbols():
+    """INTEGRATION.md shows the cgo binding a maintainer adds: every `micgpu_*` / `mic_*compress*` name it mentions must be
+    declared in include/micgpu.h (and therefore exported: test_every_declared_symbol_is_exported)."""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "micgpu.h")).read()
+    declared = set(re.findall(r"\b(micgpu_[a-z0-9_]+|mic_(?:de)?compress_[a-z_]+)\s*\(", hdr))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    used = set(re.findall(r"\b(micgpu_[a-z0-9_]+)\b", doc))
+    # families written with braces or wildcards in the prose (micgpu_wsi_plan_*, micgpu_pica_{de,}compress, ...) and plain words
+    skip = {n for n in used if n.endswith("_") or n in ("micgpu_h", "micgpu_go")}
+    missing = sorted(n for n in used - skip if n not in declared and not any(d.startswith(n) for d in declared))
+    assert not missing, missing
